@@ -1,0 +1,111 @@
+"""Parity of the tcgen05 GEMM family (vacnic_gemm) against fp32 torch.matmul on the same bf16 inputs.
+
+Covers the four operand-major combinations used by forward / dgrad / wgrad / attention, ragged
+M/N/K edges (TMA zero fill + predicated epilogue), every tile width, batched strided operands in
+the [B,S,H,hd] attention layout, and each epilogue option."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(dev)
+
+
+def _ref(a, b, a_mn, b_mn):
+    A = a.float().transpose(-1, -2) if a_mn else a.float()
+    B = b.float().transpose(-1, -2) if b_mn else b.float()
+    return A @ B.transpose(-1, -2)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (300, 200, 136), (16, 7680, 768), (80, 20, 80)])
+@pytest.mark.parametrize("tile_n", [0, 64, 128, 256])
+def test_gemm_majors_and_edges(cuda_device, a_mn, b_mn, M, N, K, tile_n):
+    from vacnic_b200 import kernels as k
+    # MN-major operands need their contiguous (M or N) extent to be a multiple of 8 for TMA strides
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("TMA row pitch must be a multiple of 16 bytes")
+    a = _mk((K, M) if a_mn else (M, K), cuda_device, seed=1)
+    b = _mk((K, N) if b_mn else (N, K), cuda_device, seed=2)
+    out = k.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, tile_n=tile_n)
+    torch.cuda.synchronize()
+    ref = _ref(a, b, a_mn, b_mn)
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+def test_gemm_large_k_and_bf16_out(cuda_device):
+    from vacnic_b200 import kernels as k
+    a = _mk((1024, 4096), cuda_device, seed=3)
+    b = _mk((1024, 4096), cuda_device, seed=4)
+    out = k.gemm(a, b)
+    torch.cuda.synchronize()
+    ref = _ref(a, b, False, False)
+    rel = ((out.float() - ref).abs().max() / ref.abs().max()).item()
+    assert out.dtype == torch.bfloat16 and rel < 1e-2, rel
+
+
+def test_gemm_epilogues(cuda_device):
+    from vacnic_b200 import kernels as k
+    M, N, K = 200, 328, 192
+    a = _mk((M, K), cuda_device, 0.2, seed=5)
+    b = _mk((N, K), cuda_device, 0.2, seed=6)
+    bias = torch.randn(N, device=cuda_device)
+    z_ref = (_ref(a, b, False, False) + bias) * 0.5
+    # bias + alpha + gelu with pre-activation side output
+    z = torch.empty(M, N, dtype=torch.bfloat16, device=cuda_device)
+    y = k.gemm(a, b, bias=bias, alpha=0.5, act=k.ACT_GELU, aux_out=z, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert (z.float() - z_ref).abs().max().item() < 2e-2
+    assert (y - torch.nn.functional.gelu(z_ref)).abs().max().item() < 5e-3
+    # tanh
+    y = k.gemm(a, b, bias=bias, act=k.ACT_TANH, out_dtype=torch.float32)
+    assert (y - torch.tanh(_ref(a, b, False, False) + bias)).abs().max().item() < 5e-3
+    # activation gradient epilogues: out = (A B^T) * act'(aux)
+    zz = _mk((M, N), cuda_device, seed=7)
+    y = k.gemm(a, b, aux_in=zz, dact=k.ACT_GELU, out_dtype=torch.float32)
+    zf = zz.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).sum().backward()
+    assert (y - _ref(a, b, False, False) * zf.grad).abs().max().item() < 5e-3
+    hh = torch.tanh(zz.float()).to(torch.bfloat16)
+    y = k.gemm(a, b, aux_in=hh, dact=k.ACT_TANH, out_dtype=torch.float32)
+    assert (y - _ref(a, b, False, False) * (1 - hh.float() ** 2)).abs().max().item() < 5e-3
+    # accumulate into fp32 (wgrad) and bf16
+    acc = torch.randn(M, N, device=cuda_device)
+    want = acc + _ref(a, b, False, False)
+    k.gemm(a, b, out=acc, accumulate=True)
+    assert (acc - want).abs().max().item() < 5e-3
+
+
+def test_gemm_attention_layouts(cuda_device):
+    """QK^T, PV and the wgrad-like dV = P^T dO on [B,S,H,hd] strided views, two batch dims."""
+    from vacnic_b200 import kernels as k
+    B, H, Sq, Sk, hd = 3, 4, 200, 136, 64
+    qkv = _mk((B, Sq, 3 * H * hd), cuda_device, 0.5, seed=8)
+    kv = _mk((B, Sk, 2 * H * hd), cuda_device, 0.5, seed=9)
+    q = qkv[..., : H * hd].view(B, Sq, H, hd).permute(0, 2, 1, 3)          # [B,H,Sq,hd] strided
+    kk = kv[..., : H * hd].view(B, Sk, H, hd).permute(0, 2, 1, 3)
+    v = kv[..., H * hd:].view(B, Sk, H, hd).permute(0, 2, 1, 3)
+    s = k.gemm(q, kk, out_dtype=torch.float32)                              # [B,H,Sq,Sk]
+    s_ref = q.float() @ kk.float().transpose(-1, -2)
+    assert (s - s_ref).abs().max().item() < 2e-3 * s_ref.abs().max().item()
+    p = torch.softmax(s_ref, -1).to(torch.bfloat16)
+    o = torch.empty(B, Sq, H, hd, dtype=torch.bfloat16, device=cuda_device)
+    k.gemm(p, v, out=o.permute(0, 2, 1, 3), b_mn=True)                      # O = P V, V is [Sk,hd]
+    o_ref = (p.float() @ v.float()).permute(0, 2, 1, 3)
+    assert (o.float() - o_ref).abs().max().item() < 1e-2
+    do = _mk((B, Sq, H, hd), cuda_device, seed=10).permute(0, 2, 1, 3)
+    dv = k.gemm(p, do, a_mn=True, b_mn=True, out_dtype=torch.float32)        # dV = P^T dO  [B,H,Sk,hd]
+    dv_ref = p.float().transpose(-1, -2) @ do.float()
+    assert (dv - dv_ref).abs().max().item() < 2e-3 * dv_ref.abs().max().item()
+
+
+def test_gemm_rejects_cpu_tensors():
+    from vacnic_b200 import kernels as k
+    from vacnic_b200.lib import VacnicError
+    a = torch.zeros(8, 8, dtype=torch.bfloat16)
+    with pytest.raises(VacnicError):
+        k.gemm(a, a)

@@ -1,0 +1,2 @@
+"""vacnic_b200 — B200-native (sm_100a) implementation of the VACNIC multimodal-BART hot path."""
+__version__ = "0.1.0"

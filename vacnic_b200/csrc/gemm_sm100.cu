@@ -1,0 +1,484 @@
+// Batched bf16 GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma (cta_group::1, M=128, N=BN, K=16 per instruction) with fp32 accumulators in TMEM
+// (double buffered) -> tcgen05.ld epilogue (bias / alpha / GELU / tanh / activation-gradient /
+// accumulate) -> global memory.  Persistent: one CTA per SM walks a static tile list.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).
+//
+// This one kernel family serves every dense contraction on the VACNIC hot path (see
+// include/vacnic_b200.h for the reference call sites): forward linears (A K-major, B K-major),
+// dgrad (B MN-major), wgrad (A and B MN-major), QK^T, PV and their gradients (batched, strided).
+#include <cuda.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+struct GemmArgs {
+  int M, N, K;
+  int batch0, batch1;
+  int num_m, num_n;
+  long long total_tiles;
+  void* c;
+  long long ldc, c_sb0, c_sb1;
+  const float* bias;
+  void* aux_out;
+  const void* aux_in;
+  float alpha;
+  int c_dtype, act, dact, accumulate;
+  int vec_ok;  // 16-byte vector access allowed on C / aux rows
+};
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kThreads = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : 2 * BN;  // 128 / 256 / 512
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == VACNIC_ACT_GELU) return gelu_erf(v);
+  if (act == VACNIC_ACT_TANH) return tanhf(v);
+  return v;
+}
+__device__ __forceinline__ float apply_dact(float aux, int dact) {
+  if (dact == VACNIC_ACT_GELU) return gelu_erf_grad(aux);
+  if (dact == VACNIC_ACT_TANH) return 1.0f - aux * aux;
+  return 1.0f;
+}
+
+// Epilogue for 32 consecutive columns of one output row held in registers.
+__device__ __forceinline__ void epilogue_row_chunk(const GemmArgs& g, float (&v)[32],
+                                                   long long row_off, int n0) {
+  const int nvalid = min(32, g.N - n0);
+  if (g.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) v[j] += __ldg(g.bias + n0 + j);
+  }
+  if (g.alpha != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
+  }
+  const bool full = (nvalid == 32) && g.vec_ok;
+  const long long off = row_off + n0;
+  if (g.aux_out != nullptr) {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(g.aux_out) + off;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+        u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+        u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+        u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+        reinterpret_cast<uint4*>(p)[q] = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) p[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+  if (g.act != VACNIC_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
+  }
+  if (g.dact != VACNIC_ACT_NONE) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(g.aux_in) + off;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + q);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[8 * q + 0] *= apply_dact(f.x, g.dact); v[8 * q + 1] *= apply_dact(f.y, g.dact);
+        f = unpack_bf16x2(u.y); v[8 * q + 2] *= apply_dact(f.x, g.dact); v[8 * q + 3] *= apply_dact(f.y, g.dact);
+        f = unpack_bf16x2(u.z); v[8 * q + 4] *= apply_dact(f.x, g.dact); v[8 * q + 5] *= apply_dact(f.y, g.dact);
+        f = unpack_bf16x2(u.w); v[8 * q + 6] *= apply_dact(f.x, g.dact); v[8 * q + 7] *= apply_dact(f.y, g.dact);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] *= apply_dact(__bfloat162float(p[j]), g.dact);
+    }
+  }
+  if (g.c_dtype == VACNIC_DT_F32) {
+    float* p = reinterpret_cast<float*>(g.c) + off;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        if (g.accumulate) {
+          const float4 c = reinterpret_cast<const float4*>(p)[q];
+          o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+        }
+        reinterpret_cast<float4*>(p)[q] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) p[j] = g.accumulate ? p[j] + v[j] : v[j];
+    }
+  } else {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(g.c) + off;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (g.accumulate) {
+          const uint4 c = reinterpret_cast<const uint4*>(p)[q];
+          float2 f;
+          f = unpack_bf16x2(c.x); v[8 * q + 0] += f.x; v[8 * q + 1] += f.y;
+          f = unpack_bf16x2(c.y); v[8 * q + 2] += f.x; v[8 * q + 3] += f.y;
+          f = unpack_bf16x2(c.z); v[8 * q + 4] += f.x; v[8 * q + 5] += f.y;
+          f = unpack_bf16x2(c.w); v[8 * q + 6] += f.x; v[8 * q + 7] += f.y;
+        }
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+        u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+        u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+        u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+        reinterpret_cast<uint4*>(p)[q] = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid)
+          p[j] = __float2bfloat16_rn(g.accumulate ? __bfloat162float(p[j]) + v[j] : v[j]);
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned stage buffers.
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k = (g.K + kBK - 1) / kBK;
+  const long long tiles_per_batch = static_cast<long long>(g.num_m) * g.num_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+        const int batch = static_cast<int>(t / tiles_per_batch);
+        const int r = static_cast<int>(t % tiles_per_batch);
+        const int m0 = (r % g.num_m) * kBM;
+        const int n0 = (r / g.num_m) * BN;
+        const int b0 = batch % g.batch0;
+        const int b1 = batch / g.batch0;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int k0 = kb * kBK;
+          if constexpr (!A_MN) {
+            tma_load_4d(sa, &tmA, &full_bar[stage], k0, m0, b0, b1);
+          } else {
+#pragma unroll
+            for (int c = 0; c < kBM / 64; ++c)
+              tma_load_4d(sa + c * (64 * kBK * 2), &tmA, &full_bar[stage], m0 + c * 64, k0, b0, b1);
+          }
+          if constexpr (!B_MN) {
+            tma_load_4d(sb, &tmB, &full_bar[stage], k0, n0, b0, b1);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_4d(sb + c * (64 * kBK * 2), &tmB, &full_bar[stage], n0 + c * 64, k0, b0, b1);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // K-major: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major: 64-element chunks along
+      // M/N are kBK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
+      constexpr uint32_t kLboA = A_MN ? kBK * 128 : 16, kLboB = B_MN ? kBK * 128 : 16;
+      constexpr uint32_t kStepA = A_MN ? 16 * 128 : 32, kStepB = B_MN ? 16 * 128 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++it) {
+        const uint32_t as = it & 1u;
+        const uint32_t aphase = (it >> 1) & 1u;
+        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * kStepA, kLboA, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * kStepB, kLboB, 1024);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 2..5
+    const int quad = warp & 3;
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++it) {
+      const int batch = static_cast<int>(t / tiles_per_batch);
+      const int r = static_cast<int>(t % tiles_per_batch);
+      const int m0 = (r % g.num_m) * kBM;
+      const int n0 = (r / g.num_m) * BN;
+      const int b0 = batch % g.batch0;
+      const int b1 = batch / g.batch0;
+      const uint32_t as = it & 1u;
+      const uint32_t aphase = (it >> 1) & 1u;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const long long row_off = static_cast<long long>(b0) * g.c_sb0 +
+                                static_cast<long long>(b1) * g.c_sb1 +
+                                static_cast<long long>(row) * g.ldc;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= g.N) break;
+        uint32_t r32[32];
+        tmem_ld_32x32(taddr + c * 32, r32);
+        tmem_ld_wait();
+        if (row < g.M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r32[j]);
+          epilogue_row_chunk(g, v, row_off, n0 + c * 32);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Tensor map for one operand.  K-major: dims (K, rows, b0, b1), box (64, box_rows).
+// MN-major: dims (rows, K, b0, b1), box (64, 64).
+static int make_operand_map(CUtensorMap* tm, const void* base, bool mn_major, int rows, int K,
+                            long long ld, int batch0, long long sb0, int batch1, long long sb1,
+                            int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return fail(VACNIC_EDEVICE, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (!mn_major) {
+    dims[0] = static_cast<cuuint64_t>(K);
+    dims[1] = static_cast<cuuint64_t>(rows);
+    box[0] = 64;
+    box[1] = static_cast<cuuint32_t>(box_rows);
+  } else {
+    dims[0] = static_cast<cuuint64_t>(rows);
+    dims[1] = static_cast<cuuint64_t>(K);
+    box[0] = 64;
+    box[1] = 64;
+  }
+  dims[2] = static_cast<cuuint64_t>(batch0);
+  dims[3] = static_cast<cuuint64_t>(batch1);
+  box[2] = 1;
+  box[3] = 1;
+  strides[0] = static_cast<cuuint64_t>(ld) * 2;
+  strides[1] = static_cast<cuuint64_t>(batch0 > 1 ? sb0 : ld) * 2;
+  strides[2] = static_cast<cuuint64_t>(batch1 > 1 ? sb1 : ld) * 2;
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] % 16 != 0 || strides[i] == 0)
+      return fail(VACNIC_EINVAL, "gemm: operand stride %d (%llu bytes) not a multiple of 16", i,
+                  static_cast<unsigned long long>(strides[i]));
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VACNIC_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return VACNIC_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_sm100_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return fail(VACNIC_ECUDA, "gemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
+                  cudaGetErrorString(e));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return fail(VACNIC_EDEVICE, "gemm: no CUDA device");
+  const int grid = static_cast<int>(g.total_tiles < sms ? g.total_tiles : sms);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, g);
+  count_launch();
+  return check_last("gemm launch");
+}
+
+template <int BN>
+static int dispatch_major(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, bool a_mn,
+                          bool b_mn, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, g, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, g, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tmA, tmB, g, stream);
+  return launch_gemm<BN, true, true>(tmA, tmB, g, stream);
+}
+
+static int choose_tile_n(const vacnic_gemm_desc* d, int sms) {
+  // Prefer the widest tile that still yields at least one full wave of CTAs; tiny N gets 64.
+  const long long batch = static_cast<long long>(d->batch0) * d->batch1;
+  const long long num_m = (d->M + kBM - 1) / kBM;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (d->N <= bn / 2 && bn > 64) continue;
+    const long long tiles = batch * num_m * ((d->N + bn - 1) / bn);
+    if (tiles >= sms || bn == 64) return bn;
+  }
+  return 64;
+}
+
+}  // namespace vb
+
+extern "C" int vacnic_gemm(const vacnic_gemm_desc* d, void* stream_v) {
+  using namespace vb;
+  if (d == nullptr) return fail(VACNIC_EINVAL, "gemm: null descriptor");
+  VB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "gemm: M,N,K must be positive (%d,%d,%d)", d->M, d->N, d->K);
+  VB_REQUIRE(d->batch0 > 0 && d->batch1 > 0, "gemm: batch dims must be positive");
+  VB_REQUIRE(d->a && d->b && d->c, "gemm: null operand pointer");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->b) & 15) == 0,
+             "gemm: operands must be 16-byte aligned");
+  VB_REQUIRE(d->c_dtype == VACNIC_DT_BF16 || d->c_dtype == VACNIC_DT_F32, "gemm: bad c_dtype");
+  VB_REQUIRE(d->dact == VACNIC_ACT_NONE || d->aux_in != nullptr, "gemm: dact needs aux_in");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const int sms = sm_count();
+  if (sms <= 0) return fail(VACNIC_EDEVICE, "gemm: no CUDA device visible");
+
+  int bn = d->tile_n;
+  if (bn == 0) bn = choose_tile_n(d, sms);
+  VB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: tile_n must be 0/64/128/256");
+
+  GemmArgs g;
+  g.M = d->M; g.N = d->N; g.K = d->K;
+  g.batch0 = d->batch0; g.batch1 = d->batch1;
+  g.num_m = (d->M + kBM - 1) / kBM;
+  g.num_n = (d->N + bn - 1) / bn;
+  g.total_tiles = static_cast<long long>(d->batch0) * d->batch1 * g.num_m * g.num_n;
+  g.c = d->c; g.ldc = d->ldc; g.c_sb0 = d->c_sb0; g.c_sb1 = d->c_sb1;
+  g.bias = d->bias; g.aux_out = d->aux_out; g.aux_in = d->aux_in;
+  g.alpha = d->alpha; g.c_dtype = d->c_dtype; g.act = d->act; g.dact = d->dact;
+  g.accumulate = d->accumulate;
+  // Vector (16 B) row access needs every row start of C / aux to be 16-byte aligned.
+  const int c_es = d->c_dtype == VACNIC_DT_F32 ? 4 : 2;
+  auto aligned = [&](const void* p, int es) {
+    return p == nullptr ||
+           ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (d->ldc * es) % 16 == 0 &&
+            (d->c_sb0 * es) % 16 == 0 && (d->c_sb1 * es) % 16 == 0);
+  };
+  g.vec_ok = aligned(d->c, c_es) && aligned(d->aux_out, 2) && aligned(d->aux_in, 2) ? 1 : 0;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_operand_map(&tmA, d->a, d->a_mn_major != 0, d->M, d->K, d->lda, d->batch0, d->a_sb0,
+                            d->batch1, d->a_sb1, kBM);
+  if (rc != VACNIC_OK) return rc;
+  rc = make_operand_map(&tmB, d->b, d->b_mn_major != 0, d->N, d->K, d->ldb, d->batch0, d->b_sb0,
+                        d->batch1, d->b_sb1, bn);
+  if (rc != VACNIC_OK) return rc;
+
+  const bool a_mn = d->a_mn_major != 0, b_mn = d->b_mn_major != 0;
+  if (bn == 256) return dispatch_major<256>(tmA, tmB, g, a_mn, b_mn, stream);
+  if (bn == 128) return dispatch_major<128>(tmA, tmB, g, a_mn, b_mn, stream);
+  return dispatch_major<64>(tmA, tmB, g, a_mn, b_mn, stream);
+}
