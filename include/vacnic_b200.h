@@ -88,6 +88,91 @@ typedef struct vacnic_gemm_desc {
 
 int vacnic_gemm(const vacnic_gemm_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm family (bf16 activations, fp32 parameters / statistics, eps = 1e-5: nn.LayerNorm
+ * defaults at MFULL:577,583,...).  d must be a multiple of 256 (768 / 1024).
+ * Dropout (config.dropout, MFULL:705,721,742 ...) is a counter-based Bernoulli mask keyed by
+ * (*rng_state, salt, element index); the backward call regenerates it from the same triple.
+ * ------------------------------------------------------------------------------------------ */
+/* y = LN(res + dropout(x)).  Output row r lands at y + (r / rows_per_group) * y_group_stride +
+ * (r % rows_per_group) * d, so a result can be written straight into a slice of the prefix/NER
+ * concat buffer (torch.cat at MFULL:691).  rows_per_group = 0 means contiguous output. */
+int vacnic_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
+                             float* mean, float* rstd, int64_t rows, int32_t d, int64_t rows_per_group,
+                             int64_t y_group_stride, float eps, float p_drop, const uint64_t* rng_state,
+                             uint32_t salt, void* stream);
+/* Gradients of the above: dsum = d(res + dropout(x)) (written or accumulated), dx = dropout-masked
+ * dsum (skipped when dx == dsum or null), dgamma/dbeta/dbias are accumulated atomically (fp32);
+ * dbias is the bias gradient of the linear layer that produced x (column sums of dx). */
+int vacnic_add_layernorm_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* mean,
+                             const float* rstd, void* dsum, void* dx, float* dgamma, float* dbeta, float* dbias,
+                             int64_t rows, int32_t d, int64_t rows_per_group, int64_t dy_group_stride, float p_drop,
+                             const uint64_t* rng_state, uint32_t salt, int32_t accumulate_dsum, void* stream);
+/* y = dropout(LN(tok[ids] + pos[(r % seq_len) + pos_offset])): MFULL:1243-1249 (article),
+ * 1254-1260 (names, embed_tokens_ner), 1555-1563 (decoder, pos_offset = 2 + cached length). */
+int vacnic_embed_ln_fwd(const int64_t* ids, const void* tok, const void* pos, const float* gamma, const float* beta,
+                        void* y, float* mean, float* rstd, int64_t rows, int32_t seq_len, int32_t pos_offset,
+                        int32_t d, float eps, float p_drop, const uint64_t* rng_state, uint32_t salt, void* stream);
+/* Scatter-add gradients into the fp32 embedding tables; rows with ids == pad_id get no token
+ * gradient (nn.Embedding padding_idx, MFULL:1115,1150). */
+int vacnic_embed_ln_bwd(const void* dy, const int64_t* ids, const void* tok, const void* pos, const float* gamma,
+                        const float* mean, const float* rstd, float* dtok, float* dpos, float* dgamma, float* dbeta,
+                        int64_t rows, int32_t seq_len, int32_t pos_offset, int32_t d, int32_t pad_id, float p_drop,
+                        const uint64_t* rng_state, uint32_t salt, void* stream);
+/* get_embedding_ner (TRAIN:112-133): out[span] = mean_t LN(tok[ids[span,t]] + pos[t + 2]), fp32. */
+int vacnic_names_embed(const int64_t* ids, const void* tok, const void* pos, const float* gamma, const float* beta,
+                       float* out, int64_t spans, int32_t len, int32_t d, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Masked softmax for the unfused attention path (MFULL:509-548).  scores fp32 / probs bf16,
+ * both [B, H, Sq, ld] with ld >= Sk (pad columns are written as zeros).  key_mask: uint8 [B, Sk],
+ * 1 = attend (the reference's attention_mask, _expand_mask MFULL:387-398) or null; causal != 0
+ * masks key j > query i + past (_make_causal_mask MFULL:373-385).
+ * ------------------------------------------------------------------------------------------ */
+int vacnic_softmax_fwd(const float* scores, void* probs, const uint8_t* key_mask, int32_t B, int32_t H, int32_t Sq,
+                       int32_t Sk, int32_t ld, int32_t causal, int32_t past, void* stream);
+/* dscores = probs * (dprobs - rowsum(probs * dprobs)), bf16 out. */
+int vacnic_softmax_bwd(const void* probs, const float* dprobs, void* dscores, int64_t rows, int32_t Sk, int32_t ld,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Elementwise / reduction helpers.
+ * ------------------------------------------------------------------------------------------ */
+int vacnic_colsum(const void* x, float* out, int64_t rows, int32_t n, int64_t ld, void* stream); /* out[c] += sum_r x[r,c] : nn.Linear bias gradients */
+int vacnic_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream); /* out = a + b (+ c) */
+/* Fused AdamW over a flat parameter buffer (TRAIN:91-107,371-373).  hyper (device, fp32[8]) =
+ * {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}; also refreshes the bf16
+ * compute shadow p16 (may be null). */
+int vacnic_adamw(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const float* hyper, void* stream);
+int vacnic_rng_advance(uint64_t* state, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Losses (script-level code in the reference, TRAIN:284-363).
+ * ------------------------------------------------------------------------------------------ */
+/* CrossEntropyLoss(ignore_index) over fp32 logits [rows, ld] (TRAIN:287,816).  out[0] = mean loss,
+ * out[1] = number of counted rows; lse / row_loss are [rows] scratch kept for the backward. */
+int vacnic_ce_fwd(const float* logits, const int64_t* targets, float* lse, float* row_loss, float* out, int64_t rows,
+                  int32_t V, int64_t ld, int64_t ignore_index, void* stream);
+/* dlogits (bf16 [rows, ld]) = (softmax - onehot) * coef * gscale[0] / out[1]. */
+int vacnic_ce_bwd(const float* logits, const float* lse, const int64_t* targets, const float* stats,
+                  const float* gscale, float coef, void* dlogits, int64_t rows, int32_t V, int64_t ld,
+                  int64_t ignore_index, void* stream);
+/* CoLaM (TRAIN:292-309): masked mean pool over non-pad label positions (nan -> 1.0), L2 normalise,
+ * diagonal cosine, HingeEmbeddingLoss(margin) with target -1.  stats is fp32 [B, 8]. */
+int vacnic_colam_fwd(const void* h, const void* h_guide, const int64_t* tgt_ids, float* pooled_a, float* pooled_b,
+                     float* stats, float* loss, int32_t B, int32_t T, int32_t d, int64_t pad_id, float margin,
+                     void* stream);
+int vacnic_colam_bwd(const float* pooled_a, const float* pooled_b, const float* stats, const int64_t* tgt_ids,
+                     const float* gscale, float coef, void* dh, int32_t B, int32_t T, int32_t d, int64_t pad_id,
+                     int32_t accumulate, void* stream);
+/* SECLA BatchSoftmax (TRAIN:631-660): names fp32 [B,N,d] (no grad), face bf16 [B,F,d]. */
+int64_t vacnic_secla_workspace_bytes(int32_t B, int32_t N, int32_t F);
+int vacnic_secla_fwd(const float* names, const void* face, float* workspace, float* loss, int32_t B, int32_t N,
+                     int32_t F, int32_t d, void* stream);
+int vacnic_secla_bwd(const float* workspace, const float* names, const float* gscale, float coef, void* dface,
+                     int32_t B, int32_t N, int32_t F, int32_t d, int32_t accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

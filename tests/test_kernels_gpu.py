@@ -1,0 +1,246 @@
+"""Parity of the bandwidth-class kernels (LayerNorm family, embeddings, softmax, reductions, AdamW,
+CE / CoLaM / SECLA) against fp32 torch on the same inputs.  bf16 outputs: tolerance = bf16 rounding of
+the result (2^-8 relative) plus accumulated input rounding, stated per assert."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model as OM
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(shape, dev, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(dev)
+
+
+@pytest.mark.parametrize("d", [768, 1024])
+@pytest.mark.parametrize("rows", [1, 37, 4096])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_add_layernorm_fwd_bwd(cuda_device, d, rows, with_res):
+    from vacnic_b200 import kernels as k
+    x = rnd((rows, d), cuda_device, 1.0, 1)
+    res = rnd((rows, d), cuda_device, 1.0, 2) if with_res else None
+    gamma = 1 + 0.1 * rnd((d,), cuda_device, 1.0, 3, torch.float32)
+    beta = 0.1 * rnd((d,), cuda_device, 1.0, 4, torch.float32)
+    y, mean, rstd = k.add_layernorm_fwd(x, res, gamma, beta)
+    xs = (x.float() + (res.float() if with_res else 0)).requires_grad_(True)
+    gref, bref = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xs, (d,), gref, bref, 1e-5)
+    assert (y.float() - yr).abs().max().item() <= 2 ** -7 * max(1.0, yr.abs().max().item())
+    dy = rnd((rows, d), cuda_device, 1.0, 5)
+    yr.backward(dy.float())
+    dgamma = torch.zeros(d, device=cuda_device)
+    dbeta = torch.zeros(d, device=cuda_device)
+    dbias = torch.zeros(d, device=cuda_device)
+    dsum, dx = k.add_layernorm_bwd(dy, x, res, gamma, mean, rstd, dgamma, dbeta, dbias)
+    torch.cuda.synchronize()
+    assert dx is dsum
+    assert (dsum.float() - xs.grad).abs().max().item() <= 2 ** -6 * max(1.0, xs.grad.abs().max().item())
+    tol = 2e-2 * max(1.0, rows ** 0.5)
+    assert (dgamma - gref.grad).abs().max().item() <= tol
+    assert (dbeta - bref.grad).abs().max().item() <= tol
+    assert (dbias - dsum.float().sum(0)).abs().max().item() <= tol
+
+
+def test_add_layernorm_strided_output_and_dropout(cuda_device):
+    from vacnic_b200 import kernels as k
+    B, P, G, d = 3, 5, 7, 1024
+    x = rnd((B * P, d), cuda_device, 1.0, 1)
+    res = rnd((B * P, d), cuda_device, 1.0, 2)
+    gamma = torch.ones(d, device=cuda_device)
+    beta = torch.zeros(d, device=cuda_device)
+    cat = torch.zeros(B, P + G, d, dtype=torch.bfloat16, device=cuda_device)
+    y, mean, rstd = k.add_layernorm_fwd(x, res, gamma, beta, out=cat, rows_per_group=P, group_stride=(P + G) * d)
+    ref = F.layer_norm(x.float() + res.float(), (d,))
+    assert (cat[:, :P].float().reshape(B * P, d) - ref).abs().max().item() < 2 ** -6
+    assert cat[:, P:].abs().max().item() == 0
+    # backward reading dy out of the same strided slice
+    dcat = rnd((B, P + G, d), cuda_device, 1.0, 6)
+    dgamma = torch.zeros(d, device=cuda_device); dbeta = torch.zeros(d, device=cuda_device)
+    dsum, _ = k.add_layernorm_bwd(dcat, x, res, gamma, mean, rstd, dgamma, dbeta, rows_per_group=P, group_stride=(P + G) * d)
+    xs = (x.float() + res.float()).requires_grad_(True)
+    F.layer_norm(xs, (d,)).backward(dcat[:, :P].float().reshape(B * P, d))
+    assert (dsum.float() - xs.grad).abs().max().item() <= 2 ** -5
+    # dropout: mask is reproducible between forward and backward and has the right keep rate
+    rng = k.Rng(cuda_device, seed=3)
+    p = 0.1
+    big = rnd((4096, d), cuda_device, 1.0, 7)
+    zero_res = torch.zeros_like(big)
+    # LN is scale invariant per row, so recover the mask from a second call with p = 0 instead:
+    y1, m1, r1 = k.add_layernorm_fwd(big, zero_res, gamma, beta, p_drop=p, rng=rng, salt=11)
+    y2, _, _ = k.add_layernorm_fwd(big, zero_res, gamma, beta, p_drop=p, rng=rng, salt=11)
+    assert torch.equal(y1, y2)
+    y3, _, _ = k.add_layernorm_fwd(big, zero_res, gamma, beta, p_drop=p, rng=rng, salt=12)
+    assert not torch.equal(y1, y3)
+    dy = torch.ones_like(big)
+    dg = torch.zeros(d, device=cuda_device); db = torch.zeros(d, device=cuda_device)
+    dsum, dx = k.add_layernorm_bwd(dy * 0 + rnd((4096, d), cuda_device, 1.0, 8), big, zero_res, gamma, m1, r1, dg, db,
+                                   want_dx=True, p_drop=p, rng=rng, salt=11)
+    dropped = (dx == 0) & (dsum != 0)
+    rate = dropped.float().mean().item()
+    assert abs(rate - p) < 0.01, rate
+    kept = ~dropped
+    assert (dx[kept].float() - dsum[kept].float() / (1 - p)).abs().max().item() <= 2 ** -6 * dsum.abs().max().item()
+
+
+@pytest.mark.parametrize("d", [768, 1024])
+def test_embed_ln_fwd_bwd(cuda_device, d):
+    from vacnic_b200 import kernels as k
+    V, S, B = 300, 24, 5
+    tok32 = rnd((V, d), cuda_device, 0.02, 1, torch.float32)
+    pos32 = rnd((S + 10, d), cuda_device, 0.02, 2, torch.float32)
+    tok, pos = tok32.to(torch.bfloat16), pos32.to(torch.bfloat16)
+    gamma = 1 + 0.1 * rnd((d,), cuda_device, 1.0, 3, torch.float32)
+    beta = 0.1 * rnd((d,), cuda_device, 1.0, 4, torch.float32)
+    ids = torch.randint(0, V, (B, S), generator=torch.Generator().manual_seed(5)).to(cuda_device)
+    ids[:, -3:] = 1
+    y, mean, rstd = k.embed_ln_fwd(ids, tok, pos, gamma, beta, pos_offset=5)
+    tr, pr = tok.float().requires_grad_(True), pos.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    h = F.embedding(ids, tr, padding_idx=1) + pr[torch.arange(S, device=cuda_device) + 5]
+    yr = F.layer_norm(h, (d,), gr, br, 1e-5)
+    assert (y.float() - yr).abs().max().item() <= 2 ** -6 * max(1.0, yr.abs().max().item())
+    dy = rnd((B, S, d), cuda_device, 1.0, 6)
+    yr.backward(dy.float())
+    dtok = torch.zeros(V, d, device=cuda_device); dpos = torch.zeros(S + 10, d, device=cuda_device)
+    dg = torch.zeros(d, device=cuda_device); db = torch.zeros(d, device=cuda_device)
+    k.embed_ln_bwd(dy, ids, tok, pos, gamma, mean, rstd, dtok, dpos, dg, db, pos_offset=5, pad_id=1)
+    torch.cuda.synchronize()
+    for got, want in ((dtok, tr.grad), (dpos, pr.grad), (dg, gr.grad), (db, br.grad)):
+        assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    assert dtok[1].abs().max().item() == 0  # padding_idx row receives no gradient
+
+
+def test_names_embed(cuda_device):
+    from vacnic_b200 import kernels as k
+    d, V = 768, 400
+    tok = rnd((V, d), cuda_device, 0.02, 1); pos = rnd((40, d), cuda_device, 0.02, 2)
+    gamma = 1 + 0.1 * rnd((d,), cuda_device, 1.0, 3, torch.float32)
+    beta = 0.1 * rnd((d,), cuda_device, 1.0, 4, torch.float32)
+    ids = torch.randint(0, V, (3, 5, 8), generator=torch.Generator().manual_seed(5)).to(cuda_device)
+    out = k.names_embed(ids, tok, pos, gamma, beta)
+    sd = {"e.embed_tokens_ner.weight": tok.float(), "e.embed_positions_ner.weight": pos.float(),
+          "e.layernorm_embedding_ner.weight": gamma, "e.layernorm_embedding_ner.bias": beta}
+    ref = OM.names_embedding(sd, ids, prefix="e.")
+    assert (out - ref).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("Sq,Sk,causal,masked", [(80, 84, False, True), (64, 64, True, False), (33, 30, False, False),
+                                                 (128, 1024, False, True), (7, 12, True, True)])
+def test_softmax_fwd_bwd(cuda_device, Sq, Sk, causal, masked):
+    from vacnic_b200 import kernels as k
+    B, H = 2, 3
+    ld = (Sk + 7) // 8 * 8
+    s = torch.zeros(B, H, Sq, ld, device=cuda_device)
+    s[..., :Sk] = rnd((B, H, Sq, Sk), cuda_device, 2.0, 1, torch.float32)
+    km = None
+    add = torch.zeros(B, 1, Sq, Sk, device=cuda_device)
+    if masked:
+        km = torch.ones(B, Sk, dtype=torch.uint8, device=cuda_device)
+        km[0, Sk // 2:] = 0
+        km[1, -1] = 0
+        add = add + OM.expand_mask(km.long(), torch.float32, Sq)
+    if causal:
+        past = Sk - Sq if Sk >= Sq else 0
+        add = add + OM.causal_mask(Sq, torch.float32, cuda_device, past)[..., :Sk]
+    else:
+        past = 0
+    p = k.softmax_fwd(s, km, Sk, causal=causal, past=past)
+    sr = s[..., :Sk].clone().requires_grad_(True)
+    pr = torch.softmax(sr + add, dim=-1)
+    assert (p[..., :Sk].float() - pr).abs().max().item() <= 2 ** -8
+    assert p[..., Sk:].abs().max().item() == 0 if ld > Sk else True
+    dp = torch.zeros(B, H, Sq, ld, device=cuda_device)
+    dp[..., :Sk] = rnd((B, H, Sq, Sk), cuda_device, 1.0, 2, torch.float32)
+    p.float()[..., :Sk].detach()
+    # reference gradient evaluated at the bf16-rounded probabilities the kernel saw
+    pb = p[..., :Sk].float()
+    want = pb * (dp[..., :Sk] - (pb * dp[..., :Sk]).sum(-1, keepdim=True))
+    ds = k.softmax_bwd(p, dp, Sk)
+    assert (ds[..., :Sk].float() - want).abs().max().item() <= 2 ** -7 * max(1.0, want.abs().max().item())
+
+
+def test_colsum_cast_add_adamw(cuda_device):
+    from vacnic_b200 import kernels as k
+    x = rnd((1000, 4096 + 24), cuda_device, 1.0, 1)[:, :4096 + 3]  # ragged width, strided rows
+    out = torch.ones(4099, device=cuda_device)
+    k.colsum_into(x, out)
+    assert (out - 1 - x.float().sum(0)).abs().max().item() <= 1e-2
+    src = rnd((100003,), cuda_device, 1.0, 2, torch.float32)
+    dst = torch.empty(100003, dtype=torch.bfloat16, device=cuda_device)
+    k.cast_bf16(src, dst)
+    assert torch.equal(dst, src.to(torch.bfloat16))
+    a, b, c = (rnd((5000,), cuda_device, 1.0, s) for s in (3, 4, 5))
+    assert (k.add_bf16(a, b).float() - (a.float() + b.float())).abs().max().item() <= 2 ** -6
+    assert (k.add_bf16(a, b, c).float() - (a.float() + b.float() + c.float())).abs().max().item() <= 2 ** -5
+    # AdamW against torch.optim.AdamW over three steps
+    n = 10007
+    p0 = rnd((n,), cuda_device, 1.0, 6, torch.float32)
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([pt], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    p16 = torch.empty(n, dtype=torch.bfloat16, device=cuda_device)
+    for step in range(1, 4):
+        g = rnd((n,), cuda_device, 1.0, 10 + step, torch.float32)
+        pt.grad = g.clone()
+        opt.step()
+        hyper = torch.tensor([3e-3, 0.9, 0.999, 1e-8, 0.01, 1 - 0.9 ** step, 1 - 0.999 ** step, 1.0], device=cuda_device)
+        k.adamw(p, g, m, v, p16, hyper)
+    assert (p - pt.data).abs().max().item() <= 1e-5
+    assert torch.equal(p16, p.to(torch.bfloat16))
+
+
+def test_ce_fwd_bwd(cuda_device):
+    from vacnic_b200 import kernels as k
+    rows, V, ld = 50, 50267, 50272
+    buf = torch.zeros(rows, ld, device=cuda_device)
+    buf[:, :V] = rnd((rows, V), cuda_device, 3.0, 1, torch.float32)
+    tgt = torch.randint(0, V, (rows,), generator=torch.Generator().manual_seed(2)).to(cuda_device)
+    tgt[::7] = 1
+    out, lse, row_loss = k.ce_fwd(buf[:, :V], V, tgt, ignore_index=1)
+    lr = buf[:, :V].clone().requires_grad_(True)
+    ref = F.cross_entropy(lr, tgt, ignore_index=1)
+    assert abs(out[0].item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert out[1].item() == (tgt != 1).sum().item()
+    (ref * 0.5).backward()
+    dl = torch.empty(rows, ld, dtype=torch.bfloat16, device=cuda_device)
+    gs = torch.tensor([0.5], device=cuda_device)
+    k.ce_bwd(buf[:, :V], V, lse, tgt, out, gs, 1.0, dl, ignore_index=1)
+    assert (dl[:, :V].float() - lr.grad).abs().max().item() <= 2 ** -8 * lr.grad.abs().max().item() + 1e-9
+    assert dl[:, V:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("margin", [1.0, 0.3])
+def test_colam(cuda_device, margin):
+    from vacnic_b200 import kernels as k
+    B, T, d = 6, 20, 1024
+    h = rnd((B, T, d), cuda_device, 1.0, 1)
+    hg = (0.7 * h.float() + 0.7 * rnd((B, T, d), cuda_device, 1.0, 2).float()).to(torch.bfloat16)
+    tgt = torch.randint(3, 100, (B, T), generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    tgt[0, 5:] = 1
+    tgt[3, 12:] = 1
+    loss, pa, pb, stats = k.colam_fwd(h, hg, tgt, margin)
+    hr = h.float().requires_grad_(True)
+    ref = OM.colam_loss(hr, hg.float(), tgt, margin)
+    assert abs(loss.item() - ref.item()) <= 1e-5
+    (ref * 0.5).backward()
+    dh = torch.empty_like(h)
+    k.colam_bwd(pa, pb, stats, tgt, torch.tensor([1.0], device=cuda_device), 0.5, dh)
+    assert (dh.float() - hr.grad).abs().max().item() <= 2 ** -7 * hr.grad.abs().max().item() + 1e-9
+
+
+def test_secla(cuda_device):
+    from vacnic_b200 import kernels as k
+    B, N, Fc, d = 16, 8, 4, 1024
+    names = rnd((B, N, d), cuda_device, 0.5, 1, torch.float32)
+    face = rnd((B, Fc, d), cuda_device, 0.5, 2)
+    loss, ws = k.secla_fwd(names, face)
+    fr = face.float().requires_grad_(True)
+    ref = OM.secla_loss(fr, names)
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    ref.backward()
+    dface = torch.empty_like(face)
+    k.secla_bwd(ws, names, None, 1.0, dface)
+    assert (dface.float() - fr.grad).abs().max().item() <= 2 ** -7 * fr.grad.abs().max().item() + 1e-9

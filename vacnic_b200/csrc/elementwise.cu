@@ -1,0 +1,200 @@
+// Small HBM-bound helpers: bias gradients (column sums), fp32 -> bf16 shadow casts, the fused
+// AdamW update (TRAIN:91-107, 371-373: AdamW(lr, betas=(0.9,0.999), eps=1e-8, weight_decay) + linear
+// warm-up schedule folded into `lr`), and gradient-buffer utilities.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+// out[c] += sum_r x[r, c]; x bf16 [rows, ld]; grid = (col tiles of 256, row slabs)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int n, long long ld,
+              int rows_per_block) {
+  const int c0 = blockIdx.x * 256 + (threadIdx.x & 31) * 8;
+  const int wr = threadIdx.x >> 5;  // 8 warps walk rows
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool vec = (c0 + 8 <= n) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (long long r = r0 + wr; r < r1; r += 8) {
+    const __nv_bfloat16* p = x + r * ld + c0;
+    if (vec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+      float2 f;
+      f = unpack_bf16x2(u.x); acc[0] += f.x; acc[1] += f.y;
+      f = unpack_bf16x2(u.y); acc[2] += f.x; acc[3] += f.y;
+      f = unpack_bf16x2(u.z); acc[4] += f.x; acc[5] += f.y;
+      f = unpack_bf16x2(u.w); acc[6] += f.x; acc[7] += f.y;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (c0 + e < n) acc[e] += __bfloat162float(p[e]);
+    }
+  }
+  __shared__ float red[8][256];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[wr][(threadIdx.x & 31) * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][c];
+  if (blockIdx.x * 256 + c < n) atomicAdd(out + blockIdx.x * 256 + c, s);
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + i) + 1);
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+    u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(dst + i) = u;
+  } else {
+    for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16_rn(src[k]);
+  }
+}
+
+// hyper = {lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, grad_scale}
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             __nv_bfloat16* __restrict__ p16, long long n, const float* __restrict__ hyper) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5],
+              bc2 = hyper[6], gs = hyper[7];
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const long long i0 = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  if (i0 + 4 <= n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i0);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + i0));
+    float4 mm = *reinterpret_cast<float4*>(m + i0);
+    float4 vv = *reinterpret_cast<float4*>(v + i0);
+    float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = ga[k] * gs;
+      pa[k] *= 1.f - lr * wd;  // decoupled weight decay (torch.optim.AdamW)
+      ma[k] = b1 * ma[k] + (1.f - b1) * gr;
+      va[k] = b2 * va[k] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(va[k]) * inv_sqrt_bc2 + eps;
+      pa[k] -= step_size * ma[k] / denom;
+    }
+    *reinterpret_cast<float4*>(p + i0) = pp;
+    *reinterpret_cast<float4*>(m + i0) = mm;
+    *reinterpret_cast<float4*>(v + i0) = vv;
+    if (p16) {
+      uint2 u;
+      u.x = pack_bf16x2(pp.x, pp.y); u.y = pack_bf16x2(pp.z, pp.w);
+      *reinterpret_cast<uint2*>(p16 + i0) = u;
+    }
+  } else {
+    for (long long i = i0; i < n; ++i) {
+      const float gr = g[i] * gs;
+      float pv = p[i] * (1.f - lr * wd);
+      const float mv = b1 * m[i] + (1.f - b1) * gr;
+      const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+      pv -= step_size * mv / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+      p[i] = pv; m[i] = mv; v[i] = vv;
+      if (p16) p16[i] = __float2bfloat16_rn(pv);
+    }
+  }
+}
+
+// out = a + b (+ c) on bf16, fp32 math; gradient fan-in of the residual / state streams
+__global__ void __launch_bounds__(256)
+add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                const __nv_bfloat16* __restrict__ c, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const uint4 ua = *reinterpret_cast<const uint4*>(a + i);
+    const uint4 ub = *reinterpret_cast<const uint4*>(b + i);
+    uint4 uc = make_uint4(0, 0, 0, 0);
+    if (c) uc = *reinterpret_cast<const uint4*>(c + i);
+    const uint32_t* pa = &ua.x; const uint32_t* pb = &ub.x; const uint32_t* pc = &uc.x;
+    uint4 o; uint32_t* po = &o.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = unpack_bf16x2(pa[k]), fb = unpack_bf16x2(pb[k]), fc = unpack_bf16x2(pc[k]);
+      po[k] = pack_bf16x2(fa.x + fb.x + fc.x, fa.y + fb.y + fc.y);
+    }
+    *reinterpret_cast<uint4*>(out + i) = o;
+  } else {
+    for (long long k = i; k < n; ++k) {
+      float v = __bfloat162float(a[k]) + __bfloat162float(b[k]);
+      if (c) v += __bfloat162float(c[k]);
+      out[k] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+__global__ void rng_advance_kernel(unsigned long long* state) { *state += 0x9E3779B97F4A7C15ull; }
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vacnic_colsum(const void* x, float* out, int64_t rows, int32_t n, int64_t ld, void* stream) {
+  VB_REQUIRE(x && out, "colsum: null pointer");
+  VB_REQUIRE(rows >= 0 && n > 0 && ld >= n, "colsum: bad shape");
+  if (rows == 0) return VACNIC_OK;
+  const int col_tiles = (n + 255) / 256;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  long long slabs = (2LL * sms + col_tiles - 1) / col_tiles;
+  if (slabs > (rows + 63) / 64) slabs = (rows + 63) / 64;
+  if (slabs < 1) slabs = 1;
+  const int rpb = static_cast<int>((rows + slabs - 1) / slabs);
+  dim3 grid(col_tiles, static_cast<unsigned>((rows + rpb - 1) / rpb));
+  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), out, rows,
+                                                                    n, ld, rpb);
+  count_launch();
+  return check_last("colsum");
+}
+
+extern "C" int vacnic_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  VB_REQUIRE(src && dst, "cast: null pointer");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+             "cast: pointers must be 16-byte aligned");
+  if (n <= 0) return VACNIC_OK;
+  const long long blocks = (n + 2047) / 2048;
+  cast_f32_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
+  count_launch();
+  return check_last("cast_f32_bf16");
+}
+
+extern "C" int vacnic_adamw(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const float* hyper,
+                            void* stream) {
+  VB_REQUIRE(p && g && m && v && hyper, "adamw: null pointer");
+  VB_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+               reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p16) & 7) == 0,
+             "adamw: buffers must be 16-byte aligned");
+  if (n <= 0) return VACNIC_OK;
+  const long long blocks = (n + 1023) / 1024;
+  adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, static_cast<__nv_bfloat16*>(p16), n, hyper);
+  count_launch();
+  return check_last("adamw");
+}
+
+extern "C" int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream) {
+  VB_REQUIRE(a && b && out, "add_bf16: null pointer");
+  VB_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+               reinterpret_cast<uintptr_t>(out)) & 15) == 0, "add_bf16: buffers must be 16-byte aligned");
+  if (n <= 0) return VACNIC_OK;
+  const long long blocks = (n + 2047) / 2048;
+  add_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b),
+      static_cast<const __nv_bfloat16*>(c), static_cast<__nv_bfloat16*>(out), n);
+  count_launch();
+  return check_last("add_bf16");
+}
+
+extern "C" int vacnic_rng_advance(uint64_t* state, void* stream) {
+  VB_REQUIRE(state, "rng_advance: null pointer");
+  rng_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(state));
+  count_launch();
+  return check_last("rng_advance");
+}

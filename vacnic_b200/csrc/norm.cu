@@ -1,0 +1,591 @@
+// LayerNorm family for the VACNIC hot path (HBM-bound, one warp per row, 16-byte vector access):
+//   add_layernorm fwd/bwd : y = LN(res + dropout(x))            (MFULL:652-653, 663-664, 678-679,
+//                                                                 688, 705-707, 721-723, 742-744, 839-841, ...)
+//   embed_ln fwd/bwd      : y = dropout(LN(E[ids] + Pos[t + off]))   (MFULL:1243-1249, 1254-1260, 1555-1563)
+//   names_embed           : mean_t LN(E[ids] + Pos[t + 2])       (get_embedding_ner, TRAIN:112-133)
+// d_model must be a multiple of 256 (768 and 1024 are the only widths the reference can build:
+// MFULL:1136, 1142).  Statistics and parameter gradients are fp32; activations bf16.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+// Bernoulli keep decision for element `idx` of call site `salt` in step `seed`.
+__device__ __forceinline__ bool keep_elem(uint32_t seed, uint32_t salt, uint64_t idx, uint32_t thresh) {
+  uint32_t h = hash32(static_cast<uint32_t>(idx) * 0x9E3779B1u + seed);
+  h = hash32(h ^ (static_cast<uint32_t>(idx >> 32) + salt * 0x7F4A7C15u));
+  return h >= thresh;
+}
+__host__ __device__ inline uint32_t drop_thresh(float p) {
+  double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+struct LnArgs {
+  const __nv_bfloat16* x;    // [rows, d]
+  const __nv_bfloat16* res;  // [rows, d] or null
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* y;          // row r at y + (r / rpg) * y_gs + (r % rpg) * d
+  float* mean;
+  float* rstd;
+  long long rows;
+  int d;
+  long long rpg, y_gs;
+  float eps;
+  float p_drop;
+  const unsigned long long* rng;  // device step counter (null when p_drop == 0)
+  uint32_t salt;
+};
+
+// v[j][e] for lane: vector index (lane + 32*j), element e.
+template <int VPL>
+__device__ __forceinline__ void ln_row_stats(float (&v)[VPL][8], int d, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[j][e];
+  mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float c = v[j][e] - mean;
+      q += c * c;
+    }
+  rstd = rsqrtf(warp_sum(q) / d + eps);
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(const LnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= a.rows) return;
+  const uint4* xp = reinterpret_cast<const uint4*>(a.x + row * a.d);
+  const uint4* rp = a.res ? reinterpret_cast<const uint4*>(a.res + row * a.d) : nullptr;
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t seed = drop ? static_cast<uint32_t>(*a.rng) : 0u;
+  const uint32_t thr = drop_thresh(a.p_drop);
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  float v[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+    unpack8(__ldg(xp + vi), v[j]);
+    if (drop) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        v[j][e] = keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + vi * 8 + e, thr) ? v[j][e] * inv_keep : 0.f;
+    }
+    if (rp) {
+      float r[8];
+      unpack8(__ldg(rp + vi), r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j][e] += r[e];
+    }
+  }
+  float mean, rstd;
+  ln_row_stats<VPL>(v, a.d, a.eps, mean, rstd);
+  if (lane == 0) {
+    if (a.mean) a.mean[row] = mean;
+    if (a.rstd) a.rstd[row] = rstd;
+  }
+  uint4* yp = reinterpret_cast<uint4*>(a.y + (row / a.rpg) * a.y_gs + (row % a.rpg) * a.d);
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2 + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta) + vi * 2);
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta) + vi * 2 + 1);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * g[e] + b[e];
+    yp[vi] = pack8(o);
+  }
+}
+
+struct LnBwdArgs {
+  const __nv_bfloat16* dy;   // row r at dy + (r / rpg) * dy_gs + (r % rpg) * d
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* res;  // or null
+  const float* gamma;
+  const float* mean;
+  const float* rstd;
+  __nv_bfloat16* dsum;       // [rows,d] gradient of (res + dropout(x)); null allowed when dx given
+  __nv_bfloat16* dx;         // [rows,d] gradient of x (= dsum when no dropout); may alias / be null
+  float* dgamma;             // += (atomic)
+  float* dbeta;              // += (atomic)
+  float* dbias;              // += column sums of dx (bias of the linear that produced x), or null
+  long long rows;
+  int d;
+  long long rpg, dy_gs;
+  float p_drop;
+  const unsigned long long* rng;
+  uint32_t salt;
+  int accumulate_dsum;       // dsum += instead of = (residual stream fan-in)
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_bwd_kernel(const LnBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t seed = drop ? static_cast<uint32_t>(*a.rng) : 0u;
+  const uint32_t thr = drop_thresh(a.p_drop);
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  float dg[VPL][8], db[VPL][8], dbi[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dg[j][e] = db[j][e] = dbi[j][e] = 0.f;
+
+  const long long wstride = static_cast<long long>(gridDim.x) * kWarpsPerBlock;
+  for (long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; row < a.rows; row += wstride) {
+    const uint4* xp = reinterpret_cast<const uint4*>(a.x + row * a.d);
+    const uint4* rp = a.res ? reinterpret_cast<const uint4*>(a.res + row * a.d) : nullptr;
+    const uint4* dyp = reinterpret_cast<const uint4*>(a.dy + (row / a.rpg) * a.dy_gs + (row % a.rpg) * a.d);
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    float xh[VPL][8], g[VPL][8];
+    bool keep[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = lane + 32 * j;
+      float v[8], dyv[8];
+      unpack8(__ldg(xp + vi), v);
+      unpack8(__ldg(dyp + vi), dyv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        keep[j][e] = !drop || keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + vi * 8 + e, thr);
+        v[e] = keep[j][e] ? v[e] * inv_keep : 0.f;
+      }
+      if (rp) {
+        float r[8];
+        unpack8(__ldg(rp + vi), r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += r[e];
+      }
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2 + 1);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xh[j][e] = (v[e] - mean) * rstd;
+        g[j][e] = dyv[e] * gm[e];
+        s1 += g[j][e];
+        s2 += g[j][e] * xh[j][e];
+        dg[j][e] += dyv[e] * xh[j][e];
+        db[j][e] += dyv[e];
+      }
+    }
+    s1 = warp_sum(s1) / a.d;
+    s2 = warp_sum(s2) / a.d;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = lane + 32 * j;
+      float ds[8], dxv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ds[e] = rstd * (g[j][e] - s1 - xh[j][e] * s2);
+      if (a.dsum) {
+        uint4* p = reinterpret_cast<uint4*>(a.dsum + row * a.d) + vi;
+        if (a.accumulate_dsum) {
+          float old[8];
+          unpack8(*p, old);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ds[e] += old[e];
+        }
+        *p = pack8(ds);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dxv[e] = keep[j][e] ? ds[e] * inv_keep : 0.f;
+        dbi[j][e] += dxv[e];
+      }
+      if (a.dx && a.dx != a.dsum) reinterpret_cast<uint4*>(a.dx + row * a.d)[vi] = pack8(dxv);
+    }
+  }
+  // block-level reduction of the parameter gradients, then one atomic per column per block
+  __shared__ float red[kWarpsPerBlock][256];
+  for (int which = 0; which < 3; ++which) {
+    if (which == 2 && a.dbias == nullptr) break;
+    float* dst = which == 0 ? a.dgamma : (which == 1 ? a.dbeta : a.dbias);
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        red[warp][lane * 8 + e] = which == 0 ? dg[j][e] : (which == 1 ? db[j][e] : dbi[j][e]);
+      __syncthreads();
+      // columns of this j-slab: vector (l + 32 j), element e  ->  col = (l + 32 j) * 8 + e
+      for (int c = threadIdx.x; c < 256; c += kWarpsPerBlock * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) s += red[w][c];
+        atomicAdd(dst + j * 256 + c, s);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ embeddings
+struct EmbArgs {
+  const long long* ids;        // [rows]
+  const __nv_bfloat16* tok;    // [V, d]
+  const __nv_bfloat16* pos;    // [max_pos + 2, d]
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* y;            // [rows, d]
+  float* mean;
+  float* rstd;
+  long long rows;
+  int seq_len, pos_offset, d;
+  float eps, p_drop;
+  const unsigned long long* rng;
+  uint32_t salt;
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) embed_ln_fwd_kernel(const EmbArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= a.rows) return;
+  const long long id = a.ids[row];
+  const int p = static_cast<int>(row % a.seq_len) + a.pos_offset;
+  const uint4* tp = reinterpret_cast<const uint4*>(a.tok + id * a.d);
+  const uint4* pp = reinterpret_cast<const uint4*>(a.pos + static_cast<long long>(p) * a.d);
+  float v[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    float t[8], q[8];
+    unpack8(__ldg(tp + lane + 32 * j), t);
+    unpack8(__ldg(pp + lane + 32 * j), q);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[j][e] = t[e] + q[e];
+  }
+  float mean, rstd;
+  ln_row_stats<VPL>(v, a.d, a.eps, mean, rstd);
+  if (lane == 0) {
+    if (a.mean) a.mean[row] = mean;
+    if (a.rstd) a.rstd[row] = rstd;
+  }
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t seed = drop ? static_cast<uint32_t>(*a.rng) : 0u;
+  const uint32_t thr = drop_thresh(a.p_drop);
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  uint4* yp = reinterpret_cast<uint4*>(a.y + row * a.d);
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2 + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta) + vi * 2);
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta) + vi * 2 + 1);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o[e] = (v[j][e] - mean) * rstd * g[e] + b[e];
+      if (drop) o[e] = keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + vi * 8 + e, thr) ? o[e] * inv_keep : 0.f;
+    }
+    yp[vi] = pack8(o);
+  }
+}
+
+struct EmbBwdArgs {
+  const __nv_bfloat16* dy;
+  const long long* ids;
+  const __nv_bfloat16* tok;
+  const __nv_bfloat16* pos;
+  const float* gamma;
+  const float* mean;
+  const float* rstd;
+  float* dtok;   // [V, d]  += (atomic), skipped for ids == pad_id (nn.Embedding padding_idx)
+  float* dpos;   // [max_pos + 2, d] += (atomic)
+  float* dgamma;
+  float* dbeta;
+  long long rows;
+  int seq_len, pos_offset, d, pad_id;
+  float p_drop;
+  const unsigned long long* rng;
+  uint32_t salt;
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) embed_ln_bwd_kernel(const EmbBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t seed = drop ? static_cast<uint32_t>(*a.rng) : 0u;
+  const uint32_t thr = drop_thresh(a.p_drop);
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  float dg[VPL][8], db[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dg[j][e] = db[j][e] = 0.f;
+  const long long wstride = static_cast<long long>(gridDim.x) * kWarpsPerBlock;
+  for (long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; row < a.rows; row += wstride) {
+    const long long id = a.ids[row];
+    const int p = static_cast<int>(row % a.seq_len) + a.pos_offset;
+    const uint4* tp = reinterpret_cast<const uint4*>(a.tok + id * a.d);
+    const uint4* pp = reinterpret_cast<const uint4*>(a.pos + static_cast<long long>(p) * a.d);
+    const uint4* dyp = reinterpret_cast<const uint4*>(a.dy + row * a.d);
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    float xh[VPL][8], g[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = lane + 32 * j;
+      float t[8], q[8], dyv[8];
+      unpack8(__ldg(tp + vi), t);
+      unpack8(__ldg(pp + vi), q);
+      unpack8(__ldg(dyp + vi), dyv);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2 + 1);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (drop) dyv[e] = keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + vi * 8 + e, thr) ? dyv[e] * inv_keep : 0.f;
+        xh[j][e] = (t[e] + q[e] - mean) * rstd;
+        g[j][e] = dyv[e] * gm[e];
+        s1 += g[j][e];
+        s2 += g[j][e] * xh[j][e];
+        dg[j][e] += dyv[e] * xh[j][e];
+        db[j][e] += dyv[e];
+      }
+    }
+    s1 = warp_sum(s1) / a.d;
+    s2 = warp_sum(s2) / a.d;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = lane + 32 * j;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dh = rstd * (g[j][e] - s1 - xh[j][e] * s2);
+        const int col = vi * 8 + e;
+        if (a.dtok && id != a.pad_id) atomicAdd(a.dtok + id * a.d + col, dh);
+        if (a.dpos) atomicAdd(a.dpos + static_cast<long long>(p) * a.d + col, dh);
+      }
+    }
+  }
+  __shared__ float red[kWarpsPerBlock][256];
+  for (int which = 0; which < 2; ++which) {
+    float* dst = which == 0 ? a.dgamma : a.dbeta;
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = which == 0 ? dg[j][e] : db[j][e];
+      __syncthreads();
+      for (int c = threadIdx.x; c < 256; c += kWarpsPerBlock * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) s += red[w][c];
+        atomicAdd(dst + j * 256 + c, s);
+      }
+    }
+  }
+}
+
+// out[span, :] = mean_t LN(E[ids[span, t]] + Pos[t + 2]) ; one warp per span, fp32 output.
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+names_embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ tok,
+                   const __nv_bfloat16* __restrict__ pos, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ out, long long spans, int len, int d,
+                   float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long span = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (span >= spans) return;
+  float acc[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  for (int t = 0; t < len; ++t) {
+    const long long id = ids[span * len + t];
+    const uint4* tp = reinterpret_cast<const uint4*>(tok + id * d);
+    const uint4* pp = reinterpret_cast<const uint4*>(pos + static_cast<long long>(t + 2) * d);
+    float v[VPL][8];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      float a[8], b[8];
+      unpack8(__ldg(tp + lane + 32 * j), a);
+      unpack8(__ldg(pp + lane + 32 * j), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j][e] = a[e] + b[e];
+    }
+    float mean, rstd;
+    ln_row_stats<VPL>(v, d, eps, mean, rstd);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[j][e] += (v[j][e] - mean) * rstd;
+  }
+  const float inv = 1.f / len;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = vi * 8 + e;
+      // mean_t (xhat * g + b) = g * mean_t xhat + b
+      out[span * d + col] = acc[j][e] * inv * __ldg(gamma + col) + __ldg(beta + col);
+    }
+  }
+}
+
+static int bwd_grid(long long rows) {
+  const int sms = sm_count();
+  long long want = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  long long cap = static_cast<long long>(sms > 0 ? sms : 148) * 4;
+  return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+#define VB_DISPATCH_VPL(d, CALL)                                              \
+  switch ((d) / 256) {                                                        \
+    case 1: { constexpr int VPL = 1; CALL; } break;                           \
+    case 2: { constexpr int VPL = 2; CALL; } break;                           \
+    case 3: { constexpr int VPL = 3; CALL; } break;                           \
+    case 4: { constexpr int VPL = 4; CALL; } break;                           \
+    default: return fail(VACNIC_EINVAL, "d_model %d not supported (need 256..1024, multiple of 256)", (d)); \
+  }
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vacnic_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta,
+                                        void* y, float* mean, float* rstd, int64_t rows, int32_t d,
+                                        int64_t rows_per_group, int64_t y_group_stride, float eps, float p_drop,
+                                        const uint64_t* rng_state, uint32_t salt, void* stream) {
+  VB_REQUIRE(x && gamma && beta && y, "add_layernorm_fwd: null pointer");
+  VB_REQUIRE(rows >= 0 && d > 0 && d % 256 == 0, "add_layernorm_fwd: bad shape rows=%lld d=%d", (long long)rows, d);
+  VB_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng_state), "add_layernorm_fwd: bad dropout args");
+  if (rows == 0) return VACNIC_OK;
+  LnArgs a;
+  a.x = static_cast<const __nv_bfloat16*>(x); a.res = static_cast<const __nv_bfloat16*>(res);
+  a.gamma = gamma; a.beta = beta; a.y = static_cast<__nv_bfloat16*>(y); a.mean = mean; a.rstd = rstd;
+  a.rows = rows; a.d = d;
+  a.rpg = rows_per_group > 0 ? rows_per_group : rows;
+  a.y_gs = rows_per_group > 0 ? y_group_stride : 0;
+  VB_REQUIRE(a.y_gs % 8 == 0, "add_layernorm_fwd: group stride must be a multiple of 8 elements");
+  a.eps = eps; a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
+  const int grid = static_cast<int>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VB_DISPATCH_VPL(d, (add_layernorm_fwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(a)));
+  count_launch();
+  return check_last("add_layernorm_fwd");
+}
+
+extern "C" int vacnic_add_layernorm_bwd(const void* dy, const void* x, const void* res, const float* gamma,
+                                        const float* mean, const float* rstd, void* dsum, void* dx, float* dgamma,
+                                        float* dbeta, float* dbias, int64_t rows, int32_t d, int64_t rows_per_group,
+                                        int64_t dy_group_stride, float p_drop, const uint64_t* rng_state,
+                                        uint32_t salt, int32_t accumulate_dsum, void* stream) {
+  VB_REQUIRE(dy && x && gamma && mean && rstd, "add_layernorm_bwd: null pointer");
+  VB_REQUIRE(dsum || dx, "add_layernorm_bwd: need dsum or dx");
+  VB_REQUIRE(rows >= 0 && d > 0 && d % 256 == 0, "add_layernorm_bwd: bad shape");
+  VB_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng_state), "add_layernorm_bwd: bad dropout args");
+  if (rows == 0) return VACNIC_OK;
+  LnBwdArgs a;
+  a.dy = static_cast<const __nv_bfloat16*>(dy); a.x = static_cast<const __nv_bfloat16*>(x);
+  a.res = static_cast<const __nv_bfloat16*>(res); a.gamma = gamma; a.mean = mean; a.rstd = rstd;
+  a.dsum = static_cast<__nv_bfloat16*>(dsum); a.dx = static_cast<__nv_bfloat16*>(dx);
+  a.dgamma = dgamma; a.dbeta = dbeta; a.dbias = dbias; a.rows = rows; a.d = d;
+  a.rpg = rows_per_group > 0 ? rows_per_group : rows;
+  a.dy_gs = rows_per_group > 0 ? dy_group_stride : 0;
+  VB_REQUIRE(a.dy_gs % 8 == 0, "add_layernorm_bwd: group stride must be a multiple of 8 elements");
+  a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
+  a.accumulate_dsum = accumulate_dsum;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = bwd_grid(rows);
+  VB_DISPATCH_VPL(d, (add_layernorm_bwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(a)));
+  count_launch();
+  return check_last("add_layernorm_bwd");
+}
+
+extern "C" int vacnic_embed_ln_fwd(const int64_t* ids, const void* tok, const void* pos, const float* gamma,
+                                   const float* beta, void* y, float* mean, float* rstd, int64_t rows,
+                                   int32_t seq_len, int32_t pos_offset, int32_t d, float eps, float p_drop,
+                                   const uint64_t* rng_state, uint32_t salt, void* stream) {
+  VB_REQUIRE(ids && tok && pos && gamma && beta && y, "embed_ln_fwd: null pointer");
+  VB_REQUIRE(rows >= 0 && seq_len > 0 && d > 0 && d % 256 == 0, "embed_ln_fwd: bad shape");
+  VB_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng_state), "embed_ln_fwd: bad dropout args");
+  if (rows == 0) return VACNIC_OK;
+  EmbArgs a;
+  a.ids = reinterpret_cast<const long long*>(ids); a.tok = static_cast<const __nv_bfloat16*>(tok);
+  a.pos = static_cast<const __nv_bfloat16*>(pos); a.gamma = gamma; a.beta = beta;
+  a.y = static_cast<__nv_bfloat16*>(y); a.mean = mean; a.rstd = rstd; a.rows = rows; a.seq_len = seq_len;
+  a.pos_offset = pos_offset; a.d = d; a.eps = eps; a.p_drop = p_drop;
+  a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
+  const int grid = static_cast<int>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VB_DISPATCH_VPL(d, (embed_ln_fwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(a)));
+  count_launch();
+  return check_last("embed_ln_fwd");
+}
+
+extern "C" int vacnic_embed_ln_bwd(const void* dy, const int64_t* ids, const void* tok, const void* pos,
+                                   const float* gamma, const float* mean, const float* rstd, float* dtok,
+                                   float* dpos, float* dgamma, float* dbeta, int64_t rows, int32_t seq_len,
+                                   int32_t pos_offset, int32_t d, int32_t pad_id, float p_drop,
+                                   const uint64_t* rng_state, uint32_t salt, void* stream) {
+  VB_REQUIRE(dy && ids && tok && pos && gamma && mean && rstd, "embed_ln_bwd: null pointer");
+  VB_REQUIRE(rows >= 0 && seq_len > 0 && d > 0 && d % 256 == 0, "embed_ln_bwd: bad shape");
+  if (rows == 0) return VACNIC_OK;
+  EmbBwdArgs a;
+  a.dy = static_cast<const __nv_bfloat16*>(dy); a.ids = reinterpret_cast<const long long*>(ids);
+  a.tok = static_cast<const __nv_bfloat16*>(tok); a.pos = static_cast<const __nv_bfloat16*>(pos);
+  a.gamma = gamma; a.mean = mean; a.rstd = rstd; a.dtok = dtok; a.dpos = dpos; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.rows = rows; a.seq_len = seq_len; a.pos_offset = pos_offset; a.d = d; a.pad_id = pad_id; a.p_drop = p_drop;
+  a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = bwd_grid(rows);
+  VB_DISPATCH_VPL(d, (embed_ln_bwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(a)));
+  count_launch();
+  return check_last("embed_ln_bwd");
+}
+
+extern "C" int vacnic_names_embed(const int64_t* ids, const void* tok, const void* pos, const float* gamma,
+                                  const float* beta, float* out, int64_t spans, int32_t len, int32_t d, float eps,
+                                  void* stream) {
+  VB_REQUIRE(ids && tok && pos && gamma && beta && out, "names_embed: null pointer");
+  VB_REQUIRE(spans >= 0 && len > 0 && d > 0 && d % 256 == 0, "names_embed: bad shape");
+  if (spans == 0) return VACNIC_OK;
+  const int grid = static_cast<int>((spans + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VB_DISPATCH_VPL(d, (names_embed_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(
+                         reinterpret_cast<const long long*>(ids), static_cast<const __nv_bfloat16*>(tok),
+                         static_cast<const __nv_bfloat16*>(pos), gamma, beta, out, spans, len, d, eps)));
+  count_launch();
+  return check_last("names_embed");
+}

@@ -78,3 +78,202 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     d.act, d.dact, d.accumulate, d.tile_n = act, dact, int(accumulate), tile_n
     check(lib().vacnic_gemm(C.byref(d), stream_ptr()), "vacnic_gemm")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm family, embeddings, softmax, reductions, optimizer, losses (thin checks + C-ABI call)
+# ------------------------------------------------------------------------------------------------
+LN_EPS = 1e-5  # nn.LayerNorm default (MFULL:577)
+
+
+def _c(t, dtype, what):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _l.VacnicError(f"{what}: CUDA tensor required (no CPU fallback)")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{what}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t
+
+
+class Rng:
+    """Device-side dropout counter: one uint64 advanced once per training step (graph-capturable)."""
+
+    def __init__(self, device, seed: int = 0):
+        self.state = torch.tensor([seed * 0x9E3779B97F4A7C15 % (1 << 63)], dtype=torch.int64, device=device)
+
+    def advance(self):
+        check(lib().vacnic_rng_advance(self.state.data_ptr(), stream_ptr()), "vacnic_rng_advance")
+
+
+def add_layernorm_fwd(x, res, gamma, beta, out=None, rows_per_group=0, group_stride=0, p_drop=0.0, rng=None, salt=0):
+    """y = LN(res + dropout(x)); returns (y, mean, rstd).  `out` may be a [rows, d] view whose groups of
+    `rows_per_group` rows are `group_stride` elements apart (slice of the prefix/NER concat buffer)."""
+    d = x.shape[-1]
+    rows = x.numel() // d
+    _c(x, torch.bfloat16, "x"); _c(res, torch.bfloat16, "res"); _c(gamma, torch.float32, "gamma"); _c(beta, torch.float32, "beta")
+    if out is None:
+        out = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    check(lib().vacnic_add_layernorm_fwd(ptr(x), ptr(res), ptr(gamma), ptr(beta), ptr(out), ptr(mean), ptr(rstd), rows, d,
+                                         rows_per_group, group_stride, LN_EPS, p_drop,
+                                         rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt,
+                                         stream_ptr()), "vacnic_add_layernorm_fwd")
+    return out, mean, rstd
+
+
+def add_layernorm_bwd(dy, x, res, gamma, mean, rstd, dgamma, dbeta, dbias=None, dsum=None, want_dx=False,
+                      rows_per_group=0, group_stride=0, p_drop=0.0, rng=None, salt=0, accumulate_dsum=False):
+    """Returns (dsum, dx).  dx is dsum itself when no dropout is active."""
+    d = x.shape[-1]
+    rows = x.numel() // d
+    if dsum is None:
+        dsum = torch.empty_like(x)
+    dx = dsum
+    if p_drop > 0 and want_dx:
+        dx = torch.empty_like(x)
+    check(lib().vacnic_add_layernorm_bwd(ptr(dy), ptr(x), ptr(res), ptr(gamma), ptr(mean), ptr(rstd), ptr(dsum), ptr(dx),
+                                         ptr(dgamma), ptr(dbeta), ptr(dbias), rows, d, rows_per_group, group_stride, p_drop,
+                                         rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt,
+                                         int(accumulate_dsum), stream_ptr()), "vacnic_add_layernorm_bwd")
+    return dsum, dx
+
+
+def embed_ln_fwd(ids, tok, pos, gamma, beta, pos_offset=2, p_drop=0.0, rng=None, salt=0):
+    _c(ids, torch.int64, "ids"); _c(tok, torch.bfloat16, "tok"); _c(pos, torch.bfloat16, "pos")
+    d = tok.shape[1]
+    rows, seq = ids.numel(), ids.shape[-1]
+    y = torch.empty(tuple(ids.shape) + (d,), dtype=torch.bfloat16, device=ids.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=ids.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=ids.device)
+    check(lib().vacnic_embed_ln_fwd(ptr(ids), ptr(tok), ptr(pos), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows,
+                                    seq, pos_offset, d, LN_EPS, p_drop,
+                                    rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt, stream_ptr()),
+          "vacnic_embed_ln_fwd")
+    return y, mean, rstd
+
+
+def embed_ln_bwd(dy, ids, tok, pos, gamma, mean, rstd, dtok, dpos, dgamma, dbeta, pos_offset=2, pad_id=1, p_drop=0.0,
+                 rng=None, salt=0):
+    d = tok.shape[1]
+    check(lib().vacnic_embed_ln_bwd(ptr(dy), ptr(ids), ptr(tok), ptr(pos), ptr(gamma), ptr(mean), ptr(rstd), ptr(dtok),
+                                    ptr(dpos), ptr(dgamma), ptr(dbeta), ids.numel(), ids.shape[-1], pos_offset, d, pad_id,
+                                    p_drop, rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt,
+                                    stream_ptr()), "vacnic_embed_ln_bwd")
+
+
+def names_embed(ids3, tok, pos, gamma, beta):
+    """get_embedding_ner (TRAIN:112-133): ids [B,N,len] -> fp32 [B,N,d]."""
+    _c(ids3, torch.int64, "names_ids")
+    B, N, ln = ids3.shape
+    d = tok.shape[1]
+    out = torch.empty(B, N, d, dtype=torch.float32, device=ids3.device)
+    check(lib().vacnic_names_embed(ptr(ids3), ptr(tok), ptr(pos), ptr(gamma), ptr(beta), ptr(out), B * N, ln, d, LN_EPS,
+                                   stream_ptr()), "vacnic_names_embed")
+    return out
+
+
+def softmax_fwd(scores, key_mask, Sk, causal=False, past=0, out=None):
+    """scores fp32 [B,H,Sq,ld] -> probs bf16 [B,H,Sq,ld] (pad columns zero)."""
+    _c(scores, torch.float32, "scores"); _c(key_mask, torch.uint8, "key_mask")
+    B, H, Sq, ld = scores.shape
+    if out is None:
+        out = torch.empty(scores.shape, dtype=torch.bfloat16, device=scores.device)
+    check(lib().vacnic_softmax_fwd(ptr(scores), ptr(out), ptr(key_mask), B, H, Sq, Sk, ld, int(causal), past, stream_ptr()),
+          "vacnic_softmax_fwd")
+    return out
+
+
+def softmax_bwd(probs, dprobs, Sk, out=None):
+    _c(probs, torch.bfloat16, "probs"); _c(dprobs, torch.float32, "dprobs")
+    ld = probs.shape[-1]
+    if out is None:
+        out = torch.empty_like(probs)
+    check(lib().vacnic_softmax_bwd(ptr(probs), ptr(dprobs), ptr(out), probs.numel() // ld, Sk, ld, stream_ptr()),
+          "vacnic_softmax_bwd")
+    return out
+
+
+def colsum_into(x2d, out):
+    """out[c] += sum_r x2d[r, c]   (bias gradients)."""
+    if x2d.dtype != torch.bfloat16 or x2d.stride(-1) != 1 or x2d.dim() != 2:
+        raise ValueError("colsum: expected 2-D bf16 with innermost stride 1")
+    check(lib().vacnic_colsum(ptr(x2d), ptr(out), x2d.shape[0], x2d.shape[1], x2d.stride(0), stream_ptr()), "vacnic_colsum")
+
+
+def cast_bf16(src, dst):
+    check(lib().vacnic_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), "vacnic_cast_f32_bf16")
+
+
+def add_bf16(a, b, c=None, out=None):
+    if out is None:
+        out = torch.empty_like(a)
+    for t in (a, b, c, out):
+        _c(t, torch.bfloat16, "add_bf16 operand")
+    check(lib().vacnic_add_bf16(ptr(a), ptr(b), ptr(c), ptr(out), a.numel(), stream_ptr()), "vacnic_add_bf16")
+    return out
+
+
+def adamw(p, g, m, v, p16, hyper):
+    check(lib().vacnic_adamw(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p16), p.numel(), ptr(hyper), stream_ptr()), "vacnic_adamw")
+
+
+def ce_fwd(logits2d, V, targets, ignore_index=1):
+    """logits fp32 [rows, ld] (ld >= V). Returns (out[2] = {mean loss, count}, lse, row_loss)."""
+    _c(targets, torch.int64, "targets")
+    if logits2d.dtype != torch.float32 or logits2d.stride(1) != 1:
+        raise ValueError("ce_fwd: logits must be fp32 with innermost stride 1")
+    rows, ld = logits2d.shape[0], logits2d.stride(0)
+    dev = logits2d.device
+    lse = torch.empty(rows, dtype=torch.float32, device=dev)
+    row_loss = torch.empty(rows, dtype=torch.float32, device=dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    check(lib().vacnic_ce_fwd(ptr(logits2d), ptr(targets), ptr(lse), ptr(row_loss), ptr(out), rows, V, ld, ignore_index,
+                              stream_ptr()), "vacnic_ce_fwd")
+    return out, lse, row_loss
+
+
+def ce_bwd(logits2d, V, lse, targets, stats, gscale, coef, dlogits, ignore_index=1):
+    rows, ld = logits2d.shape[0], logits2d.stride(0)
+    check(lib().vacnic_ce_bwd(ptr(logits2d), ptr(lse), ptr(targets), ptr(stats), ptr(gscale), coef, ptr(dlogits), rows, V, ld,
+                              ignore_index, stream_ptr()), "vacnic_ce_bwd")
+    return dlogits
+
+
+def colam_fwd(h, hg, tgt_ids, margin, pad_id=1):
+    _c(h, torch.bfloat16, "h"); _c(hg, torch.bfloat16, "h_guide"); _c(tgt_ids, torch.int64, "tgt_ids")
+    B, T, d = h.shape
+    dev = h.device
+    pa = torch.empty(B, d, dtype=torch.float32, device=dev)
+    pb = torch.empty(B, d, dtype=torch.float32, device=dev)
+    stats = torch.empty(B, 8, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    check(lib().vacnic_colam_fwd(ptr(h), ptr(hg), ptr(tgt_ids), ptr(pa), ptr(pb), ptr(stats), ptr(loss), B, T, d, pad_id,
+                                 margin, stream_ptr()), "vacnic_colam_fwd")
+    return loss, pa, pb, stats
+
+
+def colam_bwd(pa, pb, stats, tgt_ids, gscale, coef, dh, accumulate=False, pad_id=1):
+    B, T, d = dh.shape
+    check(lib().vacnic_colam_bwd(ptr(pa), ptr(pb), ptr(stats), ptr(tgt_ids), ptr(gscale), coef, ptr(dh), B, T, d, pad_id,
+                                 int(accumulate), stream_ptr()), "vacnic_colam_bwd")
+    return dh
+
+
+def secla_fwd(names, face):
+    _c(names, torch.float32, "names"); _c(face, torch.bfloat16, "face")
+    B, N, d = names.shape
+    F = face.shape[1]
+    ws = torch.empty(int(lib().vacnic_secla_workspace_bytes(B, N, F)) // 4, dtype=torch.float32, device=face.device)
+    loss = torch.empty(1, dtype=torch.float32, device=face.device)
+    check(lib().vacnic_secla_fwd(ptr(names), ptr(face), ptr(ws), ptr(loss), B, N, F, d, stream_ptr()), "vacnic_secla_fwd")
+    return loss, ws
+
+
+def secla_bwd(ws, names, gscale, coef, dface, accumulate=False):
+    B, N, d = names.shape
+    F = dface.shape[1]
+    check(lib().vacnic_secla_bwd(ptr(ws), ptr(names), ptr(gscale), coef, ptr(dface), B, N, F, d, int(accumulate), stream_ptr()),
+          "vacnic_secla_bwd")
+    return dface
