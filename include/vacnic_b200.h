@@ -136,10 +136,24 @@ int vacnic_softmax_bwd(const void* probs, const float* dprobs, void* dscores, in
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * NER-prefix map (MFULL:682-687): rows = B*d_model rows of E contiguous bf16 elements (the
+ * reference's reshape(B, d, E) reinterpretation of [B, E, d]); z1 = x W_up^T + b_up (bf16 [rows, U],
+ * kept for the backward), z2 = gelu(z1) W_down^T + b_down (bf16 [rows, G]).  E, U <= 80, G <= 32.
+ * The backward writes dx and atomically accumulates the fp32 parameter gradients.
+ * ------------------------------------------------------------------------------------------ */
+int vacnic_ner_map_fwd(const void* x, const void* w_up, const float* b_up, const void* w_down, const float* b_down,
+                       void* z1, void* z2, int64_t rows, int32_t E, int32_t U, int32_t G, void* stream);
+int vacnic_ner_map_bwd(const void* dz2, const void* z1, const void* x, const void* w_up, const void* w_down, void* dx,
+                       float* dw_up, float* db_up, float* dw_down, float* db_down, int64_t rows, int32_t E, int32_t U,
+                       int32_t G, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Elementwise / reduction helpers.
  * ------------------------------------------------------------------------------------------ */
 int vacnic_colsum(const void* x, float* out, int64_t rows, int32_t n, int64_t ld, void* stream); /* out[c] += sum_r x[r,c] : nn.Linear bias gradients */
 int vacnic_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int vacnic_concat_rows(const void* a, const void* b, void* out, int32_t B, int64_t rows_a, int64_t rows_b, int32_t d,
+                       void* stream); /* out[B, ra+rb, d] = cat(a[B,ra,d], b[B,rb,d]) : MFULL:668, 691 */
 int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream); /* out = a + b (+ c) */
 /* Fused AdamW over a flat parameter buffer (TRAIN:91-107,371-373).  hyper (device, fp32[8]) =
  * {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}; also refreshes the bf16

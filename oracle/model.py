@@ -99,7 +99,8 @@ def embed(sd: SD, prefix: str, ids: torch.Tensor, tok: str, pos: str, ln: str, p
     """LN(E[ids] * 1.0 + Pos[arange + 2]); MFULL:1243-1249 / 1254-1260 / 1555-1563, offset 2 MFULL:409-418."""
     S = ids.shape[-1]
     positions = torch.arange(past, past + S, device=ids.device) + 2
-    h = sd[prefix + tok + ".weight"][ids] + sd[prefix + pos + ".weight"][positions]
+    # nn.Embedding(..., padding_idx=1): the pad row receives no gradient (MFULL:1115, 1150, 1400)
+    h = F.embedding(ids, sd[prefix + tok + ".weight"], padding_idx=1) + sd[prefix + pos + ".weight"][positions]
     return layer_norm(sd, prefix + ln, h)
 
 

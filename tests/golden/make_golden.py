@@ -202,7 +202,9 @@ def main():
                             "model.encoder.layers.0.cross_attn_img_ner.k_proj.weight",
                             "model.encoder.layers.0.ner_map_up.weight", "model.encoder.visual_map.weight",
                             "model.encoder._linear_1.weight", "model.decoder.layers.1.encoder_attn.v_proj.weight",
-                            "model.decoder.layernorm_embedding.weight", "model.encoder.layers.1.img_layer_norm.bias")
+                            "model.decoder.layernorm_embedding.weight", "model.encoder.layers.1.img_layer_norm.bias",
+                            "model.encoder.embed_tokens_ner.weight", "model.shared.weight",
+                            "model.encoder.embed_positions.weight", "lm_head.weight")
                 if k in grads]
         fx = dict(
             case=name, cfg=cfg.as_dict(), batch_kwargs=bkw, weight_seed=wseed, guide_seed=wseed + 100, lm_scale=lm_scale,

@@ -1,0 +1,440 @@
+"""Block-level autograd functions of the VACNIC encoder / decoder, built only from the C-ABI kernels.
+
+Granularity = one residual block of the reference (`x -> LN(x + dropout(f(x)))`), so that the
+gradient fan-in of the residual stream is fused into kernel epilogues (LayerNorm-backward writes the
+residual gradient, the data-gradient GEMM accumulates onto it) instead of being summed by autograd.
+Parameter gradients are written straight into the flat fp32 gradient buffer of the ParamStore
+(`Lin.gw / Lin.gb`), never returned through autograd.
+
+Reference: BartAttention.forward MFULL:454-565, BartEncoderLayer.forward MFULL:618-762,
+BartDecoderLayer.forward MFULL:793-890, embeddings MFULL:1243-1260, 1555-1563.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import kernels as K
+from .store import Lin, ParamStore
+
+
+class Runtime:
+    """Per-model execution context shared by all blocks."""
+
+    def __init__(self, store: ParamStore, p_drop: float = 0.0, seed: int = 0):
+        self.store = store
+        self.p_drop = p_drop
+        self.training = False
+        self.rng = K.Rng(store.device, seed)
+        self._salt = 0
+
+    def new_salt(self) -> int:
+        self._salt += 1
+        return self._salt
+
+    @property
+    def drop(self) -> float:
+        return self.p_drop if self.training else 0.0
+
+
+class LN:
+    """fp32 LayerNorm parameter views + gradient views + dropout salt of one call site."""
+    __slots__ = ("g", "b", "gg", "gb", "salt")
+
+    def __init__(self, store: ParamStore, mod, salt: int):
+        self.g, self.b = store.f32(mod.weight).view(-1), store.f32(mod.bias).view(-1)
+        self.gg = None if store.frozen else store.g32(mod.weight).view(-1)
+        self.gb = None if store.frozen else store.g32(mod.bias).view(-1)
+        self.salt = salt
+
+
+def _ceil8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _wgrad(rt: Runtime, lin: Lin, dy2d: torch.Tensor, x2d: torch.Tensor, bias_from: Optional[torch.Tensor] = None):
+    """gw (+)= dy^T x ; gb += colsum(dy)."""
+    K.gemm(dy2d, x2d, out=lin.gw, a_mn=True, b_mn=True, accumulate=rt.store.touch(lin.key))
+    if lin.gb is not None and bias_from is not None:
+        K.colsum_into(bias_from, lin.gb)
+
+
+# --------------------------------------------------------------------------------------------------
+# scaled dot-product attention core (unfused tensor-core path: QK^T GEMM -> masked softmax -> PV GEMM)
+# --------------------------------------------------------------------------------------------------
+def sdpa_fwd(q4, k4, v4, key_mask, causal, past, scale):
+    """q4 [B,H,Sq,hd], k4/v4 [B,H,Sk,hd] (strided views).  Returns (O [B,Sq,H*hd], P [B,H,Sq,Skp])."""
+    B, H, Sq, hd = q4.shape
+    Sk = k4.shape[2]
+    Skp = _ceil8(Sk)
+    S = torch.empty(B, H, Sq, Skp, dtype=torch.float32, device=q4.device)
+    K.gemm(q4, k4, out=S[..., :Sk], alpha=scale)
+    P = K.softmax_fwd(S, key_mask, Sk, causal=causal, past=past)
+    O = torch.empty(B, Sq, H, hd, dtype=torch.bfloat16, device=q4.device)
+    K.gemm(P[..., :Sk], v4, out=O.permute(0, 2, 1, 3), b_mn=True)
+    return O.view(B, Sq, H * hd), P
+
+
+def sdpa_bwd(dO, q4, k4, v4, P, scale, dq4, dk4, dv4):
+    B, H, Sq, hd = q4.shape
+    Sk = k4.shape[2]
+    Skp = P.shape[-1]
+    dO4 = dO.view(B, Sq, H, hd).permute(0, 2, 1, 3)
+    dP = torch.empty(B, H, Sq, Skp, dtype=torch.float32, device=dO.device)
+    K.gemm(dO4, v4, out=dP[..., :Sk])
+    dS = K.softmax_bwd(P, dP, Sk)
+    K.gemm(P[..., :Sk], dO4, out=dv4, a_mn=True, b_mn=True)
+    K.gemm(dS[..., :Sk], k4, out=dq4, b_mn=True, alpha=scale)
+    K.gemm(dS[..., :Sk], q4, out=dk4, a_mn=True, b_mn=True, alpha=scale)
+
+
+def _heads(t2d: torch.Tensor, B: int, S: int, H: int, col0: int, hd: int) -> torch.Tensor:
+    """[B*S, ld] buffer -> [B,H,S,hd] view of columns [col0, col0 + H*hd)."""
+    ld = t2d.stride(0)
+    return t2d.as_strided((B, H, S, hd), (S * ld, hd, ld, 1), t2d.storage_offset() + col0)
+
+
+class AttnBlockFn(torch.autograd.Function):
+    """y = LN(x + dropout(out_proj(softmax(q k^T * hd^-0.5 + mask) v)))   (MFULL:697-707, 711-723,
+    669-679, 831-841, 856-866).  Self-attention: kv_src is None and one fused [k;v;q] GEMM projects x.
+    Cross-attention: q from x; k/v either from `kv_src` through `lin_kv`, or precomputed (`kv_pre`,
+    the hoisted decoder cross-K/V GEMM) with gradients written to `dkv_pre`."""
+
+    @staticmethod
+    def forward(ctx, x, kv_src, kv_pre, rt: Runtime, lin_qkv: Lin, lin_q: Lin, lin_kv: Lin, lin_o: Lin, ln: LN,
+                H: int, key_mask, causal: bool, use_dropout: bool, kv_col0: int, dkv_all, return_dkv_all: bool):
+        B, Sq, d = x.shape
+        hd = d // H
+        scale = hd ** -0.5
+        x2 = x.view(B * Sq, d)
+        if lin_qkv is not None:  # self attention, fused [k; v; q] projection (MFULL:444-446 order)
+            qkv = K.gemm(x2, lin_qkv.w16, bias=lin_qkv.b32)
+            Sk = Sq
+            k4, v4, q4 = (_heads(qkv, B, Sq, H, c * d, hd) for c in range(3))
+            kvp = None
+        else:
+            qkv = K.gemm(x2, lin_q.w16, bias=lin_q.b32)
+            q4 = _heads(qkv, B, Sq, H, 0, hd)
+            if kv_pre is not None:  # [B, Sk, n_layers*2d]: this layer's k|v live at columns [kv_col0, +2d)
+                Sk = kv_pre.shape[1]
+                kvp = kv_pre.view(B * Sk, -1)[:, kv_col0:kv_col0 + 2 * d]
+            else:
+                Sk = kv_src.shape[1]
+                kvp = K.gemm(kv_src.view(B * Sk, d), lin_kv.w16, bias=lin_kv.b32)
+            k4, v4 = _heads(kvp, B, Sk, H, 0, hd), _heads(kvp, B, Sk, H, d, hd)
+        O, P = sdpa_fwd(q4, k4, v4, key_mask, causal, 0, scale)
+        a = K.gemm(O.view(B * Sq, d), lin_o.w16, bias=lin_o.b32)
+        p = rt.drop if use_dropout else 0.0
+        y, mean, rstd = K.add_layernorm_fwd(a, x2, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt)
+        ctx.rt, ctx.lins, ctx.ln, ctx.H, ctx.p = rt, (lin_qkv, lin_q, lin_kv, lin_o), ln, H, p
+        ctx.saved = (x2, kv_src, qkv, kvp, P, O, a, mean, rstd, q4, k4, v4)
+        hoisted = kv_pre is not None and dkv_all is not None
+        ctx.dkv_pre = dkv_all.view(B * Sk, -1)[:, kv_col0:kv_col0 + 2 * d] if hoisted else None
+        ctx.dkv_all = dkv_all if (hoisted and return_dkv_all) else None
+        ctx.shape = (B, Sq, d, Sk)
+        return y.view(B, Sq, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt, ln, H = ctx.rt, ctx.ln, ctx.H
+        lin_qkv, lin_q, lin_kv, lin_o = ctx.lins
+        x2, kv_src, qkv, kvp, P, O, a, mean, rstd, q4, k4, v4 = ctx.saved
+        B, Sq, d, Sk = ctx.shape
+        hd = d // H
+        dy = dy.contiguous()
+        dsum, da = K.add_layernorm_bwd(dy.view(B * Sq, d), a, x2, ln.g, mean, rstd, ln.gg, ln.gb, dbias=lin_o.gb,
+                                       want_dx=True, p_drop=ctx.p, rng=rt.rng, salt=ln.salt)
+        O2 = O.view(B * Sq, d)
+        _wgrad(rt, lin_o, da, O2)
+        dO = K.gemm(da, lin_o.w16, b_mn=True)
+        dkv_src = None
+        if lin_qkv is not None:
+            dqkv = torch.empty_like(qkv)
+            dk4, dv4, dq4 = (_heads(dqkv, B, Sq, H, c * d, hd) for c in range(3))
+            sdpa_bwd(dO, q4, k4, v4, P, hd ** -0.5, dq4, dk4, dv4)
+            _wgrad(rt, lin_qkv, dqkv, x2, bias_from=dqkv)
+            K.gemm(dqkv, lin_qkv.w16, out=dsum, b_mn=True, accumulate=True)  # dx = dsum + dqkv W
+        else:
+            dq = torch.empty_like(qkv)
+            dq4 = _heads(dq, B, Sq, H, 0, hd)
+            dkvp = ctx.dkv_pre if ctx.dkv_pre is not None else torch.empty_like(kvp)
+            dk4, dv4 = _heads(dkvp, B, Sk, H, 0, hd), _heads(dkvp, B, Sk, H, d, hd)
+            sdpa_bwd(dO, q4, k4, v4, P, hd ** -0.5, dq4, dk4, dv4)
+            _wgrad(rt, lin_q, dq, x2, bias_from=dq)
+            K.gemm(dq, lin_q.w16, out=dsum, b_mn=True, accumulate=True)
+            if ctx.dkv_pre is None:
+                kv2 = kv_src.view(B * Sk, d)
+                _wgrad(rt, lin_kv, dkvp, kv2, bias_from=dkvp)
+                if ctx.needs_input_grad[1]:
+                    dkv_src = K.gemm(dkvp, lin_kv.w16, b_mn=True).view(B, Sk, d)
+        ctx.saved = None
+        # hoisted cross K/V: every layer wrote its slice of the shared gradient buffer in place; the
+        # block that runs last in the backward pass (layer 0) hands the whole buffer to autograd.
+        return (dsum.view(B, Sq, d), dkv_src, ctx.dkv_all) + (None,) * 13
+
+
+class MlpBlockFn(torch.autograd.Function):
+    """z = act(x W1^T + b1) W2^T + b2, then y = LN(x + dropout(z)) when `ln` is given (the FFN blocks,
+    MFULL:647-653, 658-664, 738-744, 868-878) or y = z (the ClipCap prefix MLP, MFULL:111-123)."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, rt: Runtime, lin1: Lin, lin2: Lin, act: int, ln: Optional[LN]):
+        shp = x.shape
+        d_in = shp[-1]
+        x2 = x.reshape(-1, d_in)
+        rows = x2.shape[0]
+        aux = torch.empty(rows, lin1.out_f, dtype=torch.bfloat16, device=x.device) if act == K.ACT_GELU else None
+        h = K.gemm(x2, lin1.w16, bias=lin1.b32, act=act, aux_out=aux)
+        z = K.gemm(h, lin2.w16, bias=lin2.b32)
+        if ln is not None:
+            p = rt.drop
+            y, mean, rstd = K.add_layernorm_fwd(z, x2, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt)
+            ctx.lnstate = (z, mean, rstd, p)
+            out = y.view(shp)
+        else:
+            ctx.lnstate = None
+            out = z.view(shp[:-1] + (lin2.out_f,))
+        ctx.rt, ctx.lin1, ctx.lin2, ctx.act, ctx.ln = rt, lin1, lin2, act, ln
+        ctx.saved = (x2, aux, h)
+        ctx.in_shape = shp
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt, lin1, lin2, act, ln = ctx.rt, ctx.lin1, ctx.lin2, ctx.act, ctx.ln
+        x2, aux, h = ctx.saved
+        rows = x2.shape[0]
+        if ln is not None:
+            z, mean, rstd, p = ctx.lnstate
+            dsum, dz = K.add_layernorm_bwd(dy.contiguous(), z, x2, ln.g, mean, rstd, ln.gg, ln.gb, dbias=lin2.gb,
+                                           want_dx=True, p_drop=p, rng=rt.rng, salt=ln.salt)
+        else:
+            dz = dy.contiguous().view(rows, lin2.out_f)
+            dsum = None
+            if lin2.gb is not None:
+                K.colsum_into(dz, lin2.gb)
+        _wgrad(rt, lin2, dz, h)
+        # dh * act'(.) fused in the data-gradient GEMM epilogue (GELU' from the pre-activation, tanh' from the output)
+        dpre = K.gemm(dz, lin2.w16, b_mn=True, dact=act, aux_in=aux if act == K.ACT_GELU else h)
+        _wgrad(rt, lin1, dpre, x2, bias_from=dpre)
+        if dsum is not None:
+            K.gemm(dpre, lin1.w16, out=dsum, b_mn=True, accumulate=True)
+            dx = dsum.view(ctx.in_shape)
+        elif ctx.needs_input_grad[0]:
+            dx = K.gemm(dpre, lin1.w16, b_mn=True).view(ctx.in_shape)
+        else:
+            dx = None
+        ctx.saved = None
+        return (dx,) + (None,) * 6
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (visual_map MFULL:1277-1278, face _linear_1 MFULL:1269, hoisted decoder cross K/V,
+    LM head MFULL:1997 with fp32 output)."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, rt: Runtime, lin: Lin, out_dtype, need_dx: bool, out_buf, dy_buf):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if out_buf is not None:
+            y = K.gemm(x2, lin.w16, out=out_buf, bias=lin.b32)
+        else:
+            y = K.gemm(x2, lin.w16, bias=lin.b32, out_dtype=out_dtype)
+        ctx.rt, ctx.lin, ctx.x2, ctx.need_dx, ctx.shp, ctx.dy_buf = rt, lin, x2, need_dx, shp, dy_buf
+        return y.view(shp[:-1] + (y.shape[-1],))
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt, lin, x2 = ctx.rt, ctx.lin, ctx.x2
+        if ctx.dy_buf is not None:
+            dy2 = ctx.dy_buf  # gradients were written in place by the consumers (hoisted cross K/V)
+        else:
+            dy2 = dy.reshape(x2.shape[0], -1)
+            if dy2.dtype != torch.bfloat16:
+                d16 = torch.empty(dy2.shape, dtype=torch.bfloat16, device=dy2.device)
+                K.cast_bf16(dy2.contiguous(), d16)
+                dy2 = d16
+            elif dy2.stride(-1) != 1:
+                dy2 = dy2.contiguous()
+        _wgrad(rt, lin, dy2, x2, bias_from=dy2 if lin.gb is not None else None)
+        dx = K.gemm(dy2, lin.w16, b_mn=True).view(ctx.shp) if (ctx.need_dx and ctx.needs_input_grad[0]) else None
+        return (dx,) + (None,) * 7
+
+
+class EmbedFn(torch.autograd.Function):
+    """y = dropout(LN(tok[ids] + pos[t + offset]))  (MFULL:1243-1249, 1254-1260, 1555-1563)."""
+
+    @staticmethod
+    def forward(ctx, anchor, ids, rt: Runtime, tok_p, pos_p, ln: LN, pos_offset: int, pad_id: int):
+        st = rt.store
+        tok16, pos16 = st.w16(tok_p), st.w16(pos_p)
+        p = rt.drop
+        y, mean, rstd = K.embed_ln_fwd(ids, tok16, pos16, ln.g, ln.b, pos_offset=pos_offset, p_drop=p, rng=rt.rng,
+                                       salt=ln.salt)
+        ctx.rt, ctx.ln, ctx.args = rt, ln, (ids, tok_p, pos_p, tok16, pos16, mean, rstd, pos_offset, pad_id, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt, ln = ctx.rt, ctx.ln
+        ids, tok_p, pos_p, tok16, pos16, mean, rstd, pos_offset, pad_id, p = ctx.args
+        st = rt.store
+        K.embed_ln_bwd(dy.contiguous(), ids, tok16, pos16, ln.g, mean, rstd, st.g32(tok_p), st.g32(pos_p), ln.gg, ln.gb,
+                       pos_offset=pos_offset, pad_id=pad_id, p_drop=p, rng=rt.rng, salt=ln.salt)
+        return (None,) * 8
+
+
+class NerMapFn(torch.autograd.Function):
+    """prefix = LN(reshape(gelu(reshape(ner) W_up^T + b) W_down^T + b))  (MFULL:682-688): [B,E,d] -> [B,G,d]."""
+
+    @staticmethod
+    def forward(ctx, ner, rt: Runtime, up: Lin, down: Lin, ln: LN):
+        B, E, d = ner.shape
+        G = down.out_f
+        x_rows = ner.reshape(B * d, E)
+        z1, z2 = K.ner_map_fwd(x_rows, up.w16, up.b32, down.w16, down.b32)
+        z2r = z2.view(B * G, d)
+        y, mean, rstd = K.add_layernorm_fwd(z2r, None, ln.g, ln.b)
+        ctx.rt, ctx.up, ctx.down, ctx.ln = rt, up, down, ln
+        ctx.saved = (x_rows, z1, z2r, mean, rstd)
+        ctx.dims = (B, E, d, G)
+        return y.view(B, G, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt, up, down, ln = ctx.rt, ctx.up, ctx.down, ctx.ln
+        x_rows, z1, z2r, mean, rstd = ctx.saved
+        B, E, d, G = ctx.dims
+        dz2, _ = K.add_layernorm_bwd(dy.contiguous().view(B * G, d), z2r, None, ln.g, mean, rstd, ln.gg, ln.gb)
+        # the NER-map weight gradients live in the atomically accumulated (zeroed each step) region? No:
+        # they are 2-D, so zero them on first touch, then accumulate atomically.
+        for lin in (up, down):
+            if not rt.store.touch(lin.key):
+                lin.gw.zero_()
+        dx = K.ner_map_bwd(dz2.view(B * d, G), z1, x_rows, up.w16, down.w16, up.gw, up.gb, down.gw, down.gb)
+        ctx.saved = None
+        return dx.view(B, E, d), None, None, None, None
+
+
+class Concat2Fn(torch.autograd.Function):
+    """torch.cat((a, b), dim=1) for [B, Sa, d] / [B, Sb, d] (MFULL:668, 691): pure data movement."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.sa = a.shape[1]
+        out = torch.empty(a.shape[0], a.shape[1] + b.shape[1], a.shape[2], dtype=a.dtype, device=a.device)
+        K.concat_rows(a, b, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return d[:, :ctx.sa], d[:, ctx.sa:]
+
+
+class FanoutFn(torch.autograd.Function):
+    """Identity with n outputs whose gradients are summed by the vacnic_add_bf16 kernel."""
+
+    @staticmethod
+    def forward(ctx, x, n: int):
+        ctx.set_materialize_grads(False)
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gs = [g.contiguous() for g in grads if g is not None]
+        if not gs:
+            return None, None
+        acc = gs[0]
+        i = 1
+        while i < len(gs):
+            if i + 1 < len(gs):
+                acc = K.add_bf16(acc, gs[i], gs[i + 1])
+                i += 2
+            else:
+                acc = K.add_bf16(acc, gs[i])
+                i += 1
+        return acc, None
+
+
+def fanout(x, n):
+    if n == 1 or not x.requires_grad:
+        return (x,) * n
+    return FanoutFn.apply(x, n)
+
+
+# --------------------------------------------------------------------------------------------------
+# heads and losses
+# --------------------------------------------------------------------------------------------------
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class LmHeadCeFn(torch.autograd.Function):
+    """logits = h W_lm^T + final_logits_bias (MFULL:1997) fused with CrossEntropyLoss(ignore_index=pad)
+    (TRAIN:287, 816).  Returns (loss[1], logits fp32 [B,T,V]); only the loss is differentiable here."""
+
+    @staticmethod
+    def forward(ctx, h, rt: Runtime, lin: Lin, targets, pad_id: int):
+        ctx.set_materialize_grads(False)
+        B, T, d = h.shape
+        V = lin.out_f
+        ldp = _pad8(V)
+        h2 = h.reshape(B * T, d)
+        buf = torch.empty(B * T, ldp, dtype=torch.float32, device=h.device)
+        logits = K.gemm(h2, lin.w16, out=buf[:, :V], bias=lin.b32)
+        tflat = targets.reshape(-1).contiguous()
+        out, lse, _ = K.ce_fwd(logits, V, tflat, ignore_index=pad_id)
+        ctx.rt, ctx.lin, ctx.saved, ctx.pad = rt, lin, (h2, logits, lse, tflat, out), pad_id
+        ctx.shape = (B, T, d, V, ldp)
+        lg = logits.view(B, T, V) if ldp == V else buf.view(B, T, ldp)[..., :V]
+        ctx.mark_non_differentiable(lg)
+        return out[:1], lg
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        rt, lin = ctx.rt, ctx.lin
+        h2, logits, lse, tflat, out = ctx.saved
+        B, T, d, V, ldp = ctx.shape
+        dl = torch.empty(B * T, ldp, dtype=torch.bfloat16, device=h2.device)
+        K.ce_bwd(logits, V, lse, tflat, out, dloss.contiguous().float(), 1.0, dl, ignore_index=ctx.pad)
+        _wgrad(rt, lin, dl[:, :V], h2)
+        dh = K.gemm(dl[:, :V], lin.w16, b_mn=True)
+        ctx.saved = None
+        return dh.view(B, T, d), None, None, None, None
+
+
+class ColamFn(torch.autograd.Function):
+    """CoLaM margin loss (TRAIN:292-309) between the model's and the frozen guide's last decoder states."""
+
+    @staticmethod
+    def forward(ctx, h, h_guide, tgt_ids, margin: float, pad_id: int):
+        loss, pa, pb, stats = K.colam_fwd(h.contiguous(), h_guide.contiguous(), tgt_ids.contiguous(), margin, pad_id)
+        ctx.saved = (pa, pb, stats, tgt_ids)
+        ctx.shape, ctx.pad = h.shape, pad_id
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        pa, pb, stats, tgt_ids = ctx.saved
+        dh = torch.empty(ctx.shape, dtype=torch.bfloat16, device=pa.device)
+        K.colam_bwd(pa, pb, stats, tgt_ids, dloss.contiguous().float(), 1.0, dh, pad_id=ctx.pad)
+        return dh, None, None, None, None
+
+
+class SeclaFn(torch.autograd.Function):
+    """SECLA BatchSoftmax (TRAIN:631-660): gradient flows into the face states only (names are no_grad)."""
+
+    @staticmethod
+    def forward(ctx, face, names):
+        loss, ws = K.secla_fwd(names.contiguous(), face.contiguous())
+        ctx.saved = (ws, names)
+        ctx.shape = face.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        ws, names = ctx.saved
+        dface = torch.empty(ctx.shape, dtype=torch.bfloat16, device=names.device)
+        K.secla_bwd(ws, names, dloss.contiguous().float(), 1.0, dface)
+        return dface, None

@@ -130,6 +130,18 @@ add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __rest
   }
 }
 
+// out[b] = [a[b] ; c[b]] along the row dimension (torch.cat(dim=1) at MFULL:668, 691); 16-byte vectors
+__global__ void __launch_bounds__(256)
+concat_rows_kernel(const uint4* __restrict__ a, const uint4* __restrict__ c, uint4* __restrict__ out, int B,
+                   long long va, long long vc) {
+  const long long per = va + vc;
+  const long long n = per * B;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const long long b = i / per, r = i % per;
+    out[i] = r < va ? a[b * va + r] : c[b * vc + (r - va)];
+  }
+}
+
 __global__ void rng_advance_kernel(unsigned long long* state) { *state += 0x9E3779B97F4A7C15ull; }
 
 }  // namespace vb
@@ -190,6 +202,21 @@ extern "C" int vacnic_add_bf16(const void* a, const void* b, const void* c, void
       static_cast<const __nv_bfloat16*>(c), static_cast<__nv_bfloat16*>(out), n);
   count_launch();
   return check_last("add_bf16");
+}
+
+extern "C" int vacnic_concat_rows(const void* a, const void* b, void* out, int32_t B, int64_t rows_a, int64_t rows_b,
+                                  int32_t d, void* stream) {
+  VB_REQUIRE(a && b && out, "concat_rows: null pointer");
+  VB_REQUIRE(B > 0 && rows_a >= 0 && rows_b >= 0 && d > 0 && d % 8 == 0, "concat_rows: bad shape");
+  const long long va = rows_a * d / 8, vc = rows_b * d / 8;
+  const long long n = (va + vc) * B;
+  if (n == 0) return VACNIC_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  concat_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), B, va, vc);
+  count_launch();
+  return check_last("concat_rows");
 }
 
 extern "C" int vacnic_rng_advance(uint64_t* state, void* stream) {

@@ -1,0 +1,170 @@
+"""Flat parameter storage: one fp32 master buffer, one bf16 compute shadow and one fp32 gradient buffer
+for the whole model, with every nn.Parameter a view into them.
+
+Why: (1) the tensor-core kernels consume bf16 weights while the reference trains fp32 parameters
+(TRAIN:95, `bart-large-fp32`), (2) projections the reference runs as separate nn.Linear calls on the
+same input (k/v/q of BartAttention MFULL:444-446; the twelve decoder cross-attention k/v projections
+of the encoder memory, MFULL:856) become ONE GEMM when their weights are adjacent in memory, (3) the
+optimizer and the gradient all-reduce become single passes over a flat buffer.  Parameter names and
+shapes stay those of the reference state_dict.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import kernels as K
+
+ALIGN = 64  # elements; keeps every view 128-byte (bf16) / 256-byte (fp32) aligned
+
+
+class Lin:
+    """Views one (possibly fused) linear layer needs: bf16 weight, fp32 bias, fp32 gradient views."""
+    __slots__ = ("w16", "b32", "gw", "gb", "key", "out_f", "in_f")
+
+    def __init__(self, w16, b32, gw, gb, key):
+        self.w16, self.b32, self.gw, self.gb, self.key = w16, b32, gw, gb, key
+        self.out_f, self.in_f = w16.shape
+
+
+class ParamStore:
+    def __init__(self, module: nn.Module, device, first: Sequence[str] = (), frozen: bool = False):
+        """`first`: parameter names to lay out first in their region, in the given order (used to make
+        fused groups adjacent).  `frozen`: no gradient / optimizer buffers (the CoLaM guide)."""
+        named = []
+        seen = set()
+        for n, p in module.named_parameters():
+            if id(p) in seen:
+                continue
+            seen.add(id(p))
+            named.append((n, p))
+        by_name = dict(named)
+        order = [n for n in first if n in by_name] + [n for n, _ in named if n not in set(first)]
+
+        def is_matrix(n, p):
+            return p.dim() == 2 and "embed_" not in n and "shared" not in n
+
+        w_names = [n for n in order if is_matrix(n, by_name[n])]
+        z_names = [n for n in order if not is_matrix(n, by_name[n])]
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for n in w_names + z_names:
+            if n == (z_names[0] if z_names else None):
+                self.z_begin = off
+            self.offsets[n] = off
+            off += (by_name[n].numel() + ALIGN - 1) // ALIGN * ALIGN
+        if not z_names:
+            self.z_begin = off
+        self.total = off
+        self.device = torch.device(device)
+        self.frozen = frozen
+        self.master = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.shadow = torch.zeros(self.total, dtype=torch.bfloat16, device=self.device)
+        self.grad = None if frozen else torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.params: Dict[str, nn.Parameter] = {}
+        self._by_id: Dict[int, str] = {}
+        remap: Dict[int, nn.Parameter] = {}
+        for n, p in named:
+            o, k = self.offsets[n], p.numel()
+            view = self.master[o:o + k].view(p.shape)
+            if p.device.type != "meta":
+                view.copy_(p.data.to(self.device, torch.float32))
+            q = nn.Parameter(view, requires_grad=not frozen)
+            if not frozen:
+                q.grad = self.grad[o:o + k].view(p.shape)
+            remap[id(p)] = q
+            self.params[n] = q
+            self._by_id[id(q)] = n
+        for m in module.modules():  # swap the (possibly meta) parameters for the flat views, ties preserved
+            for k, p in list(m._parameters.items()):
+                if p is not None and id(p) in remap:
+                    m._parameters[k] = remap[id(p)]
+        self._touched = set()
+        self._lin_span: Dict[str, tuple] = {}
+        self.dirty_shadow = True
+        # requires-grad anchor so that autograd records the first block of a forward pass
+        self.anchor = torch.zeros(1, device=self.device, requires_grad=not frozen)
+
+    # ------------------------------------------------------------------ views
+    def name_of(self, p: nn.Parameter) -> str:
+        return self._by_id[id(p)]
+
+    def _span(self, ps: Sequence[nn.Parameter]):
+        names = [self.name_of(p) for p in ps]
+        o0 = self.offsets[names[0]]
+        o = o0
+        for n, p in zip(names, ps):
+            if self.offsets[n] != o:
+                raise RuntimeError(f"parameters {names} are not adjacent in the flat store")
+            if p.numel() % ALIGN and n != names[-1]:
+                raise RuntimeError(f"{n}: size {p.numel()} not a multiple of {ALIGN}; cannot fuse")
+            o += p.numel()
+        return o0, o - o0
+
+    def w16(self, *ps: nn.Parameter) -> torch.Tensor:
+        """bf16 shadow of one parameter, or of several adjacent ones stacked along dim 0."""
+        o, k = self._span(ps)
+        return self.shadow[o:o + k].view(-1, *ps[0].shape[1:])
+
+    def f32(self, *ps: nn.Parameter) -> torch.Tensor:
+        o, k = self._span(ps)
+        return self.master[o:o + k].view(-1, *ps[0].shape[1:])
+
+    def g32(self, *ps: nn.Parameter) -> Optional[torch.Tensor]:
+        if self.frozen:
+            return None
+        o, k = self._span(ps)
+        return self.grad[o:o + k].view(-1, *ps[0].shape[1:])
+
+    def lin(self, weights: Sequence[nn.Parameter], biases: Optional[Sequence[nn.Parameter]]) -> Lin:
+        b32 = self.f32(*biases).view(-1) if biases else None
+        gb = self.g32(*biases).view(-1) if (biases and not self.frozen) else None
+        key = f"{self.name_of(weights[0])}+{len(weights)}"
+        self._lin_span[key] = self._span(weights)
+        return Lin(self.w16(*weights), b32, self.g32(*weights), gb, key)
+
+    # ------------------------------------------------------------------ step protocol
+    def begin_step(self):
+        """Call before the forward pass of a training step: zero the atomically-accumulated gradient
+        region (biases, LayerNorm, embeddings); GEMM weight gradients are overwritten on first touch."""
+        if self.frozen:
+            return
+        self.grad[self.z_begin:].zero_()
+        self._touched.clear()
+        for p in self.params.values():  # optimizer.zero_grad(set_to_none=True) drops the views
+            if p.grad is None:
+                o = self.offsets[self.name_of(p)]
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def finish_backward(self):
+        """GEMM-weight gradients never touched in this step (unused parameters) must read as zero."""
+        if self.frozen:
+            return
+        spans = sorted(self._lin_span[k] for k in self._touched)
+        for n, p in self.params.items():
+            o = self.offsets[n]
+            if o < self.z_begin and not any(a <= o < a + k for a, k in spans):
+                self.grad[o:o + p.numel()].zero_()
+
+    def touch(self, key: str) -> bool:
+        """True if `key`'s weight gradient already holds this step's partial sum (-> accumulate)."""
+        seen = key in self._touched
+        self._touched.add(key)
+        return seen
+
+    def refresh_shadow(self):
+        K.cast_bf16(self.master, self.shadow)
+        self.dirty_shadow = False
+
+    def load_state_dict_flat(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        missing = []
+        for n, p in self.params.items():
+            if n in sd:
+                p.data.copy_(sd[n].to(self.device, torch.float32))
+            else:
+                missing.append(n)
+        if strict and missing:
+            raise KeyError(f"missing parameters: {missing[:5]} ...")
+        self.refresh_shadow()

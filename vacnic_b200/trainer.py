@@ -1,0 +1,161 @@
+"""One VACNIC training step (TRAIN:253-374) on the B200-native model: forward, token CE, CoLaM margin
+loss against the frozen stock-BART guide, SECLA face-name loss, backward, (data-parallel gradient
+all-reduce), fused AdamW with the linear warm-up/decay schedule — optionally captured once as a CUDA
+graph and replayed, so that the ~2.5k kernel launches of a step cost no host time.
+
+Host-side work per step is: copy the batch into static device buffers, write the step's scalar
+hyper-parameters (lr and Adam bias corrections), replay.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import blocks as Bk
+from . import kernels as K
+from .modeling import VacnicBart, shift_tokens_right
+
+
+def linear_schedule(step: int, warmup: int, total: int) -> float:
+    """transformers.get_linear_schedule_with_warmup (TRAIN:102): multiplier applied to the base lr."""
+    if step < warmup:
+        return step / max(1, warmup)
+    return max(0.0, (total - step) / max(1, total - warmup))
+
+
+class TrainStep:
+    def __init__(self, model: VacnicBart, guide: Optional[VacnicBart], lr: float = 3e-5, weight_decay: float = 0.01,
+                 betas=(0.9, 0.999), eps: float = 1e-8, warmup_steps: int = 0, total_steps: int = 1_000_000,
+                 margin: float = 1.0, alpha: float = 0.5, secla_weight: float = 1.0, use_graph: bool = True,
+                 process_group=None):
+        self.model, self.guide = model, guide
+        self.cfg = model.cfg
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.warmup, self.total = warmup_steps, total_steps
+        self.margin, self.alpha, self.w_secla = margin, alpha, secla_weight
+        self.use_graph = use_graph
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        st = model.store
+        dev = st.device
+        self.m = torch.zeros_like(st.master)
+        self.v = torch.zeros_like(st.master)
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.step_no = 0
+        self.graph = None
+        self.static: Dict[str, torch.Tensor] = {}
+        self.losses: Dict[str, torch.Tensor] = {}
+        self.launches_per_step = 0
+        self._g_txt = torch.ones(1, device=dev)
+        self._g_margin = torch.full((1,), alpha, device=dev)
+        self._g_secla = torch.full((1,), secla_weight, device=dev)
+
+    # ------------------------------------------------------------------ the step body (capturable)
+    def _body(self, b: Dict[str, torch.Tensor]):
+        model, guide, cfg = self.model, self.guide, self.cfg
+        st = model.store
+        st.begin_step()
+        model.rt.rng.advance()
+        src, tgt = b["article_ids"], b["caption_ids"]
+        dec_in = b["decoder_input_ids"]
+        kw = dict(input_ids=src, attention_mask=b["src_mask"], decoder_input_ids=dec_in,
+                  image_features=b["image_features"], ce_targets=tgt)
+        if not cfg.only_image:
+            kw.update(face_features=b["face_emb"], face_mask=b["face_mask"], name_ids=b["names_art_ids"],
+                      name_mask=b["name_mask"])
+        out = model(**kw)
+        heads, grads = [out["loss"]], [self._g_txt]
+        losses = {"txt": out["loss"]}
+        if guide is not None:
+            with torch.no_grad():
+                gout = guide(input_ids=src, attention_mask=b["src_mask"], decoder_input_ids=dec_in)
+            margin = Bk.ColamFn.apply(out["decoder_hidden_states"][-1], gout["decoder_hidden_states"][-1], tgt, self.margin,
+                                      cfg.pad_token_id)
+            heads.append(margin); grads.append(self._g_margin)
+            losses["margin"] = margin
+        if not cfg.only_image:
+            enc = model.model.encoder
+            names = K.names_embed(b["names_ids"], st.w16(enc.embed_tokens_ner.weight), st.w16(enc.embed_positions_ner.weight),
+                                  enc.ln_emb_ner.g, enc.ln_emb_ner.b)
+            secla = Bk.SeclaFn.apply(out["hidden_states_face"], names)
+            heads.append(secla); grads.append(self._g_secla)
+            losses["secla"] = secla
+        torch.autograd.backward(heads, grads)
+        st.finish_backward()
+        if self.world > 1:
+            torch.distributed.all_reduce(st.grad, group=self.pg)  # sum; the 1/world mean is folded into hyper[7]
+        K.adamw(st.master, st.grad, self.m, self.v, st.shadow, self.hyper)
+        return losses
+
+    # ------------------------------------------------------------------ host side
+    @staticmethod
+    def prepare(batch: Dict[str, torch.Tensor], cfg) -> Dict[str, torch.Tensor]:
+        """Host-side derived inputs of the training loop (TRAIN:267-271): decoder inputs and pad masks."""
+        b = dict(batch)
+        b["decoder_input_ids"] = shift_tokens_right(batch["caption_ids"], cfg.pad_token_id, cfg.eos_token_id)
+        b["src_mask"] = (batch["article_ids"] != 1).to(torch.int64)
+        if "face_emb" in batch:
+            b["face_mask"] = (batch["face_emb"][:, :, -1] != 1).to(torch.int64)
+            b["name_mask"] = (batch["names_art_ids"] != 1).to(torch.int64)
+        return b
+
+    def _write_hyper(self):
+        self.step_no += 1
+        t = self.step_no
+        lr = self.lr * linear_schedule(t - 1, self.warmup, self.total)  # scheduler.step() follows optimizer.step()
+        h = self.hyper_host
+        h[0], h[1], h[2], h[3], h[4] = lr, self.betas[0], self.betas[1], self.eps, self.wd
+        h[5], h[6], h[7] = 1 - self.betas[0] ** t, 1 - self.betas[1] ** t, 1.0 / self.world
+        self.hyper.copy_(h, non_blocking=True)
+
+    def _load_static(self, b: Dict[str, torch.Tensor]):
+        for k, v in b.items():
+            if k not in self.static:
+                self.static[k] = torch.empty(v.shape, dtype=v.dtype, device=self.model.store.device)
+            if self.static[k].shape != v.shape:
+                raise ValueError(f"batch field {k} changed shape {tuple(self.static[k].shape)} -> {tuple(v.shape)}: "
+                                 "the captured step is shape-specialised; build one TrainStep per bucket")
+            self.static[k].copy_(v, non_blocking=True)
+
+    def step(self, batch: Dict[str, torch.Tensor], prepared: bool = False) -> Dict[str, torch.Tensor]:
+        """Run one optimisation step on a (host or device) batch; returns device scalars {txt, margin, secla}."""
+        b = batch if prepared else self.prepare(batch, self.cfg)
+        self.model.train()
+        if self.guide is not None:
+            self.guide.eval()
+        self._write_hyper()
+        if not self.use_graph:
+            dev = self.model.store.device
+            b = {k: v.to(dev, non_blocking=True) for k, v in b.items()}
+            c0 = K._l.launch_count()
+            self.losses = self._body(b)
+            self.launches_per_step = K._l.launch_count() - c0
+            return self.losses
+        self._load_static(b)
+        if self.graph is None:
+            # warm-up on a side stream (allocator, lazy kernel attribute setup), then capture
+            self.step_no -= 1
+            saved = (self.model.store.master.clone(), self.m.clone(), self.v.clone(), self.model.rt.rng.state.clone())
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._body(self.static)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            # the warm-up steps must not count as optimisation steps
+            self.model.store.master.copy_(saved[0]); self.m.copy_(saved[1]); self.v.copy_(saved[2])
+            self.model.rt.rng.state.copy_(saved[3])
+            self.model.store.refresh_shadow()
+            del saved
+            self.graph = torch.cuda.CUDAGraph()
+            c0 = K._l.launch_count()
+            with torch.cuda.graph(self.graph):
+                self.losses = self._body(self.static)
+            self.launches_per_step = K._l.launch_count() - c0
+            self._write_hyper()
+        self.graph.replay()
+        return self.losses
