@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the VACNIC hot path (BASELINE.json): BART-large VACNIC training step, bf16 compute,
+batch 16 per GPU, 1024-token article segments + 20-token ClipCap prefix, CoLaM (margin 1.0, alpha 0.5)
+against the frozen stock-BART guide, SECLA face-name loss, fused AdamW — synthetic NYTimes800k-shaped
+batches, random-init weights (no network for data or checkpoints).
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (sm_100a kernels through the C ABI)
+  python bench.py --impl reference [...]                    the reference algorithm on host cores (oracle port)
+  python bench.py --workload infer [...]                    beam-4 caption generation instead of training
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PEAKS_FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    d = dict(PEAKS_FALLBACK)
+    d["_source"] = "fallback"
+    return d
+
+
+# ----------------------------------------------------------------------------------------- FLOP model
+def train_flops_per_sample(cfg, L, T, with_guide=True):
+    """Algorithmic FLOPs (multiply-add = 2) per sample of one training step, SURVEY.md §8(d):
+    backward = 2 x forward, attention recompute not counted, causal half not discounted."""
+    d, f, P, G, F, E = cfg.d_model, cfg.ffn, cfg.prompt_size, cfg.max_ner_type_len_gt, 4, cfg.max_ner_type_len
+    full = not cfg.only_image
+    Gk = G if full else 0
+    enc = 8 * L * d * d + 4 * L * L * d + 4 * L * d * d + 4 * (P + Gk) * d * d + 4 * L * (P + Gk) * d + 4 * L * d * f + 4 * P * d * f
+    if full:
+        enc += 4 * F * d * 3072 + 4 * E * d * d + 4 * (F + E) * d * d + 4 * E * (F + E) * d + 2 * d * E * E + 2 * d * E * G
+    dec = 8 * T * d * d + 4 * T * T * d + 4 * T * d * d + 4 * L * d * d + 4 * T * L * d + 4 * T * d * f
+    head = 2 * T * d * cfg.vocab
+    prefix = 2 * 768 * 384 * P + 2 * 384 * P * 768 * P + (2 * P * 768 * d if d == 1024 else 0) + (2 * F * 512 * d if full else 0)
+    fwd = cfg.enc_layers * enc + cfg.dec_layers * dec + head + prefix
+    stock_enc = 8 * L * d * d + 4 * L * L * d + 4 * L * d * f
+    guide = cfg.enc_layers * stock_enc + cfg.dec_layers * dec
+    return 3 * fwd + (guide if with_guide else 0), fwd, guide
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.stop = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+        while not self.stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, attr in names.items():
+                    if r & getattr(nv, attr, 0):
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.nv is not None:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_train(threads: int, steps: int, warmup: int, large: bool = True):
+    """The reference algorithm (oracle/model.py, pinned to the reference classes) on host cores: one
+    training step = forward, CE + CoLaM (frozen guide) + SECLA, backward, torch AdamW.  Bounded sample:
+    BART-large config-2 shapes at batch 1 (the per-sample cost of the batch-16 workload)."""
+    from oracle import model as OM
+    from vacnic_b200 import spec, synthetic
+    torch.set_num_threads(threads)
+    cfg = spec.bart_large()
+    gcfg = spec.VacnicConfig(stock=True)
+    sd = spec.test_state_dict(cfg, 1)
+    for k in sd:
+        if sd[k].is_floating_point() and k != "final_logits_bias" and k not in spec.TIED_TO_SHARED:
+            sd[k].requires_grad_(True)
+    for k in spec.TIED_TO_SHARED:
+        sd[k] = sd["model.shared.weight"]
+    gsd = spec.test_state_dict(gcfg, 2)
+    params = [v for k, v in sd.items() if v.requires_grad and k not in spec.TIED_TO_SHARED]
+    opt = torch.optim.AdamW(params, lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    Bs = 1
+    times = []
+    for i in range(warmup + steps):
+        batch = synthetic.make_batch(B=Bs, L=1024, T=64, seed=100 + i, full_length=True)
+        t0 = time.perf_counter()
+        res = OM.training_losses(sd, cfg.as_dict(), gsd, gcfg.as_dict(), batch, margin=1.0, alpha=0.5)
+        res["loss"].backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return Bs / (ms / 1e3), ms, f"BART-large config-2 shapes (L=1024, T=64, P=20, F=4, N=8), batch {Bs} per step, fp32, {len(times)} timed step(s)"
+
+
+# ----------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--article-len", type=int, default=1024)
+    ap.add_argument("--caption-len", type=int, default=64)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small", action="store_true", help="BART-base config-1 shapes (debug)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    metric = "train_samples_per_sec" if args.workload == "train" else "beam4_captions_per_sec"
+    unit = "samples/s" if args.workload == "train" else "captions/s"
+    config = {"workload": "BART-large VACNIC full-model training step (BASELINE.json configs[1]): bf16 compute, "
+                          f"batch {args.batch}/GPU, L={args.article_len} article tokens + P=20 ClipCap prefix, T={args.caption_len}, "
+                          "CE + 0.5*CoLaM(margin 1.0, frozen BART-large guide) + SECLA(F=4,N=8), dropout 0.1, AdamW",
+              "global_batch": args.batch * world, "parallelism": f"dp{world}",
+              "l2": "working set per step (>=1.8 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        steps = max(1, min(args.steps, 2))
+        val, ms, sample = cpu_reference_train(threads, steps, min(args.warmup, 1))
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the VACNIC hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+        pg = torch.distributed.group.WORLD
+
+    from vacnic_b200 import kernels as K
+    from vacnic_b200 import spec, synthetic
+    from vacnic_b200.modeling import VacnicBart
+    from vacnic_b200.trainer import TrainStep
+
+    if args.small:
+        cfg = spec.bart_base()
+        gcfg = spec.bart_base(stock=True)
+    else:
+        cfg = spec.bart_large()
+        gcfg = spec.VacnicConfig(stock=True)
+    B, L, T = args.batch, args.article_len, args.caption_len
+    model = VacnicBart(cfg, device=dev, p_drop=0.1, seed=684331)          # seed of run_full_train.sh:2
+    guide = VacnicBart(gcfg, device=dev, p_drop=0.0, seed=7, frozen=True)
+    ts = TrainStep(model, guide, lr=3e-5, weight_decay=0.01, warmup_steps=100, total_steps=100000, margin=1.0, alpha=0.5,
+                   use_graph=not args.no_graph, process_group=pg)
+
+    n_batches = 4
+    host = [TrainStep.prepare(synthetic.make_batch(B=B, L=L, T=T, seed=1000 * rank + i), cfg) for i in range(n_batches)]
+    host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def run(batches, steps, read_loss):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        last = None
+        for i in range(steps):
+            losses = ts.step(batches[i % len(batches)], prepared=True)
+            if read_loss:
+                last = float(losses["txt"].item())  # device -> host read of the step's result
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    for i in range(max(3, args.warmup)):
+        ts.step(devb[i % n_batches], prepared=True)
+    torch.cuda.synchronize()
+    c0 = K._l.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms_dev, _ = run(devb, args.steps, read_loss=False)
+    eager_launches = K._l.launch_count() - c0
+    launches = ts.launches_per_step * args.steps if ts.use_graph else eager_launches
+    ms_e2e, last_loss = run(host, args.steps, read_loss=True)
+
+    value = B * world * args.steps / (ms_dev / 1e3)
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+    pk = peaks()
+    flops_sample, fwd_f, guide_f = train_flops_per_sample(cfg, L, T)
+    step_tflops = flops_sample * B / 1e12
+
+    # ---- roofline of the dominant kernel (gemm_sm100_kernel): one eager, event-instrumented step
+    roof = None
+    if rank == 0:
+        eager = TrainStep(model, guide, use_graph=False, process_group=None)
+        eager.m, eager.v = ts.m, ts.v
+        eager.step(devb[0], prepared=True)  # warm the eager path
+        torch.cuda.synchronize()
+        K.PROFILE = []
+        eager.step(devb[1], prepared=True)
+        torch.cuda.synchronize()
+        prof, K.PROFILE = K.PROFILE, None
+        gf = sum(p[0] for p in prof)
+        gms = sum(p[1].elapsed_time(p[2]) for p in prof)
+        ach = gf / 1e12 / (gms / 1e3) if gms > 0 else 0.0
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05/TMEM/TMA batched bf16 GEMM)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk["_source"] + " sustained",
+                "launches_per_step": len(prof), "gemm_ms_per_step": gms, "gemm_share_of_step": gms / (ms_dev / args.steps),
+                "algorithmic_tflop_per_step": step_tflops, "step_mfu": step_tflops / (ms_dev / args.steps / 1e3) / peak}
+    if world > 1:
+        torch.distributed.barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, ms, sample = cpu_reference_train(threads, 1, 0)
+        cpu = {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clk.summary(),
+                "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                        "last_txt_loss": last_loss},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -11,6 +11,9 @@ from .lib import (ACT_GELU, ACT_NONE, ACT_TANH, DT_BF16, DT_F32, MASK_CAUSAL, MA
                   MASK_NONE, GemmDesc, check, lib, ptr, stream_ptr)
 
 
+PROFILE = None  # set to a list to collect (flops, start_event, end_event, shape) per GEMM launch
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -76,6 +79,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     if out.dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("gemm out must be bf16 or fp32")
     d.act, d.dact, d.accumulate, d.tile_n = act, dact, int(accumulate), tile_n
+    if PROFILE is not None:  # bench.py roofline pass: CUDA events around every launch, on the launching stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib().vacnic_gemm(C.byref(d), stream_ptr()), "vacnic_gemm")
+        e1.record()
+        PROFILE.append((2.0 * M * N * K * nb0 * nb1, e0, e1, (M, N, K, nb0 * nb1)))
+        return out
     check(lib().vacnic_gemm(C.byref(d), stream_ptr()), "vacnic_gemm")
     return out
 
