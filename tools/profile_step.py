@@ -34,3 +34,19 @@ ts.step(b, prepared=True)
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_pop()
 print("total launches", lib.launch_count(), "losses", {k: float(v) for k, v in ts.losses.items()}, flush=True)
+
+if os.environ.get("GEMM_SHAPES"):
+    import collections
+    from vacnic_b200 import kernels as K
+    K.PROFILE = []
+    ts.step(b, prepared=True)
+    torch.cuda.synchronize()
+    prof, K.PROFILE = K.PROFILE, None
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for fl, e0, e1, shape in prof:
+        a = agg[shape]
+        a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl
+    tot = sum(a[1] for a in agg.values())
+    print(f"GEMM total {tot:.2f} ms, {sum(a[2] for a in agg.values())/1e12:.2f} TFLOP")
+    for shape, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+        print(f"{a[1]:8.3f} ms {100*a[1]/tot:5.1f}% n={a[0]:4d} M,N,K,batch={shape} {a[2]/1e9/a[1]:8.1f} TF/s")
