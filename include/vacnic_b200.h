@@ -187,6 +187,48 @@ int vacnic_secla_fwd(const float* names, const void* face, float* workspace, flo
 int vacnic_secla_bwd(const float* workspace, const float* names, const float* gscale, float coef, void* dface,
                      int32_t B, int32_t N, int32_t F, int32_t d, int32_t accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Cached decoding + device-side greedy / beam search (generate() call sites INFER:798,867,
+ * TRAIN:513-520; hooks MFULL:2023-2074; cached attention branches MFULL:474-501).  The search
+ * algorithm is transformers' `_beam_search` / greedy `_sample` (third-party, restated in
+ * oracle/generate.py).  Rows r = caption * beams + beam.  Every kernel reads the current sequence
+ * length from the device integer `cur_len`, so one captured CUDA graph serves every step.
+ * Ping-pong state buffers hold two copies; step t reads copy (t & 1) and writes copy ((t+1) & 1).
+ * ------------------------------------------------------------------------------------------ */
+/* y[r] = LN(tok[seq[r][cur_len-1]] + pos[cur_len-1 + pos_offset])  (MFULL:1552-1563, cached).
+ * seq: int32 [R][maxT] (pingpong = 0) or [2][R][maxT] (pingpong = 1). */
+int vacnic_decode_embed_ln(const int32_t* seq, const int32_t* cur_len, const void* tok, const void* pos,
+                           const float* gamma, const float* beta, void* y, int32_t R, int32_t maxT, int32_t d,
+                           int32_t pos_offset, int32_t pingpong, float eps, void* stream);
+/* Self-attention of the newest token over the cache (MFULL:490-495,509-563).  qkv bf16 [R][3d] in
+ * [k|v|q] order; the new k/v are appended to kcache/vcache [R][maxT][d] at position cur_len-1; position
+ * s < cur_len-1 is read from row anc[(cur_len&1)][r][s] (null anc = own row: greedy).  out bf16 [R][d]. */
+int vacnic_decode_self_attn(const void* qkv, void* kcache, void* vcache, const int32_t* anc, const int32_t* cur_len,
+                            void* out, int32_t R, int32_t H, int32_t head_dim, int32_t maxT, void* stream);
+/* Cross-attention of the nq beams of each caption over its L encoder keys (MFULL:474-479): q bf16
+ * row (c*nq+i) at q + row*ldq; k row (c*L+s) at kv + row*ldkv, v at + v_off; key_mask uint8 [captions][L]
+ * (1 = attend) and key_len int32 [captions] (keys >= key_len are skipped; see vacnic_mask_key_len) may
+ * be null.  out row stride ldo. */
+int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t v_off,
+                             const uint8_t* key_mask, const int32_t* key_len, void* out, int64_t ldo, int32_t captions,
+                             int32_t nq, int32_t L, int32_t H, int32_t head_dim, void* stream);
+int vacnic_mask_key_len(const uint8_t* mask, int32_t* key_len, int32_t B, int32_t L, void* stream);
+/* Per row of fp32 logits [rows][ld]: log-softmax statistics and the K best entries, sorted (ties: lower
+ * index).  top_lp[r][k] = logit - logsumexp(row). */
+int vacnic_decode_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, int32_t K, float* top_lp,
+                       int32_t* top_idx, void* stream);
+/* One `_beam_search` iteration (top-2*beams continuations, running beams, finished set with
+ * score / len^length_penalty, early-stop heuristic for early_stopping=False, forced EOS at
+ * max_len-1).  flags int32 [maxT][2]: flags[t] = {some caption can still improve, some candidate was
+ * not stopped}; the host continues while both are set. */
+int vacnic_beam_step(const float* top_lp, const int32_t* top_idx, int32_t* run_seq, int32_t* run_anc, float* run_score,
+                     int32_t* fin_seq, float* fin_score, int32_t* fin_len, uint8_t* fin_flag, uint8_t* unsat,
+                     int32_t* flags, const int32_t* cur_len, int32_t captions, int32_t beams, int32_t maxT,
+                     int32_t max_len, int32_t eos, int32_t V, float length_penalty, void* stream);
+int vacnic_greedy_step(const int32_t* top_idx, int32_t* seq, uint8_t* unfinished, int32_t* flags, const int32_t* cur_len,
+                       int32_t rows, int32_t maxT, int32_t max_len, int32_t eos, int32_t pad, void* stream);
+int vacnic_advance_len(int32_t* cur_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

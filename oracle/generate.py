@@ -19,8 +19,14 @@ import torch.nn.functional as F
 from . import model as M
 
 
-def _encode(sd, cfg, batch_inputs):
-    return M.encoder_forward(sd, cfg, **batch_inputs)
+# Test-only robustness probe: when set to (amplitude, torch.Generator), every next-token logit gets uniform
+# noise in [-amplitude, amplitude].  tests/golden/make_golden.py uses it to keep only inputs whose decoded ids
+# do not depend on perturbations of the size of the bf16 logit tolerance ("margin-vetted" goldens).
+LOGIT_NOISE = None
+
+
+def _encode(sd, cfg, batch_inputs, enc=None):
+    return enc if enc is not None else M.encoder_forward(sd, cfg, **batch_inputs)
 
 
 def _step_logits(sd, cfg, ids, enc_out, enc_mask, past):
@@ -30,7 +36,11 @@ def _step_logits(sd, cfg, ids, enc_out, enc_mask, past):
         dec = M.decoder_forward(sd, cfg, ids, enc_out, enc_mask, past=None, use_cache=True)
     else:
         dec = M.decoder_forward(sd, cfg, ids[:, -1:], enc_out, enc_mask, past=past, use_cache=True)
-    return M.lm_logits(sd, dec["last_hidden_state"][:, -1, :]).float(), dec["past_key_values"]
+    logits = M.lm_logits(sd, dec["last_hidden_state"][:, -1, :]).float()
+    if LOGIT_NOISE is not None:
+        amp, gen = LOGIT_NOISE
+        logits = logits + (torch.rand(logits.shape, generator=gen) * 2 - 1).to(logits.device) * amp
+    return logits, dec["past_key_values"]
 
 
 def _forced_eos(log_probs, cur_len, max_length, eos):
@@ -42,9 +52,9 @@ def _forced_eos(log_probs, cur_len, max_length, eos):
 
 
 @torch.no_grad()
-def greedy(sd, cfg, enc_inputs, max_length=50):
+def greedy(sd, cfg, enc_inputs, max_length=50, enc=None):
     eos, pad = cfg["eos_token_id"], cfg["pad_token_id"]
-    enc = _encode(sd, cfg, enc_inputs)
+    enc = _encode(sd, cfg, enc_inputs, enc)
     enc_out, enc_mask = enc["last_hidden_state"], enc_inputs["attention_mask"]
     B = enc_out.shape[0]
     ids = torch.full((B, 1), cfg["decoder_start_token_id"], dtype=torch.long, device=enc_out.device)
@@ -69,19 +79,33 @@ def _gather_beams(t, idx):
 
 
 @torch.no_grad()
-def beam_search(sd, cfg, enc_inputs, num_beams=4, max_length=50, length_penalty=2.0):
+def beam_search(sd, cfg, enc_inputs, num_beams=4, max_length=50, length_penalty=2.0, enc=None):
     """transformers 5.5.0 `_beam_search` (vectorised), early_stopping=False."""
-    eos, pad = cfg["eos_token_id"], cfg["pad_token_id"]
-    V = cfg["vocab"]
-    enc = _encode(sd, cfg, enc_inputs)
+    enc = _encode(sd, cfg, enc_inputs, enc)
     enc_out = enc["last_hidden_state"].repeat_interleave(num_beams, dim=0)
     enc_mask = enc_inputs["attention_mask"].repeat_interleave(num_beams, dim=0)
-    dev = enc_out.device
     B = enc_out.shape[0] // num_beams
+    state = {"past": None}
+
+    def step_fn(flat_ids, reorder):
+        # g. reorder the self-attention cache by the source beam of each surviving running beam
+        if reorder is not None:
+            state["past"] = [(l[0].index_select(0, reorder), l[1].index_select(0, reorder), l[2], l[3]) for l in state["past"]]
+        logits, state["past"] = _step_logits(sd, cfg, flat_ids, enc_out, enc_mask, state["past"])
+        return logits
+
+    return beam_search_core(step_fn, B, cfg["vocab"], enc_out.device, num_beams, max_length, length_penalty,
+                            cfg["eos_token_id"], cfg["pad_token_id"], cfg["decoder_start_token_id"])
+
+
+@torch.no_grad()
+def beam_search_core(step_fn, B, V, dev, num_beams, max_length, length_penalty, eos, pad, start):
+    """The search loop proper.  `step_fn(flat_ids [B*beams, cur_len], reorder or None)` returns fp32 next-token
+    logits [B*beams, V]; `reorder` is the beam permutation chosen by the previous iteration."""
     K = 2 * num_beams  # beams_to_keep = max(2, 1 + n_eos) * num_beams
     cur_len = prompt = 1
     running = torch.full((B, num_beams, max_length), pad, dtype=torch.long, device=dev)
-    running[:, :, 0] = cfg["decoder_start_token_id"]
+    running[:, :, 0] = start
     sequences = running.clone()
     running_scores = torch.zeros(B, num_beams, device=dev)
     running_scores[:, 1:] = -1e9
@@ -91,10 +115,10 @@ def beam_search(sd, cfg, enc_inputs, num_beams=4, max_length=50, length_penalty=
     run_idx = torch.full((B, num_beams, max_length - 1), -1, dtype=torch.int32, device=dev)
     beam_idx_out = run_idx.clone()
     top_mask = torch.cat((torch.ones(num_beams, dtype=torch.bool), torch.zeros(K - num_beams, dtype=torch.bool))).to(dev)
-    past = None
+    bidx = None
     while True:
         flat = running[:, :, :cur_len].reshape(B * num_beams, cur_len)
-        logits, past = _step_logits(sd, cfg, flat, enc_out, enc_mask, past)
+        logits = step_fn(flat, bidx)
         lp = _forced_eos(F.log_softmax(logits, dim=-1), cur_len, max_length, eos)
         lp = (lp.view(B, num_beams, V) + running_scores[:, :, None]).reshape(B, num_beams * V)
         # c. top-K continuations
@@ -124,9 +148,7 @@ def beam_search(sd, cfg, enc_inputs, num_beams=4, max_length=50, length_penalty=
         sel = torch.topk(m_sc, k=num_beams)[1]
         sequences, beam_scores = _gather_beams(m_seq, sel), _gather_beams(m_sc, sel)
         beam_idx_out, finished = _gather_beams(m_idx, sel), _gather_beams(m_fin, sel)
-        # g. reorder the self-attention cache by the source beam of each surviving running beam
         bidx = run_idx[..., cur_len - prompt].reshape(-1).long()
-        past = [(l[0].index_select(0, bidx), l[1].index_select(0, bidx), l[2], l[3]) for l in past]
         cur_len += 1
         best_possible = running_scores[:, :1] / ((cur_len - prompt) ** length_penalty)
         worst_fin = torch.where(finished, beam_scores.min(dim=1, keepdim=True)[0], torch.tensor(-1.0e9, device=dev))

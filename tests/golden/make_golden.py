@@ -129,6 +129,39 @@ def ref_losses(m, guide, batch, cfg, margin=1.0, alpha=0.5, w=1.0):
     return res
 
 
+def enc_inputs_of(cfg, batch):
+    src = batch["article_ids"]
+    d = dict(input_ids=src, attention_mask=OM.src_mask(src), image_features=batch["image_features"])
+    if not cfg.only_image:
+        face = batch["face_emb"]
+        d.update(face_features=face, face_mask=OM.src_mask(face[:, :, -1]), name_ids=batch["names_art_ids"],
+                 name_mask=OM.src_mask(batch["names_art_ids"]))
+    return d
+
+
+def vet_generation(sd, cfg, batch, max_len, amp, trials=10):
+    """True when greedy and beam-4 ids of the (reference-pinned) oracle do not change under uniform logit noise of
+    amplitude `amp` (= the bf16 logit tolerance of the GPU tests) in any of `trials` draws."""
+    inp = enc_inputs_of(cfg, batch)
+    with torch.no_grad():
+        enc = OM.encoder_forward(sd, cfg.as_dict(), **inp)
+    OG.LOGIT_NOISE = None
+    g0 = OG.greedy(sd, cfg.as_dict(), inp, max_length=max_len, enc=enc)
+    b0, _ = OG.beam_search(sd, cfg.as_dict(), inp, num_beams=4, max_length=max_len, length_penalty=2.0, enc=enc)
+    try:
+        for t in range(trials):
+            OG.LOGIT_NOISE = (amp, torch.Generator().manual_seed(1000 + t))
+            g = OG.greedy(sd, cfg.as_dict(), inp, max_length=max_len, enc=enc)
+            if g.shape != g0.shape or not bool((g == g0).all()):
+                return False
+            b, _ = OG.beam_search(sd, cfg.as_dict(), inp, num_beams=4, max_length=max_len, length_penalty=2.0, enc=enc)
+            if b.shape != b0.shape or not bool((b == b0).all()):
+                return False
+    finally:
+        OG.LOGIT_NOISE = None
+    return True
+
+
 def close(a, b, tol, what):
     err = (a - b).abs().max().item()
     assert err <= tol, f"{what}: max abs err {err} > {tol}"
@@ -147,7 +180,20 @@ def main():
         cfg = spec.VacnicConfig(**ckw)
         sd = spec.test_state_dict(cfg, wseed, lm_scale=lm_scale)
         sd["final_logits_bias"][0, cfg.eos_token_id] = eos_bias
-        batch = synthetic.make_batch(**bkw)
+        # margin vetting: walk the batch seed until the decoded ids are robust to the bf16 logit tolerance
+        max_len = 16 if name != "config1_base" else 24
+        # bf16 logit errors measured on B200: max-abs ~1e-2 * lm_scale over all 50k logits, sigma ~2e-3 * lm_scale;
+        # vet with uniform noise of amplitude 6.25e-3 * lm_scale (sigma 3.6e-3 * lm_scale) in 10 independent draws
+        amp = 6.25e-3 * max(1.0, lm_scale)
+        bkw = dict(bkw)
+        for attempt in range(3000):
+            batch = synthetic.make_batch(**bkw)
+            if vet_generation(sd, cfg, batch, max_len, amp):
+                break
+            bkw["seed"] += 1000
+        else:
+            raise RuntimeError(name + ": no margin-robust batch seed found")
+        print(name, "margin-vetted batch seed", bkw["seed"], "after", attempt + 1, "attempt(s), amp", amp, flush=True)
         m = build_reference(cfg, sd)
         guide, gcfg, gsd = build_guide(cfg, wseed + 100)
         # ---- reference forward + loss block (with grad, for gradient goldens)
@@ -181,7 +227,6 @@ def main():
                              name_mask=OM.src_mask(batch["names_art_ids"]))
                 kw.update(extra, add_ner_ffn=True)
                 enc_in.update(extra)
-            max_len = 16 if name != "config1_base" else 24
             with torch.no_grad():
                 ids_g = m.generate(**kw, num_beams=1, max_length=max_len, do_sample=False)
                 ids_b = m.generate(**kw, num_beams=4, max_length=max_len, length_penalty=2.0)
@@ -191,7 +236,7 @@ def main():
             ob, _ = OG.beam_search(sd, cfg.as_dict(), enc_in, num_beams=4, max_length=max_len, length_penalty=2.0)
             assert og.shape == ids_g.shape and bool((og == ids_g).all()), (name, "greedy ids differ", og, ids_g)
             assert ob.shape == ids_b.shape and bool((ob == ids_b).all()), (name, "beam ids differ", ob, ids_b)
-            gen = dict(greedy_ids=ids_g, beam4_ids=ids_b, max_length=max_len)
+            gen = dict(greedy_ids=ids_g, beam4_ids=ids_b, max_length=max_len, vetted_logit_noise=amp)
             print(name, "greedy", ids_g.tolist(), "beam4", ids_b.tolist())
         # ---- fixture
         gcols = torch.Generator().manual_seed(1234)

@@ -1,0 +1,746 @@
+// Cached single-token decoding and device-side greedy / beam search for the VACNIC caption generator
+// (generation hooks MFULL:2023-2074, cached BartAttention branches MFULL:474-501, decoder embedding
+// MFULL:1552-1563; the search loop itself is transformers' `_beam_search` / greedy `_sample`, the
+// algorithm restated in oracle/generate.py and pinned to the real generate()).
+//
+// Everything here is HBM / latency bound.  All kernels read the current sequence length from a DEVICE
+// integer (`cur_len`), so that ONE captured CUDA graph of a decoding step is replayed for every step.
+//
+// Decode state layout (rows r = caption * beams + beam, R rows in total):
+//   self K/V cache  [R][maxT][d] bf16 per layer, written once per (row, position) and NEVER reordered:
+//                   the beam search keeps an ancestry table anc[R][maxT] (int32, transformers'
+//                   `running_beam_indices`) and attention gathers position s from row anc[r][s];
+//   cross K/V       [captions * L][2d] bf16 per layer (k | v), ONE copy per caption shared by its beams
+//                   (the reference keeps `beams` identical copies, MFULL:2066-2074);
+//   beam state      ping-pong buffers indexed by (cur_len & 1): running sequences, ancestry, finished set.
+#include <float.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x[r] = LN(tok[seq[r][cur_len-1]] + pos[cur_len-1 + pos_offset])      (MFULL:1552-1563 with a cache)
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+decode_embed_ln_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ cur_len_p,
+                       const __nv_bfloat16* __restrict__ tok, const __nv_bfloat16* __restrict__ pos,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                       int R, int maxT, int d, int pos_offset, int pingpong, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int t = *cur_len_p;
+  const int32_t* s = seq + (pingpong ? static_cast<long long>(t & 1) * R * maxT : 0);
+  const long long id = s[static_cast<long long>(row) * maxT + t - 1];
+  const uint4* tp = reinterpret_cast<const uint4*>(tok + id * d);
+  const uint4* pp = reinterpret_cast<const uint4*>(pos + static_cast<long long>(t - 1 + pos_offset) * d);
+  float v[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    float a[8], b[8];
+    unpack8f(__ldg(tp + lane + 32 * j), a);
+    unpack8f(__ldg(pp + lane + 32 * j), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      // the reference adds two fp32 tensors; here both tables are bf16 shadows, summed in fp32
+      v[j][e] = a[e] + b[e];
+      sum += v[j][e];
+    }
+  }
+  const float mean = warp_sum(sum) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float c = v[j][e] - mean;
+      q += c * c;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  uint4* yp = reinterpret_cast<uint4*>(y + static_cast<long long>(row) * d);
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * __ldg(gamma + vi * 8 + e) + __ldg(beta + vi * 8 + e);
+    uint4 u;
+    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+    u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+    yp[vi] = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cached causal self-attention of the newest token (MFULL:490-495 cache branch + :509-563).
+// grid (H, R), 64 threads, head_dim == 64.  qkv row = [k | v | q] (fused projection order).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxT = 256;
+
+__global__ void __launch_bounds__(64)
+decode_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache,
+                        __nv_bfloat16* __restrict__ vcache, const int32_t* __restrict__ anc,
+                        const int32_t* __restrict__ cur_len_p, __nv_bfloat16* __restrict__ out, int R, int maxT, int d,
+                        float scale) {
+  const int h = blockIdx.x, r = blockIdx.y, j = threadIdx.x;
+  const int t = *cur_len_p;
+  const int pos = t - 1;
+  __shared__ float qs[64], kcur[64], vcur[64], sc[kMaxT], red[2];
+  const __nv_bfloat16* row = qkv + static_cast<long long>(r) * 3 * d + h * 64;
+  const __nv_bfloat16 kb = row[j], vb_ = row[d + j];
+  qs[j] = __bfloat162float(row[2 * d + j]) * scale;
+  kcur[j] = __bfloat162float(kb);
+  vcur[j] = __bfloat162float(vb_);
+  const long long self_off = (static_cast<long long>(r) * maxT + pos) * d + h * 64 + j;
+  kcache[self_off] = kb;
+  vcache[self_off] = vb_;
+  __syncthreads();
+  const int32_t* an = anc ? anc + static_cast<long long>(t & 1) * R * maxT + static_cast<long long>(r) * maxT : nullptr;
+  float mx = -INFINITY;
+  for (int s = j; s <= pos; s += 64) {
+    float dot = 0.f;
+    if (s == pos) {
+#pragma unroll
+      for (int e = 0; e < 64; ++e) dot += qs[e] * kcur[e];
+    } else {
+      const int src = an ? an[s] : r;
+      const uint4* kp = reinterpret_cast<const uint4*>(kcache + (static_cast<long long>(src) * maxT + s) * d + h * 64);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float f[8];
+        unpack8f(__ldg(kp + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dot += qs[c * 8 + e] * f[e];
+      }
+    }
+    sc[s] = dot;
+    mx = fmaxf(mx, dot);
+  }
+  mx = warp_max(mx);
+  if ((j & 31) == 0) red[j >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(red[0], red[1]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int s = j; s <= pos; s += 64) {
+    const float e = __expf(sc[s] - mx);
+    sc[s] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if ((j & 31) == 0) red[j >> 5] = sum;
+  __syncthreads();
+  const float inv = 1.f / (red[0] + red[1]);
+  float acc = 0.f;
+  for (int s = 0; s < pos; ++s) {
+    const int src = an ? an[s] : r;
+    acc += sc[s] * __bfloat162float(vcache[(static_cast<long long>(src) * maxT + s) * d + h * 64 + j]);
+  }
+  acc += sc[pos] * vcur[j];
+  out[static_cast<long long>(r) * d + h * 64 + j] = __float2bfloat16_rn(acc * inv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-attention of NQ query rows (the beams of one caption) over that caption's L cached keys
+// (MFULL:474-479 cache branch).  grid (H, captions), 128 threads; two streaming passes: K -> scores in
+// shared memory -> exact max-subtracted softmax -> V.  Keys at or beyond key_len[c] and keys whose mask
+// byte is 0 contribute exactly 0 in the reference (exp(finfo.min - max) == 0), so they are skipped.
+// ------------------------------------------------------------------------------------------------
+template <int NQ>
+__global__ void __launch_bounds__(128)
+decode_cross_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kv,
+                         long long ldkv, int v_off, const uint8_t* __restrict__ key_mask,
+                         const int32_t* __restrict__ key_len, __nv_bfloat16* __restrict__ out, long long ldo, int nq,
+                         int L, float scale) {
+  extern __shared__ float dsm[];
+  float* sc = dsm;                 // [NQ][L]
+  float* red = dsm + NQ * L;       // [4 warps][NQ][64] partial outputs (also used for max / sum)
+  __shared__ float stat[2][NQ][4];
+  const int h = blockIdx.x, c = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 3, dl = lane & 7;
+  const int Lc = key_len ? min(L, key_len[c]) : L;
+  const uint8_t* mk = key_mask ? key_mask + static_cast<long long>(c) * L : nullptr;
+  float qf[NQ][8];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    if (i < nq) {
+      unpack8f(__ldg(reinterpret_cast<const uint4*>(q + (static_cast<long long>(c) * nq + i) * ldq + h * 64) + dl), qf[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) qf[i][e] *= scale;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) qf[i][e] = 0.f;
+    }
+  }
+  const __nv_bfloat16* kbase = kv + static_cast<long long>(c) * L * ldkv + h * 64;
+  // ---- pass 1: scores
+  constexpr int UN = 4;
+  for (int kb = 0; kb < Lc; kb += 16 * UN) {  // block-uniform trip count: the shuffles below need full warps
+    const int k0 = kb + warp * 4 + g;
+    uint4 kk[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int key = k0 + 16 * u;
+      kk[u] = key < Lc ? __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<long long>(key) * ldkv) + dl)
+                       : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int key = k0 + 16 * u;
+      float f[8];
+      unpack8f(kk[u], f);
+      float dot[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += qf[i][e] * f[e];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        dot[i] = s;
+      }
+      if (dl == 0 && key < Lc) {
+        const bool ok = mk == nullptr || mk[key] != 0;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) sc[i * L + key] = ok ? dot[i] : -INFINITY;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- exact softmax statistics per query
+  float mx[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    float m = -INFINITY;
+    for (int k = threadIdx.x; k < Lc; k += 128) m = fmaxf(m, sc[i * L + k]);
+    m = warp_max(m);
+    if (lane == 0) stat[0][i][warp] = m;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    mx[i] = fmaxf(fmaxf(stat[0][i][0], stat[0][i][1]), fmaxf(stat[0][i][2], stat[0][i][3]));
+    float s = 0.f;
+    for (int k = threadIdx.x; k < Lc; k += 128) {
+      const float e = __expf(sc[i * L + k] - mx[i]);
+      sc[i * L + k] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    if (lane == 0) stat[1][i][warp] = s;
+  }
+  __syncthreads();
+  // ---- pass 2: P V
+  float o[NQ][8];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[i][e] = 0.f;
+  const __nv_bfloat16* vbase = kbase + v_off;
+  for (int kb = 0; kb < Lc; kb += 16 * UN) {
+    const int k0 = kb + warp * 4 + g;
+    uint4 vv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int key = k0 + 16 * u;
+      vv[u] = key < Lc ? __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<long long>(key) * ldkv) + dl)
+                       : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int key = k0 + 16 * u;
+      if (key < Lc) {
+        float f[8];
+        unpack8f(vv[u], f);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float p = sc[i * L + key];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[i][e] += p * f[e];
+        }
+      }
+    }
+  }
+  // reduce over the 4 key sub-groups of the warp, then over the 4 warps
+#pragma unroll
+  for (int i = 0; i < NQ; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = o[i][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      o[i][e] = v;
+    }
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < NQ; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[(warp * NQ + i) * 64 + dl * 8 + e] = o[i][e];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nq * 64; idx += 128) {
+    const int i = idx >> 6, dim = idx & 63;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) v += red[(w * NQ + i) * 64 + dim];
+    const float s = stat[1][i][0] + stat[1][i][1] + stat[1][i][2] + stat[1][i][3];
+    out[(static_cast<long long>(c) * nq + i) * ldo + h * 64 + dim] = __float2bfloat16_rn(v / s);
+  }
+}
+
+// key_len[b] = 1 + index of the last non-zero mask byte (0 when the row is fully masked)
+__global__ void mask_key_len_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ out, int B, int L) {
+  const int b = blockIdx.x;
+  int last = 0;
+  for (int k = threadIdx.x; k < L; k += blockDim.x)
+    if (mask[static_cast<long long>(b) * L + k]) last = max(last, k + 1);
+  last = __reduce_max_sync(0xffffffffu, last);
+  __shared__ int red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = max(m, red[w]);
+    out[b] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-row log-softmax statistics + top-K of the LM-head logits (the `log_softmax` and the row-local part
+// of `torch.topk(..., 2*num_beams)` of _beam_search; greedy uses K = 1).  One CTA per row, the row is
+// staged once in shared memory.  Ties: lower vocabulary index first.
+// ------------------------------------------------------------------------------------------------
+struct ValIdx {
+  float v;
+  int i;
+};
+__device__ __forceinline__ bool better(float v, int i, float w, int k) { return v > w || (v == w && i < k); }
+__device__ __forceinline__ ValIdx warp_argmax(ValIdx a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, a.v, o);
+    const int k = __shfl_xor_sync(0xffffffffu, a.i, o);
+    if (better(w, k, a.v, a.i)) { a.v = w; a.i = k; }
+  }
+  return a;
+}
+
+constexpr int kTopThreads = 1024;
+
+__global__ void __launch_bounds__(kTopThreads)
+decode_topk_kernel(const float* __restrict__ logits, long long ld, int V, int K, float* __restrict__ top_lp,
+                   int32_t* __restrict__ top_idx) {
+  extern __shared__ float row[];  // [V]
+  __shared__ float redf[32];
+  __shared__ int redi[32];
+  __shared__ float bc_f;
+  __shared__ int bc_i;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* src = logits + static_cast<long long>(blockIdx.x) * ld;
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += kTopThreads) {
+    const float x = __ldg(src + i);
+    row[i] = x;
+    mx = fmaxf(mx, x);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) redf[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    float m = warp_max(redf[lane]);
+    if (lane == 0) bc_f = m;
+  }
+  __syncthreads();
+  mx = bc_f;
+  float sum = 0.f;
+  for (int i = tid; i < V; i += kTopThreads) sum += expf(row[i] - mx);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) redf[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float s = warp_sum(redf[lane]);
+    if (lane == 0) bc_f = mx + logf(s);
+  }
+  __syncthreads();
+  const float lse = bc_f;
+  // thread-local best over its strided elements
+  ValIdx best = {-INFINITY, 0x7fffffff};
+  for (int i = tid; i < V; i += kTopThreads)
+    if (better(row[i], i, best.v, best.i)) { best.v = row[i]; best.i = i; }
+  for (int k = 0; k < K; ++k) {
+    ValIdx w = warp_argmax(best);
+    __syncthreads();
+    if (lane == 0) { redf[warp] = w.v; redi[warp] = w.i; }
+    __syncthreads();
+    if (warp == 0) {
+      ValIdx a = {redf[lane], redi[lane]};
+      a = warp_argmax(a);
+      if (lane == 0) {
+        bc_f = a.v;
+        bc_i = a.i;
+        top_lp[static_cast<long long>(blockIdx.x) * K + k] = a.v - lse;
+        top_idx[static_cast<long long>(blockIdx.x) * K + k] = a.i;
+      }
+    }
+    __syncthreads();
+    const int win = bc_i;
+    if (win != 0x7fffffff && (win % kTopThreads) == tid) {  // owner removes the winner and rescans
+      row[win] = -INFINITY;
+      best.v = -INFINITY;
+      best.i = 0x7fffffff;
+      for (int i = tid; i < V; i += kTopThreads)
+        if (better(row[i], i, best.v, best.i) && row[i] > -INFINITY) { best.v = row[i]; best.i = i; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One step of transformers' `_beam_search` (steps c-g, oracle/generate.py:beam_search) for every caption:
+// one warp per caption.  State buffers are ping-pong pairs indexed by (cur_len & 1) -> ((cur_len+1) & 1).
+// ------------------------------------------------------------------------------------------------
+struct BeamArgs {
+  const float* top_lp;      // [R][K]   row-local log-probs, sorted
+  const int32_t* top_idx;   // [R][K]
+  int32_t* run_seq;         // [2][C][nb][maxT]
+  int32_t* run_anc;         // [2][C][nb][maxT]   global cache row of the ancestor at each position
+  float* run_score;         // [2][C][nb]
+  int32_t* fin_seq;         // [2][C][nb][maxT]
+  float* fin_score;         // [2][C][nb]
+  int32_t* fin_len;         // [2][C][nb]   generated tokens of the finished hypothesis (0 = empty slot)
+  uint8_t* fin_flag;        // [2][C][nb]
+  uint8_t* unsat;           // [C]
+  int32_t* flags;           // [maxT][2]   per step: {any caption still improving, any candidate not stopped}
+  const int32_t* cur_len_p;
+  int C, nb, K, maxT, max_len, eos, V;
+  float length_penalty;
+};
+
+constexpr int kMaxBeams = 8;
+constexpr int kMaxCand = 2 * kMaxBeams * kMaxBeams;  // nb rows x K = 2 nb candidates each
+
+__global__ void __launch_bounds__(128) beam_step_kernel(const BeamArgs a) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int c = blockIdx.x * 4 + wib;
+  __shared__ float s_lp[4][kMaxCand];
+  __shared__ int s_tok[4][kMaxCand], s_src[4][kMaxCand];
+  __shared__ float k_lp[4][2 * kMaxBeams], k_run[4][2 * kMaxBeams], k_fin[4][2 * kMaxBeams];
+  __shared__ int k_tok[4][2 * kMaxBeams], k_src[4][2 * kMaxBeams], k_hit[4][2 * kMaxBeams];
+  __shared__ int n_sel[4][kMaxBeams], f_sel[4][kMaxBeams];
+  __shared__ float m_sc[4][3 * kMaxBeams];
+  if (c >= a.C) return;
+  const int t = *a.cur_len_p;
+  const int nb = a.nb, K = a.K, maxT = a.maxT;
+  const int ib = t & 1, ob = ib ^ 1;
+  const long long SB = static_cast<long long>(a.C) * nb;  // rows per ping-pong buffer
+  const int ncand = nb * K;
+  const bool forced = (t == a.max_len - 1);  // ForcedEOSTokenLogitsProcessor
+  // ---- c. candidates: running score + row-local log-prob
+  for (int i = lane; i < ncand; i += 32) {
+    const int b = i / K, k = i % K;
+    const long long r = static_cast<long long>(c) * nb + b;
+    float lp = a.top_lp[r * K + k];
+    int tok = a.top_idx[r * K + k];
+    if (forced) {
+      lp = (k == 0) ? 0.f : -INFINITY;
+      tok = (k == 0) ? a.eos : tok;
+      if (k != 0 && tok == a.eos) tok = (a.eos + 1) % a.V;
+    }
+    s_lp[wib][i] = a.run_score[ib * SB + r] + lp;
+    s_tok[wib][i] = tok;
+    s_src[wib][i] = b;
+  }
+  __syncwarp();
+  // rank = number of candidates that beat this one (value desc, flat index b*V+tok asc)
+  for (int i = lane; i < ncand; i += 32) {
+    const float v = s_lp[wib][i];
+    const long long fi = static_cast<long long>(s_src[wib][i]) * a.V + s_tok[wib][i];
+    int rank = 0;
+    for (int j = 0; j < ncand; ++j) {
+      const float w = s_lp[wib][j];
+      const long long fj = static_cast<long long>(s_src[wib][j]) * a.V + s_tok[wib][j];
+      rank += (w > v || (w == v && fj < fi)) ? 1 : 0;
+    }
+    if (rank < K) {
+      k_lp[wib][rank] = v;
+      k_tok[wib][rank] = s_tok[wib][i];
+      k_src[wib][rank] = s_src[wib][i];
+    }
+  }
+  __syncwarp();
+  // ---- d. stopping criteria, e. running log-probs, f. finished log-probs
+  const bool uns = a.unsat[c] != 0;
+  if (lane < K) {
+    const int hit = (k_tok[wib][lane] == a.eos) || (t + 1 >= a.max_len);
+    k_hit[wib][lane] = hit;
+    k_run[wib][lane] = k_lp[wib][lane] + (hit ? -1.0e9f : 0.f);
+    const float denom = static_cast<float>(pow(static_cast<double>(t + 1 - 1), static_cast<double>(a.length_penalty)));
+    float f = k_lp[wib][lane] / denom;
+    f = f + (uns ? 0.f : -1.0e9f);
+    const bool just = hit && lane < nb;
+    f = f + (just ? 0.f : -1.0e9f);
+    k_fin[wib][lane] = f;
+  }
+  __syncwarp();
+  // ---- e. next running beams = top nb of k_run
+  if (lane < K) {
+    const float v = k_run[wib][lane];
+    int rank = 0;
+    for (int j = 0; j < K; ++j) {
+      const float w = k_run[wib][j];
+      rank += (w > v || (w == v && j < lane)) ? 1 : 0;
+    }
+    if (rank < nb) n_sel[wib][rank] = lane;
+  }
+  // ---- f. merge finished set: [old finished (nb) | candidates (K)] -> top nb
+  for (int i = lane; i < nb + K; i += 32)
+    m_sc[wib][i] = i < nb ? a.fin_score[ib * SB + static_cast<long long>(c) * nb + i] : k_fin[wib][i - nb];
+  __syncwarp();
+  for (int i = lane; i < nb + K; i += 32) {
+    const float v = m_sc[wib][i];
+    int rank = 0;
+    for (int j = 0; j < nb + K; ++j) {
+      const float w = m_sc[wib][j];
+      rank += (w > v || (w == v && j < i)) ? 1 : 0;
+    }
+    if (rank < nb) f_sel[wib][rank] = i;
+  }
+  __syncwarp();
+  // ---- write the next state
+  int any_not_hit = 0;
+  for (int j = 0; j < K; ++j) any_not_hit |= !k_hit[wib][j];
+  for (int j = 0; j < nb; ++j) {
+    const int cand = n_sel[wib][j];
+    const int srcb = k_src[wib][cand];
+    const long long in_row = ib * SB + static_cast<long long>(c) * nb + srcb;
+    const long long out_row = ob * SB + static_cast<long long>(c) * nb + j;
+    for (int s = lane; s < maxT; s += 32) {
+      int tokv = a.run_seq[in_row * maxT + s];
+      int ancv = a.run_anc[in_row * maxT + s];
+      if (s == t) tokv = k_tok[wib][cand];
+      if (s == t - 1) ancv = static_cast<int>(static_cast<long long>(c) * nb + srcb);
+      a.run_seq[out_row * maxT + s] = tokv;
+      a.run_anc[out_row * maxT + s] = ancv;
+    }
+    if (lane == 0) a.run_score[out_row] = k_run[wib][cand];
+    // finished slot j
+    const int m = f_sel[wib][j];
+    if (m < nb) {
+      const long long fr = ib * SB + static_cast<long long>(c) * nb + m;
+      for (int s = lane; s < maxT; s += 32) a.fin_seq[out_row * maxT + s] = a.fin_seq[fr * maxT + s];
+      if (lane == 0) {
+        a.fin_score[out_row] = a.fin_score[fr];
+        a.fin_len[out_row] = a.fin_len[fr];
+        a.fin_flag[out_row] = a.fin_flag[fr];
+      }
+    } else {
+      const int cd = m - nb;
+      const long long sr = ib * SB + static_cast<long long>(c) * nb + k_src[wib][cd];
+      for (int s = lane; s < maxT; s += 32) {
+        int tokv = a.run_seq[sr * maxT + s];
+        if (s == t) tokv = k_tok[wib][cd];
+        a.fin_seq[out_row * maxT + s] = tokv;
+      }
+      if (lane == 0) {
+        const bool just = k_hit[wib][cd] && cd < nb;
+        a.fin_score[out_row] = k_fin[wib][cd];
+        a.fin_len[out_row] = t;  // generated tokens = cur_len + 1 - prompt
+        a.fin_flag[out_row] = just ? 1 : 0;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- g. early-stop heuristic (early_stopping=False): can the best running beam still improve?
+  if (lane == 0) {
+    const long long o0 = ob * SB + static_cast<long long>(c) * nb;
+    const float denom = static_cast<float>(pow(static_cast<double>(t + 1 - 1), static_cast<double>(a.length_penalty)));
+    const float best_possible = k_run[wib][n_sel[wib][0]] / denom;
+    float mn = INFINITY;
+    for (int j = 0; j < nb; ++j) {
+      const int m = f_sel[wib][j];
+      mn = fminf(mn, m_sc[wib][m]);
+    }
+    bool any = false;
+    for (int j = 0; j < nb; ++j) {
+      const int m = f_sel[wib][j];
+      const bool fin = m < nb ? (a.fin_flag[ib * SB + static_cast<long long>(c) * nb + m] != 0)
+                              : (k_hit[wib][m - nb] && (m - nb) < nb);
+      const float worst = fin ? mn : -1.0e9f;
+      any |= best_possible > worst;
+    }
+    (void)o0;
+    const bool nu = uns && any;
+    a.unsat[c] = nu ? 1 : 0;
+    if (nu) atomicOr(a.flags + 2 * t, 1);
+    if (any_not_hit) atomicOr(a.flags + 2 * t + 1, 1);
+  }
+}
+
+// greedy `_sample` step: next = argmax (forced eos at the last position), finished rows emit pad
+__global__ void greedy_step_kernel(const int32_t* __restrict__ top_idx, int32_t* __restrict__ seq,
+                                   uint8_t* __restrict__ unfinished, int32_t* __restrict__ flags,
+                                   const int32_t* __restrict__ cur_len_p, int R, int maxT, int max_len, int eos, int pad) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int t = *cur_len_p;
+  int tok = (t == max_len - 1) ? eos : top_idx[r];
+  const bool un = unfinished[r] != 0;
+  if (!un) tok = pad;
+  seq[static_cast<long long>(r) * maxT + t] = tok;
+  const bool nu = un && tok != eos && (t + 1 < max_len);
+  unfinished[r] = nu ? 1 : 0;
+  if (nu) atomicOr(flags + 2 * t, 1);
+  atomicOr(flags + 2 * t + 1, 1);
+}
+
+__global__ void advance_len_kernel(int32_t* cur_len_p) { *cur_len_p += 1; }
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vacnic_decode_embed_ln(const int32_t* seq, const int32_t* cur_len, const void* tok, const void* pos,
+                                      const float* gamma, const float* beta, void* y, int32_t R, int32_t maxT, int32_t d,
+                                      int32_t pos_offset, int32_t pingpong, float eps, void* stream) {
+  VB_REQUIRE(seq && cur_len && tok && pos && gamma && beta && y, "decode_embed_ln: null pointer");
+  VB_REQUIRE(R > 0 && maxT > 0 && d > 0 && d % 256 == 0 && d <= 1024, "decode_embed_ln: d must be 256/512/768/1024");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = (R + 7) / 8;
+  const __nv_bfloat16* tk = static_cast<const __nv_bfloat16*>(tok);
+  const __nv_bfloat16* ps = static_cast<const __nv_bfloat16*>(pos);
+  __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
+  switch (d / 256) {
+    case 1: decode_embed_ln_kernel<1><<<grid, 256, 0, s>>>(seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
+    case 2: decode_embed_ln_kernel<2><<<grid, 256, 0, s>>>(seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
+    case 3: decode_embed_ln_kernel<3><<<grid, 256, 0, s>>>(seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
+    default: decode_embed_ln_kernel<4><<<grid, 256, 0, s>>>(seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
+  }
+  count_launch();
+  return check_last("decode_embed_ln");
+}
+
+extern "C" int vacnic_decode_self_attn(const void* qkv, void* kcache, void* vcache, const int32_t* anc,
+                                       const int32_t* cur_len, void* out, int32_t R, int32_t H, int32_t head_dim,
+                                       int32_t maxT, void* stream) {
+  VB_REQUIRE(qkv && kcache && vcache && cur_len && out, "decode_self_attn: null pointer");
+  VB_REQUIRE(head_dim == 64, "decode_self_attn: head_dim must be 64 (BART-base / BART-large)");
+  VB_REQUIRE(R > 0 && H > 0 && maxT > 0 && maxT <= kMaxT, "decode_self_attn: maxT must be in 1..%d", kMaxT);
+  const int d = H * head_dim;
+  decode_self_attn_kernel<<<dim3(H, R), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(kcache), static_cast<__nv_bfloat16*>(vcache),
+      anc, cur_len, static_cast<__nv_bfloat16*>(out), R, maxT, d, 1.0f / sqrtf(static_cast<float>(head_dim)));
+  count_launch();
+  return check_last("decode_self_attn");
+}
+
+template <int NQ>
+static int launch_cross(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t v_off, const uint8_t* key_mask,
+                        const int32_t* key_len, void* out, int64_t ldo, int32_t captions, int32_t nq, int32_t L,
+                        int32_t H, float scale, cudaStream_t s) {
+  const size_t smem = (static_cast<size_t>(NQ) * L + 4 * NQ * 64) * sizeof(float);
+  auto kern = decode_cross_attn_kernel<NQ>;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(VACNIC_ECUDA, "decode_cross_attn: smem %zu: %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  kern<<<dim3(H, captions), 128, smem, s>>>(static_cast<const __nv_bfloat16*>(q), ldq,
+                                            static_cast<const __nv_bfloat16*>(kv), ldkv, v_off, key_mask, key_len,
+                                            static_cast<__nv_bfloat16*>(out), ldo, nq, L, scale);
+  count_launch();
+  return check_last("decode_cross_attn");
+}
+
+extern "C" int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t v_off,
+                                        const uint8_t* key_mask, const int32_t* key_len, void* out, int64_t ldo,
+                                        int32_t captions, int32_t nq, int32_t L, int32_t H, int32_t head_dim,
+                                        void* stream) {
+  VB_REQUIRE(q && kv && out, "decode_cross_attn: null pointer");
+  VB_REQUIRE(head_dim == 64, "decode_cross_attn: head_dim must be 64");
+  VB_REQUIRE(captions > 0 && nq >= 1 && nq <= 8 && L > 0 && L <= 4096 && H > 0, "decode_cross_attn: bad shape (nq <= 8, L <= 4096)");
+  VB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && v_off % 8 == 0, "decode_cross_attn: strides must be multiples of 8 elements");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0, "decode_cross_attn: misaligned");
+  const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (nq == 1) return launch_cross<1>(q, ldq, kv, ldkv, v_off, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s);
+  if (nq == 2) return launch_cross<2>(q, ldq, kv, ldkv, v_off, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s);
+  if (nq <= 4) return launch_cross<4>(q, ldq, kv, ldkv, v_off, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s);
+  return launch_cross<8>(q, ldq, kv, ldkv, v_off, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s);
+}
+
+extern "C" int vacnic_mask_key_len(const uint8_t* mask, int32_t* key_len, int32_t B, int32_t L, void* stream) {
+  VB_REQUIRE(mask && key_len && B > 0 && L > 0, "mask_key_len: bad arguments");
+  mask_key_len_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, key_len, B, L);
+  count_launch();
+  return check_last("mask_key_len");
+}
+
+extern "C" int vacnic_decode_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, int32_t K, float* top_lp,
+                                  int32_t* top_idx, void* stream) {
+  VB_REQUIRE(logits && top_lp && top_idx, "decode_topk: null pointer");
+  VB_REQUIRE(rows > 0 && V > 0 && K >= 1 && K <= 2 * kMaxBeams && K <= V, "decode_topk: bad shape (K <= %d)", 2 * kMaxBeams);
+  const size_t smem = static_cast<size_t>(V) * sizeof(float);
+  VB_REQUIRE(smem <= 220 * 1024, "decode_topk: vocabulary %d does not fit the shared-memory row buffer", V);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(decode_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(VACNIC_ECUDA, "decode_topk: smem %zu: %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  decode_topk_kernel<<<rows, kTopThreads, smem, static_cast<cudaStream_t>(stream)>>>(logits, ld, V, K, top_lp, top_idx);
+  count_launch();
+  return check_last("decode_topk");
+}
+
+extern "C" int vacnic_beam_step(const float* top_lp, const int32_t* top_idx, int32_t* run_seq, int32_t* run_anc,
+                                float* run_score, int32_t* fin_seq, float* fin_score, int32_t* fin_len,
+                                uint8_t* fin_flag, uint8_t* unsat, int32_t* flags, const int32_t* cur_len,
+                                int32_t captions, int32_t beams, int32_t maxT, int32_t max_len, int32_t eos, int32_t V,
+                                float length_penalty, void* stream) {
+  VB_REQUIRE(top_lp && top_idx && run_seq && run_anc && run_score && fin_seq && fin_score && fin_len && fin_flag && unsat &&
+                 flags && cur_len, "beam_step: null pointer");
+  VB_REQUIRE(captions > 0 && beams >= 1 && beams <= kMaxBeams, "beam_step: beams must be in 1..%d", kMaxBeams);
+  VB_REQUIRE(max_len >= 2 && max_len <= maxT, "beam_step: max_len must be in 2..maxT");
+  BeamArgs a;
+  a.top_lp = top_lp; a.top_idx = top_idx; a.run_seq = run_seq; a.run_anc = run_anc; a.run_score = run_score;
+  a.fin_seq = fin_seq; a.fin_score = fin_score; a.fin_len = fin_len; a.fin_flag = fin_flag; a.unsat = unsat;
+  a.flags = flags; a.cur_len_p = cur_len;
+  a.C = captions; a.nb = beams; a.K = 2 * beams; a.maxT = maxT; a.max_len = max_len; a.eos = eos; a.V = V;
+  a.length_penalty = length_penalty;
+  beam_step_kernel<<<(captions + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  count_launch();
+  return check_last("beam_step");
+}
+
+extern "C" int vacnic_greedy_step(const int32_t* top_idx, int32_t* seq, uint8_t* unfinished, int32_t* flags,
+                                  const int32_t* cur_len, int32_t rows, int32_t maxT, int32_t max_len, int32_t eos,
+                                  int32_t pad, void* stream) {
+  VB_REQUIRE(top_idx && seq && unfinished && flags && cur_len, "greedy_step: null pointer");
+  VB_REQUIRE(rows > 0 && max_len >= 2 && max_len <= maxT, "greedy_step: bad shape");
+  greedy_step_kernel<<<(rows + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(top_idx, seq, unfinished, flags,
+                                                                                       cur_len, rows, maxT, max_len, eos, pad);
+  count_launch();
+  return check_last("greedy_step");
+}
+
+extern "C" int vacnic_advance_len(int32_t* cur_len, void* stream) {
+  VB_REQUIRE(cur_len, "advance_len: null pointer");
+  advance_len_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(cur_len);
+  count_launch();
+  return check_last("advance_len");
+}

@@ -3,8 +3,10 @@
 // (double buffered) -> tcgen05.ld epilogue (bias / alpha / GELU / tanh / activation-gradient /
 // accumulate) -> global memory.  Persistent: one CTA per SM walks a static tile list.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 and one half of the tile's columns
+// (two warps per lane quadrant, so the bias / activation math of a tile is spread over all four SM
+// sub-partitions twice and hides behind the next tile's main loop).
 //
 // This one kernel family serves every dense contraction on the VACNIC hot path (see
 // include/vacnic_b200.h for the reference call sites): forward linears (A K-major, B K-major),
@@ -29,11 +31,13 @@ struct GemmArgs {
   float alpha;
   int c_dtype, act, dact, accumulate;
   int vec_ok;  // 16-byte vector access allowed on C / aux rows
+  int bias_vec;  // bias pointer 16-byte aligned
 };
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 template <int BN>
 struct GemmCfg {
@@ -62,9 +66,17 @@ __device__ __forceinline__ void epilogue_row_chunk(const GemmArgs& g, float (&v)
                                                    long long row_off, int n0) {
   const int nvalid = min(32, g.N - n0);
   if (g.bias != nullptr) {
+    if (nvalid == 32 && g.bias_vec) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) v[j] += __ldg(g.bias + n0 + j);
+      for (int q = 0; q < 8; ++q) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + q);
+        v[4 * q + 0] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] += __ldg(g.bias + n0 + j);
+    }
   }
   if (g.alpha != 1.0f) {
 #pragma unroll
@@ -187,7 +199,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -277,8 +289,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps 2..5
+    // ------------------------------------------------------------ epilogue warps 2..9
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns
     uint32_t it = 0;
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++it) {
       const int batch = static_cast<int>(t / tiles_per_batch);
@@ -297,7 +310,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 static_cast<long long>(row) * g.ldc;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         if (n0 + c * 32 >= g.N) break;
         uint32_t r32[32];
         tmem_ld_32x32(taddr + c * 32, r32);
@@ -468,6 +481,7 @@ extern "C" int vacnic_gemm(const vacnic_gemm_desc* d, void* stream_v) {
             (d->c_sb0 * es) % 16 == 0 && (d->c_sb1 * es) % 16 == 0);
   };
   g.vec_ok = aligned(d->c, c_es) && aligned(d->aux_out, 2) && aligned(d->aux_in, 2) ? 1 : 0;
+  g.bias_vec = (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0 ? 1 : 0;
 
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, d->a, d->a_mn_major != 0, d->M, d->K, d->lda, d->batch0, d->a_sb0,

@@ -1,0 +1,237 @@
+"""Caption generation on the B200-native model: encoder once per caption, then a cached single-token
+decoder step replayed as ONE CUDA graph per position, with greedy / beam search running on the device.
+
+Replaces `model.generate(...)` as the VACNIC scripts call it (INFER:798, 867; TRAIN:513-520): greedy
+(`num_beams=1`) and beam search with `length_penalty`, for the generation config a default `BartConfig`
+yields (decoder_start=2, eos=2, pad=1, forced_eos_token_id=2, early_stopping=False).  The search
+semantics are transformers 5.5 `_beam_search` / `_sample` (restated and pinned in oracle/generate.py).
+
+Device design (see csrc/decode.cu): the encoder memory is projected once into per-layer cross K/V
+buffers `[layer][captions*L][2d]` shared by the beams of a caption (the reference expands the encoder
+output `num_beams` times and caches `num_beams` identical copies, MFULL:2066-2074); the self-attention
+cache is never reordered (ancestry table instead of `_reorder_cache`); all kernels read the current
+length from a device scalar so the captured step graph is position independent.  The host only replays
+the graph and polls a stop flag every few steps.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import kernels as K
+
+
+class Generator:
+    """Decode engine specialised for (captions, beams, article length, max_length) on one model."""
+
+    def __init__(self, model, captions: int, beams: int, L: int, max_length: int, length_penalty: float = 1.0,
+                 use_graph: bool = True, poll_every: int = 4):
+        cfg = model.cfg
+        if max_length < 2 or max_length > 256:
+            raise ValueError("max_length must be in 2..256")
+        if beams < 1 or beams > 8:
+            raise ValueError("num_beams must be in 1..8")
+        if max_length - 1 + 2 > cfg.max_pos + 2:
+            raise ValueError("max_length exceeds the decoder's position table")
+        self.model, self.cfg = model, cfg
+        self.C, self.nb, self.L, self.max_len = captions, beams, L, max_length
+        self.lp = float(length_penalty)
+        self.R = captions * beams
+        self.maxT = max_length
+        self.use_graph, self.poll_every = use_graph, max(1, poll_every)
+        dev = model.store.device
+        d, f, V = cfg.d_model, cfg.ffn, cfg.vocab
+        R, nl = self.R, cfg.dec_layers
+        bf, f32, i32, u8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
+
+        def buf(*shape, dtype=bf):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        self.x, self.x2, self.attn, self.proj, self.qb = (buf(R, d) for _ in range(5))
+        self.qkv, self.h = buf(R, 3 * d), buf(R, f)
+        self.ldp = (V + 7) // 8 * 8
+        self.logits = buf(R, self.ldp, dtype=f32)
+        self.kc = buf(nl, R, self.maxT, d)
+        self.vc = buf(nl, R, self.maxT, d)
+        self.cross_kv = buf(nl, captions * L, 2 * d)
+        self.key_mask = buf(captions, L, dtype=u8)
+        self.key_len = buf(captions, dtype=i32)
+        self.Kc = 2 * beams if beams > 1 else 1
+        self.top_lp = buf(R, self.Kc, dtype=f32)
+        self.top_idx = buf(R, self.Kc, dtype=i32)
+        st: Dict[str, torch.Tensor] = {"cur_len": buf(1, dtype=i32), "flags": buf(self.maxT + 1, 2, dtype=i32)}
+        if beams > 1:
+            st.update(run_seq=buf(2, captions, beams, self.maxT, dtype=i32), run_anc=buf(2, captions, beams, self.maxT, dtype=i32),
+                      run_score=buf(2, captions, beams, dtype=f32), fin_seq=buf(2, captions, beams, self.maxT, dtype=i32),
+                      fin_score=buf(2, captions, beams, dtype=f32), fin_len=buf(2, captions, beams, dtype=i32),
+                      fin_flag=buf(2, captions, beams, dtype=u8), unsat=buf(captions, dtype=u8))
+        else:
+            st.update(seq=buf(captions, self.maxT, dtype=i32), unfinished=buf(captions, dtype=u8))
+        self.st = st
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+        self.steps_run = 0
+
+    # ------------------------------------------------------------------ encoder side
+    def _reset_state(self):
+        cfg, st = self.cfg, self.st
+        st["cur_len"].fill_(1)
+        st["flags"].zero_()
+        if self.nb > 1:
+            st["run_seq"].fill_(cfg.pad_token_id)
+            st["run_seq"][:, :, :, 0] = cfg.decoder_start_token_id
+            st["fin_seq"].copy_(st["run_seq"])
+            st["run_anc"].zero_()
+            st["run_score"].fill_(-1.0e9)
+            st["run_score"][:, :, 0] = 0.0
+            st["fin_score"].fill_(-1.0e9)
+            st["fin_len"].zero_()
+            st["fin_flag"].zero_()
+            st["unsat"].fill_(1)
+        else:
+            st["seq"].fill_(cfg.pad_token_id)
+            st["seq"][:, 0] = cfg.decoder_start_token_id
+            st["unfinished"].fill_(1)
+
+    def encode(self, enc_inputs: dict):
+        """Encoder forward (a7a) + the one-off cross-attention K/V projection of every decoder layer."""
+        model, cfg = self.model, self.cfg
+        if model.store.dirty_shadow:
+            model.store.refresh_shadow()
+        was_training = model.training
+        model.eval()
+        enc = model.model.encoder(output_hidden_states=False, **enc_inputs)
+        model.train(was_training)
+        h = enc["last_hidden_state"]
+        C, L, d = h.shape
+        if (C, L) != (self.C, self.L):
+            raise ValueError(f"generator built for {self.C} captions x {self.L} tokens, got {C} x {L}")
+        mask = enc_inputs.get("attention_mask")
+        if mask is None:
+            self.key_mask.fill_(1)
+        else:
+            self.key_mask.copy_(mask.to(torch.uint8))
+        self.key_len.copy_(K.mask_key_len(self.key_mask))
+        lin = model.model.decoder.lin_cross_kv  # rows [l*2d, (l+1)*2d) = [k_l ; v_l]
+        h2 = h.reshape(C * L, d)
+        for l in range(cfg.dec_layers):
+            K.gemm(h2, lin.w16[l * 2 * d:(l + 1) * 2 * d], out=self.cross_kv[l], bias=lin.b32[l * 2 * d:(l + 1) * 2 * d])
+        return enc
+
+    # ------------------------------------------------------------------ one decoding step (capturable)
+    def _step(self):
+        model, cfg, st = self.model, self.cfg, self.st
+        dec = model.model.decoder
+        store = model.store
+        d, H, V = cfg.d_model, cfg.heads, cfg.vocab
+        beam = self.nb > 1
+        x, x2 = self.x, self.x2
+        K.decode_embed_ln(st["run_seq"] if beam else st["seq"], st["cur_len"], store.w16(dec.embed_tokens.weight),
+                          store.w16(dec.embed_positions.weight), dec.ln_emb.g, dec.ln_emb.b, x, self.maxT, pos_offset=2,
+                          pingpong=beam)
+        anc = st["run_anc"] if beam else None
+        for l, layer in enumerate(dec.layers):
+            a = layer.self_attn
+            K.gemm(x, a.lin_qkv.w16, out=self.qkv, bias=a.lin_qkv.b32)
+            K.decode_self_attn(self.qkv, self.kc[l], self.vc[l], anc, st["cur_len"], self.attn, H, self.maxT)
+            K.gemm(self.attn, a.lin_o.w16, out=self.proj, bias=a.lin_o.b32)
+            K.add_layernorm_fwd(self.proj, x, a.ln.g, a.ln.b, out=x2, want_stats=False)
+            a = layer.encoder_attn
+            K.gemm(x2, a.lin_q.w16, out=self.qb, bias=a.lin_q.b32)
+            K.decode_cross_attn(self.qb, self.cross_kv[l], d, self.key_mask, self.key_len, self.attn, self.C, self.nb, self.L, H)
+            K.gemm(self.attn, a.lin_o.w16, out=self.proj, bias=a.lin_o.b32)
+            K.add_layernorm_fwd(self.proj, x2, a.ln.g, a.ln.b, out=x, want_stats=False)
+            K.gemm(x, layer.lin_fc1.w16, out=self.h, bias=layer.lin_fc1.b32, act=K.ACT_GELU)
+            K.gemm(self.h, layer.lin_fc2.w16, out=self.proj, bias=layer.lin_fc2.b32)
+            K.add_layernorm_fwd(self.proj, x, layer.ln_final.g, layer.ln_final.b, out=x2, want_stats=False)
+            x, x2 = x2, x
+        K.gemm(x, model.lin_lm.w16, out=self.logits[:, :V], bias=model.final_logits_bias.view(-1))
+        K.decode_topk(self.logits, V, self.Kc, self.top_lp, self.top_idx)
+        if beam:
+            K.beam_step(self.top_lp, self.top_idx, st, self.C, self.nb, self.maxT, self.max_len, cfg.eos_token_id, V, self.lp)
+        else:
+            K.greedy_step(self.top_idx, st["seq"], st["unfinished"], st["flags"], st["cur_len"], self.R, self.maxT,
+                          self.max_len, cfg.eos_token_id, cfg.pad_token_id)
+        K.advance_len(st["cur_len"])
+
+    def _capture(self):
+        # one eager step first (lazy kernel attribute setup), on a side stream as CUDA graphs require;
+        # the state is reset afterwards, so the warm-up leaves no trace
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        c0 = K._l.launch_count()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        self.launches_per_step = K._l.launch_count() - c0
+
+    # ------------------------------------------------------------------ search loop
+    @torch.no_grad()
+    def decode(self) -> torch.Tensor:
+        """Run the search on the encoded captions; returns int64 ids like transformers' generate()."""
+        if self.use_graph and self.graph is None:
+            self._reset_state()
+            self._capture()
+        self._reset_state()
+        t, stop_t = 1, None
+        while t < self.max_len:
+            n = min(self.poll_every, self.max_len - t)
+            for _ in range(n):
+                if self.use_graph:
+                    self.graph.replay()
+                else:
+                    c0 = K._l.launch_count()
+                    self._step()
+                    self.launches_per_step = K._l.launch_count() - c0
+            flags = self.st["flags"][t:t + n].cpu()  # device -> host read: the stop test of the search loop
+            go = (flags[:, 0] != 0) & (flags[:, 1] != 0)
+            t += n
+            if not bool(go.all()):
+                stop_t = t - n + int((~go).nonzero()[0])
+                break
+        self.steps_run = t - 1
+        if stop_t is None:
+            stop_t = self.max_len - 1
+        st = self.st
+        if self.nb > 1:
+            ob = t & 1  # buffer written by the last executed step
+            gen_len = int(st["fin_len"][ob, :, 0].max().item())
+            return st["fin_seq"][ob, :, 0, :1 + gen_len].to(torch.int64)
+        return st["seq"][:, :stop_t + 1].to(torch.int64)
+
+    def generate(self, enc_inputs: dict) -> torch.Tensor:
+        self.encode(enc_inputs)
+        return self.decode()
+
+
+def _enc_inputs(model, input_ids, attention_mask, image_features, face_features, face_mask, name_ids, name_mask):
+    kw = dict(input_ids=input_ids, attention_mask=attention_mask)
+    if not model.cfg.stock:
+        kw["image_features"] = image_features
+        if not model.cfg.only_image:
+            kw.update(face_features=face_features, face_mask=face_mask, name_ids=name_ids, name_mask=name_mask)
+    return kw
+
+
+@torch.no_grad()
+def generate(model, input_ids=None, attention_mask=None, num_beams: int = 1, max_length: int = 20,
+             length_penalty: float = 1.0, image_features=None, face_features=None, face_mask=None, name_ids=None,
+             name_mask=None, use_graph: bool = True) -> torch.Tensor:
+    """`model.generate(...)` of the reference scripts (INFER:798, 867).  Engines are cached on the model per
+    (captions, beams, L, max_length, length_penalty) so repeated calls replay the captured step graph."""
+    if input_ids is None:
+        raise ValueError("generate() needs input_ids")
+    if not input_ids.is_cuda:
+        raise K._l.VacnicError("vacnic_b200 runs on CUDA tensors only (no CPU fallback)")
+    C, L = input_ids.shape
+    cache = model.__dict__.setdefault("_generators", {})
+    key = (C, num_beams, L, max_length, float(length_penalty), use_graph)
+    if key not in cache:
+        cache[key] = Generator(model, C, num_beams, L, max_length, length_penalty, use_graph=use_graph)
+    return cache[key].generate(_enc_inputs(model, input_ids, attention_mask, image_features, face_features, face_mask,
+                                           name_ids, name_mask))

@@ -116,16 +116,18 @@ class Rng:
         check(lib().vacnic_rng_advance(self.state.data_ptr(), stream_ptr()), "vacnic_rng_advance")
 
 
-def add_layernorm_fwd(x, res, gamma, beta, out=None, rows_per_group=0, group_stride=0, p_drop=0.0, rng=None, salt=0):
+def add_layernorm_fwd(x, res, gamma, beta, out=None, rows_per_group=0, group_stride=0, p_drop=0.0, rng=None, salt=0,
+                      want_stats=True):
     """y = LN(res + dropout(x)); returns (y, mean, rstd).  `out` may be a [rows, d] view whose groups of
-    `rows_per_group` rows are `group_stride` elements apart (slice of the prefix/NER concat buffer)."""
+    `rows_per_group` rows are `group_stride` elements apart (slice of the prefix/NER concat buffer).
+    `want_stats=False` (inference) skips the per-row statistics the backward pass needs."""
     d = x.shape[-1]
     rows = x.numel() // d
     _c(x, torch.bfloat16, "x"); _c(res, torch.bfloat16, "res"); _c(gamma, torch.float32, "gamma"); _c(beta, torch.float32, "beta")
     if out is None:
         out = torch.empty_like(x)
-    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
-    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
     check(lib().vacnic_add_layernorm_fwd(ptr(x), ptr(res), ptr(gamma), ptr(beta), ptr(out), ptr(mean), ptr(rstd), rows, d,
                                          rows_per_group, group_stride, LN_EPS, p_drop,
                                          rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt,
@@ -318,3 +320,58 @@ def concat_rows(a, b, out):
     check(lib().vacnic_concat_rows(ptr(a), ptr(b), ptr(out), a.shape[0], a.shape[1], b.shape[1], a.shape[2], stream_ptr()),
           "vacnic_concat_rows")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# cached decoding / device-side search (csrc/decode.cu)
+# ------------------------------------------------------------------------------------------------
+def decode_embed_ln(seq, cur_len, tok, pos, gamma, beta, y, maxT, pos_offset=2, pingpong=False):
+    R, d = y.shape
+    check(lib().vacnic_decode_embed_ln(ptr(seq), ptr(cur_len), ptr(tok), ptr(pos), ptr(gamma), ptr(beta), ptr(y), R, maxT, d,
+                                       pos_offset, int(pingpong), LN_EPS, stream_ptr()), "vacnic_decode_embed_ln")
+    return y
+
+
+def decode_self_attn(qkv, kcache, vcache, anc, cur_len, out, H, maxT):
+    R, d = out.shape
+    check(lib().vacnic_decode_self_attn(ptr(qkv), ptr(kcache), ptr(vcache), ptr(anc), ptr(cur_len), ptr(out), R, H, d // H,
+                                        maxT, stream_ptr()), "vacnic_decode_self_attn")
+    return out
+
+
+def decode_cross_attn(q, kv, v_off, key_mask, key_len, out, captions, nq, L, H):
+    """q [captions*nq, d] (row stride q.stride(0)), kv [captions*L, >= 2d] with k at column 0, v at v_off."""
+    d = out.shape[1]
+    check(lib().vacnic_decode_cross_attn(ptr(q), q.stride(0), ptr(kv), kv.stride(0), v_off, ptr(key_mask), ptr(key_len),
+                                         ptr(out), out.stride(0), captions, nq, L, H, d // H, stream_ptr()),
+          "vacnic_decode_cross_attn")
+    return out
+
+
+def mask_key_len(mask_u8):
+    _c(mask_u8, torch.uint8, "key mask")
+    B, L = mask_u8.shape
+    out = torch.empty(B, dtype=torch.int32, device=mask_u8.device)
+    check(lib().vacnic_mask_key_len(ptr(mask_u8), ptr(out), B, L, stream_ptr()), "vacnic_mask_key_len")
+    return out
+
+
+def decode_topk(logits2d, V, K_, top_lp, top_idx):
+    check(lib().vacnic_decode_topk(ptr(logits2d), logits2d.stride(0), logits2d.shape[0], V, K_, ptr(top_lp), ptr(top_idx),
+                                   stream_ptr()), "vacnic_decode_topk")
+
+
+def beam_step(top_lp, top_idx, st, captions, beams, maxT, max_len, eos, V, length_penalty):
+    check(lib().vacnic_beam_step(ptr(top_lp), ptr(top_idx), ptr(st["run_seq"]), ptr(st["run_anc"]), ptr(st["run_score"]),
+                                 ptr(st["fin_seq"]), ptr(st["fin_score"]), ptr(st["fin_len"]), ptr(st["fin_flag"]),
+                                 ptr(st["unsat"]), ptr(st["flags"]), ptr(st["cur_len"]), captions, beams, maxT, max_len, eos,
+                                 V, length_penalty, stream_ptr()), "vacnic_beam_step")
+
+
+def greedy_step(top_idx, seq, unfinished, flags, cur_len, rows, maxT, max_len, eos, pad):
+    check(lib().vacnic_greedy_step(ptr(top_idx), ptr(seq), ptr(unfinished), ptr(flags), ptr(cur_len), rows, maxT, max_len, eos,
+                                   pad, stream_ptr()), "vacnic_greedy_step")
+
+
+def advance_len(cur_len):
+    check(lib().vacnic_advance_len(ptr(cur_len), stream_ptr()), "vacnic_advance_len")
