@@ -229,6 +229,38 @@ int vacnic_greedy_step(const int32_t* top_idx, int32_t* seq, uint8_t* unfinished
                        int32_t rows, int32_t maxT, int32_t max_len, int32_t eos, int32_t pad, void* stream);
 int vacnic_advance_len(int32_t* cur_len, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused attention core, head_dim 64 (BartAttention.forward MFULL:503-556: bmm(q,k^T), additive mask,
+ * softmax, bmm(p,v); the q scaling of MFULL:472 is applied to the fp32 scores).  Scores and
+ * probabilities stay on chip (tcgen05 accumulators in TMEM, P in shared memory).
+ *   Q(b,h,i,c) = q[b*q_sb + h*q_sh + i*ldq + c]   (same addressing for k, v, dq, dk, dv)
+ *   O(b,i,h*64+c) = out[b*o_sb + i*ldo + h*64 + c] (same for dout)
+ * key_mask: uint8 [B][Sk], 1 = attend (null = no padding mask); causal != 0 masks key j > query i;
+ * masked scores are set to finfo(float32).min like _expand_mask / _make_causal_mask (MFULL:373-398).
+ * key_len (int32 [B], optional): keys >= key_len[b] are known to be masked and are skipped.
+ * stats: fp32 [B][H][Sq][2] = {row max (log2 domain), 1 / row sum}, written by the forward pass
+ * (may be null for inference) and read by the backward pass.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct vacnic_attn_desc {
+  int32_t B, H, Sq, Sk, head_dim, causal;
+  const void* q; int64_t ldq, q_sh, q_sb;
+  const void* k; int64_t ldk, k_sh, k_sb;
+  const void* v; int64_t ldv, v_sh, v_sb;
+  void* out; int64_t ldo, o_sb;
+  float* stats;
+  const uint8_t* key_mask;
+  const int32_t* key_len;
+  /* backward only */
+  const void* dout; int64_t lddo, do_sb;
+  void* dq; int64_t lddq, dq_sh, dq_sb;
+  void* dk; int64_t lddk, dk_sh, dk_sb;
+  void* dv; int64_t lddv, dv_sh, dv_sb;
+  float* delta; /* fp32 [B][H][Sq] scratch: rowsum(dO * O) */
+} vacnic_attn_desc;
+int vacnic_attn_fwd(const vacnic_attn_desc* d, void* stream);
+/* dq, dk, dv of the above (dq/dk carry the head_dim^-0.5 factor).  `out` must hold the forward result. */
+int vacnic_attn_bwd(const vacnic_attn_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

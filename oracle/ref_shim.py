@@ -34,11 +34,15 @@ def _import(name):
     saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
     for k in saved:
         del sys.modules[k]
-    sys.path.insert(0, REFERENCE_ROOT)
+    # the reference's `src/` has no __init__.py (namespace package) and would lose against the regular `src`
+    # package of this repo wherever it sits on sys.path: hide the repo root while importing
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    saved_path = list(sys.path)
+    sys.path[:] = [REFERENCE_ROOT] + [p for p in sys.path if os.path.abspath(p or os.getcwd()) != repo_root]
     try:
         mod = importlib.import_module(name)
     finally:
-        sys.path.remove(REFERENCE_ROOT)
+        sys.path[:] = saved_path
         for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
             sys.modules["_vacnic_ref_" + k] = sys.modules.pop(k)
         sys.modules.update(saved)

@@ -39,6 +39,8 @@ SIGNATURES = {
     "vacnic_beam_step": [P, P, P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, F32, P],
     "vacnic_greedy_step": [P, P, P, P, P, I32, I32, I32, I32, I32, P],
     "vacnic_advance_len": [P, P],
+    "vacnic_attn_fwd": [P, P],
+    "vacnic_attn_bwd": [P, P],
 }
 # entry points that do not return a status code
 OTHER = {

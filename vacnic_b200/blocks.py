@@ -61,32 +61,30 @@ def _wgrad(rt: Runtime, lin: Lin, dy2d: torch.Tensor, x2d: torch.Tensor, bias_fr
 
 
 # --------------------------------------------------------------------------------------------------
-# scaled dot-product attention core (unfused tensor-core path: QK^T GEMM -> masked softmax -> PV GEMM)
+# scaled dot-product attention core: fused tcgen05 kernels (scores and probabilities never reach HBM)
 # --------------------------------------------------------------------------------------------------
-def sdpa_fwd(q4, k4, v4, key_mask, causal, past, scale):
-    """q4 [B,H,Sq,hd], k4/v4 [B,H,Sk,hd] (strided views).  Returns (O [B,Sq,H*hd], P [B,H,Sq,Skp])."""
-    B, H, Sq, hd = q4.shape
-    Sk = k4.shape[2]
-    Skp = _ceil8(Sk)
-    S = torch.empty(B, H, Sq, Skp, dtype=torch.float32, device=q4.device)
-    K.gemm(q4, k4, out=S[..., :Sk], alpha=scale)
-    P = K.softmax_fwd(S, key_mask, Sk, causal=causal, past=past)
-    O = torch.empty(B, Sq, H, hd, dtype=torch.bfloat16, device=q4.device)
-    K.gemm(P[..., :Sk], v4, out=O.permute(0, 2, 1, 3), b_mn=True)
-    return O.view(B, Sq, H * hd), P
+class KeyMask:
+    """uint8 key-padding mask [B, Sk] (1 = attend) plus the per-row count of leading keys that can be
+    attended at all (keys beyond it are skipped by the attention kernels)."""
+    __slots__ = ("mask", "len")
+
+    def __init__(self, mask_like: torch.Tensor):
+        self.mask = mask_like.to(torch.uint8).contiguous()
+        self.len = K.mask_key_len(self.mask)
 
 
-def sdpa_bwd(dO, q4, k4, v4, P, scale, dq4, dk4, dv4):
-    B, H, Sq, hd = q4.shape
-    Sk = k4.shape[2]
-    Skp = P.shape[-1]
-    dO4 = dO.view(B, Sq, H, hd).permute(0, 2, 1, 3)
-    dP = torch.empty(B, H, Sq, Skp, dtype=torch.float32, device=dO.device)
-    K.gemm(dO4, v4, out=dP[..., :Sk])
-    dS = K.softmax_bwd(P, dP, Sk)
-    K.gemm(P[..., :Sk], dO4, out=dv4, a_mn=True, b_mn=True)
-    K.gemm(dS[..., :Sk], k4, out=dq4, b_mn=True, alpha=scale)
-    K.gemm(dS[..., :Sk], q4, out=dk4, a_mn=True, b_mn=True, alpha=scale)
+def sdpa_fwd(q4, k4, v4, key_mask: Optional[KeyMask], causal, want_stats=True):
+    """q4 [B,H,Sq,hd], k4/v4 [B,H,Sk,hd] (strided views).  Returns (O [B,Sq,H*hd], stats [B,H,Sq,2])."""
+    if key_mask is not None and tuple(key_mask.mask.shape) != (q4.shape[0], k4.shape[2]):
+        raise ValueError(f"Attention mask should be of size {(q4.shape[0], 1, q4.shape[2], k4.shape[2])}, but is "
+                         f"{(key_mask.mask.shape[0], 1, q4.shape[2], key_mask.mask.shape[1])}")  # MFULL:516-520
+    return K.attn_fwd(q4, k4, v4, key_mask.mask if key_mask is not None else None,
+                      key_mask.len if key_mask is not None else None, causal, want_stats=want_stats)
+
+
+def sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask: Optional[KeyMask], causal, dq4, dk4, dv4):
+    K.attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, key_mask.mask if key_mask is not None else None,
+               key_mask.len if key_mask is not None else None, causal)
 
 
 def _heads(t2d: torch.Tensor, B: int, S: int, H: int, col0: int, hd: int) -> torch.Tensor:
@@ -106,7 +104,6 @@ class AttnBlockFn(torch.autograd.Function):
                 H: int, key_mask, causal: bool, use_dropout: bool, kv_col0: int, dkv_all, return_dkv_all: bool):
         B, Sq, d = x.shape
         hd = d // H
-        scale = hd ** -0.5
         x2 = x.view(B * Sq, d)
         if lin_qkv is not None:  # self attention, fused [k; v; q] projection (MFULL:444-446 order)
             qkv = K.gemm(x2, lin_qkv.w16, bias=lin_qkv.b32)
@@ -123,12 +120,13 @@ class AttnBlockFn(torch.autograd.Function):
                 Sk = kv_src.shape[1]
                 kvp = K.gemm(kv_src.view(B * Sk, d), lin_kv.w16, bias=lin_kv.b32)
             k4, v4 = _heads(kvp, B, Sk, H, 0, hd), _heads(kvp, B, Sk, H, d, hd)
-        O, P = sdpa_fwd(q4, k4, v4, key_mask, causal, 0, scale)
+        O, stats = sdpa_fwd(q4, k4, v4, key_mask, causal, want_stats=not rt.store.frozen)
         a = K.gemm(O.view(B * Sq, d), lin_o.w16, bias=lin_o.b32)
         p = rt.drop if use_dropout else 0.0
         y, mean, rstd = K.add_layernorm_fwd(a, x2, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt)
         ctx.rt, ctx.lins, ctx.ln, ctx.H, ctx.p = rt, (lin_qkv, lin_q, lin_kv, lin_o), ln, H, p
-        ctx.saved = (x2, kv_src, qkv, kvp, P, O, a, mean, rstd, q4, k4, v4)
+        ctx.saved = (x2, kv_src, qkv, kvp, stats, O, a, mean, rstd, q4, k4, v4)
+        ctx.mask = (key_mask, causal)
         hoisted = kv_pre is not None and dkv_all is not None
         ctx.dkv_pre = dkv_all.view(B * Sk, -1)[:, kv_col0:kv_col0 + 2 * d] if hoisted else None
         ctx.dkv_all = dkv_all if (hoisted and return_dkv_all) else None
@@ -139,7 +137,8 @@ class AttnBlockFn(torch.autograd.Function):
     def backward(ctx, dy):
         rt, ln, H = ctx.rt, ctx.ln, ctx.H
         lin_qkv, lin_q, lin_kv, lin_o = ctx.lins
-        x2, kv_src, qkv, kvp, P, O, a, mean, rstd, q4, k4, v4 = ctx.saved
+        x2, kv_src, qkv, kvp, stats, O, a, mean, rstd, q4, k4, v4 = ctx.saved
+        key_mask, causal = ctx.mask
         B, Sq, d, Sk = ctx.shape
         hd = d // H
         dy = dy.contiguous()
@@ -147,12 +146,12 @@ class AttnBlockFn(torch.autograd.Function):
                                        want_dx=True, p_drop=ctx.p, rng=rt.rng, salt=ln.salt)
         O2 = O.view(B * Sq, d)
         _wgrad(rt, lin_o, da, O2)
-        dO = K.gemm(da, lin_o.w16, b_mn=True)
+        dO = K.gemm(da, lin_o.w16, b_mn=True).view(B, Sq, d)
         dkv_src = None
         if lin_qkv is not None:
             dqkv = torch.empty_like(qkv)
             dk4, dv4, dq4 = (_heads(dqkv, B, Sq, H, c * d, hd) for c in range(3))
-            sdpa_bwd(dO, q4, k4, v4, P, hd ** -0.5, dq4, dk4, dv4)
+            sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4)
             _wgrad(rt, lin_qkv, dqkv, x2, bias_from=dqkv)
             K.gemm(dqkv, lin_qkv.w16, out=dsum, b_mn=True, accumulate=True)  # dx = dsum + dqkv W
         else:
@@ -160,7 +159,7 @@ class AttnBlockFn(torch.autograd.Function):
             dq4 = _heads(dq, B, Sq, H, 0, hd)
             dkvp = ctx.dkv_pre if ctx.dkv_pre is not None else torch.empty_like(kvp)
             dk4, dv4 = _heads(dkvp, B, Sk, H, 0, hd), _heads(dkvp, B, Sk, H, d, hd)
-            sdpa_bwd(dO, q4, k4, v4, P, hd ** -0.5, dq4, dk4, dv4)
+            sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4)
             _wgrad(rt, lin_q, dq, x2, bias_from=dq)
             K.gemm(dq, lin_q.w16, out=dsum, b_mn=True, accumulate=True)
             if ctx.dkv_pre is None:

@@ -1,0 +1,821 @@
+// Fused scaled-dot-product attention for sm_100a (BartAttention.forward core, MFULL:503-556: bmm(q,k^T) +
+// mask -> softmax -> bmm(p,v)), head_dim 64.  Scores never leave the SM: S = Q K^T is produced by
+// tcgen05.mma into TMEM, read back with tcgen05.ld by the softmax warps (one thread per query row, so no
+// cross-thread reductions), probabilities go to 128B-swizzled shared memory as bf16 and feed the second
+// tcgen05.mma (O += P V) whose accumulator also lives in TMEM.
+//
+// Exact (non-online) softmax in two sweeps over the key blocks: sweep 1 computes the row maxima (QK^T is
+// recomputed in sweep 2: K = 64, the tensor pipe has the headroom), sweep 2 computes exp(s - max), the row
+// sums and O.  No rescaling of O is ever needed.  Masks follow the reference: masked keys get
+// finfo(float32).min (a fully masked row degenerates to a uniform row exactly like the reference),
+// keys beyond `key_len[b]` are skipped because they contribute exactly 0.
+//
+// CTA = 128 query rows of one (batch, head); 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM
+// allocator, warps 2..5 softmax/epilogue.  96 KB of shared memory and 256 TMEM columns per CTA, so two CTAs
+// share an SM and overlap each other's MMA and exp phases.
+#include <cuda.h>
+#include <float.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+constexpr int kAQ = 128;         // query rows per CTA
+constexpr int kAK = 128;         // keys per block
+constexpr int kHD = 64;          // head dim
+constexpr int kTile = kAK * kHD * 2;  // 16 KB: one [128 x 64] bf16 tile
+constexpr int kRing = 3;
+constexpr int kAttnThreads = 192;
+constexpr int kMaxKB = 40;       // key blocks per row (Sk <= 5120)
+
+struct AttnArgs {
+  int B, H, Sq, Sk;
+  int causal;
+  float scale_log2;  // head_dim^-0.5 * log2(e)
+  const uint8_t* key_mask;  // [B][Sk], 1 = attend, or null
+  const int32_t* key_len;   // [B] or null
+  __nv_bfloat16* out;       // out[b*o_sb + row*ldo + h*64 + c]
+  long long ldo, o_sb;
+  float* stats;             // [B][H][Sq][2] = {row max in the log2 domain, 1 / row sum}, or null
+};
+
+struct AttnSmem {
+  uint64_t q_full, ring_full[kRing], ring_empty[kRing], s_full, s_empty, p_full, p_empty, o_full;
+  uint32_t tmem_slot;
+  uint8_t blk_flag[kMaxKB];  // per key block: 0 = no masking needed, 1 = per-key checks needed
+};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sRing = smem + kTile;
+  uint8_t* sP = sRing + kRing * kTile;  // [2 atoms][128 rows][128 B]
+  AttnSmem* sh = reinterpret_cast<AttnSmem*>(sP + 2 * kTile);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * kAQ;
+
+  // number of key blocks that can contribute
+  int kmax = a.Sk;
+  if (a.key_len != nullptr) {
+    const int kl = a.key_len[b];
+    if (kl > 0 && kl < kmax) kmax = kl;  // kl == 0: fully masked rows are uniform over ALL keys -> keep every block
+  }
+  if (a.causal) kmax = min(kmax, q0 + kAQ);
+  const int nkb = (kmax + kAK - 1) / kAK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&sh->q_full, 1);
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(&sh->ring_full[s], 1);
+      mbar_init(&sh->ring_empty[s], 1);
+    }
+    mbar_init(&sh->s_full, 1);
+    mbar_init(&sh->s_empty, 128);
+    mbar_init(&sh->p_full, 128);
+    mbar_init(&sh->p_empty, 1);
+    mbar_init(&sh->o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sh->tmem_slot, 256);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    // classify the key blocks once: does any key of the block need a mask decision?
+    for (int j = threadIdx.x - 64; j < nkb; j += 128) {
+      const int k0 = j * kAK;
+      bool need = (k0 + kAK > a.Sk) || (a.causal && k0 + kAK - 1 > q0);
+      if (!need && a.key_mask != nullptr) {
+        const uint8_t* mk = a.key_mask + static_cast<long long>(b) * a.Sk + k0;
+        for (int c = 0; c < kAK; ++c) need |= (mk[c] == 0);
+      }
+      sh->blk_flag[j] = need ? 1 : 0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_slot;
+  const uint32_t tmem_s = tmem_base;         // 128 columns
+  const uint32_t tmem_o = tmem_base + 128;   // 64 columns
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(&sh->q_full, kTile);
+      tma_load_4d(sQ, &tmQ, &sh->q_full, 0, q0, h, b);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto push = [&](const CUtensorMap* tm, int row0) {
+        mbar_wait(&sh->ring_empty[slot], phase ^ 1u);
+        mbar_expect_tx(&sh->ring_full[slot], kTile);
+        tma_load_4d(sRing + slot * kTile, tm, &sh->ring_full[slot], 0, row0, h, b);
+        if (++slot == kRing) { slot = 0; phase ^= 1u; }
+      };
+      for (int j = 0; j < nkb; ++j) push(&tmK, j * kAK);  // sweep 1: keys only
+      for (int j = 0; j < nkb; ++j) {                     // sweep 2: keys and values in consumption order
+        push(&tmK, j * kAK);
+        push(&tmV, j * kAK);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kAQ, kAK, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(kAQ, kHD, 0, 1);
+      int slot = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      mbar_wait(&sh->q_full, 0);
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      for (int sweep = 0; sweep < 2; ++sweep) {
+        for (int j = 0; j < nkb; ++j, ++it) {
+          mbar_wait(&sh->ring_full[slot], phase);
+          mbar_wait(&sh->s_empty, (it & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sRing + slot * kTile);
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k)
+            umma_bf16_ss(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&sh->ring_empty[slot]);
+          umma_commit(&sh->s_full);
+          if (++slot == kRing) { slot = 0; phase ^= 1u; }
+          if (sweep == 1) {
+            mbar_wait(&sh->ring_full[slot], phase);
+            mbar_wait(&sh->p_full, j & 1u);
+            tc_fence_after();
+            const uint32_t v_addr = smem_u32(sRing + slot * kTile);
+#pragma unroll
+            for (int kk = 0; kk < kAK / 16; ++kk)
+              umma_bf16_ss(tmem_o, make_smem_desc_sw128(p_addr + (kk >> 2) * kTile + (kk & 3) * 32, 16, 1024),
+                           make_smem_desc_sw128(v_addr + kk * 2048, kAK * 128, 1024), idesc_o,
+                           (j | kk) != 0 ? 1u : 0u);
+            umma_commit(&sh->ring_empty[slot]);
+            umma_commit(&sh->p_empty);
+            if (++slot == kRing) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+      umma_commit(&sh->o_full);
+    }
+  } else {
+    // ------------------------------------------------------------ softmax + epilogue: thread = query row
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;   // row inside the tile == TMEM lane
+    const int row = q0 + r;
+    const uint32_t t_s = tmem_s + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint8_t* mk = a.key_mask ? a.key_mask + static_cast<long long>(b) * a.Sk : nullptr;
+    const float c2 = a.scale_log2;
+    uint32_t it = 0;
+    // masked score in the log2 domain
+    auto masked = [&](float s, int key) -> float {
+      if (key >= a.Sk) return -INFINITY;
+      if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) return -FLT_MAX;
+      return s * c2;
+    };
+    // ---- sweep 1: row maximum
+    float m = -INFINITY;
+    for (int j = 0; j < nkb; ++j, ++it) {
+      mbar_wait(&sh->s_full, it & 1u);
+      tc_fence_after();
+      const bool need = sh->blk_flag[j] != 0;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t x0[32], x1[32];
+        tmem_ld_32x32(t_s + half * 64, x0);
+        tmem_ld_32x32(t_s + half * 64 + 32, x1);
+        tmem_ld_wait();
+        if (!need) {
+          float mm = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mm = fmaxf(mm, fmaxf(__uint_as_float(x0[c]), __uint_as_float(x1[c])));
+          m = fmaxf(m, mm * c2);  // c2 > 0: max commutes with the scaling
+        } else {
+          const int kb = j * kAK + half * 64;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            m = fmaxf(m, masked(__uint_as_float(x0[c]), kb + c));
+            m = fmaxf(m, masked(__uint_as_float(x1[c]), kb + 32 + c));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh->s_empty);
+    }
+    // ---- sweep 2: p = 2^(t - m), row sum, P -> shared memory (bf16, SWIZZLE_128B K-major)
+    float l = 0.f;
+    const uint32_t p_row = smem_u32(sP) + r * 128;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    for (int j = 0; j < nkb; ++j, ++it) {
+      mbar_wait(&sh->s_full, it & 1u);
+      tc_fence_after();
+      if (j > 0) mbar_wait(&sh->p_empty, (j - 1) & 1u);
+      const bool need = sh->blk_flag[j] != 0;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t x0[32], x1[32];
+        tmem_ld_32x32(t_s + half * 64, x0);
+        tmem_ld_32x32(t_s + half * 64 + 32, x1);
+        tmem_ld_wait();
+        if (half == 1) {  // all of S_j is in registers: the tensor pipe may overwrite it
+          tc_fence_before();
+          mbar_arrive(&sh->s_empty);
+        }
+        const int kb = j * kAK + half * 64;
+        const uint32_t atom = p_row + half * kTile;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {  // 8 chunks of 8 keys (16 B)
+          float p[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = q * 8 + e;
+            const float s = __uint_as_float(c < 32 ? x0[c] : x1[c - 32]);
+            const float t = need ? masked(s, kb + c) : s * c2;
+            p[e] = ex2f(t - m);
+          }
+          const uint32_t w0 = pack_bf16x2(p[0], p[1]), w1 = pack_bf16x2(p[2], p[3]);
+          const uint32_t w2 = pack_bf16x2(p[4], p[5]), w3 = pack_bf16x2(p[6], p[7]);
+          float2 f;
+          f = unpack_bf16x2(w0); l += f.x + f.y;
+          f = unpack_bf16x2(w1); l += f.x + f.y;
+          f = unpack_bf16x2(w2); l += f.x + f.y;
+          f = unpack_bf16x2(w3); l += f.x + f.y;
+          st_shared_v4(atom + ((static_cast<uint32_t>(q) ^ sw) << 4), w0, w1, w2, w3);
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor pipe (async proxy)
+      mbar_arrive(&sh->p_full);
+    }
+    // ---- epilogue: O / l -> bf16
+    mbar_wait(&sh->o_full, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const uint32_t t_o = tmem_o + (static_cast<uint32_t>(quad * 32) << 16);
+    uint32_t o0[32], o1[32];
+    tmem_ld_32x32(t_o, o0);
+    tmem_ld_32x32(t_o + 32, o1);
+    tmem_ld_wait();
+    if (row < a.Sq) {
+      __nv_bfloat16* op = a.out + static_cast<long long>(b) * a.o_sb + static_cast<long long>(row) * a.ldo + h * kHD;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o0[8 * q + 0]) * inv, __uint_as_float(o0[8 * q + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(o0[8 * q + 2]) * inv, __uint_as_float(o0[8 * q + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(o0[8 * q + 4]) * inv, __uint_as_float(o0[8 * q + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(o0[8 * q + 6]) * inv, __uint_as_float(o0[8 * q + 7]) * inv);
+        reinterpret_cast<uint4*>(op)[q] = u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o1[8 * q + 0]) * inv, __uint_as_float(o1[8 * q + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(o1[8 * q + 2]) * inv, __uint_as_float(o1[8 * q + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(o1[8 * q + 4]) * inv, __uint_as_float(o1[8 * q + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(o1[8 * q + 6]) * inv, __uint_as_float(o1[8 * q + 7]) * inv);
+        reinterpret_cast<uint4*>(op)[4 + q] = u;
+      }
+      if (a.stats != nullptr)
+        reinterpret_cast<float2*>(a.stats)[(static_cast<long long>(b) * a.H + h) * a.Sq + row] = make_float2(m, inv);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+
+// =================================================================================================
+// Backward.  Two kernels, both "thread = row of a 128-row tile", both with 256 TMEM columns and two CTAs
+// per SM, both recomputing P from the saved row statistics {max, 1/sum}:
+//   attn_bwd_dq_kernel   CTA = 128 queries; per 64-key block: S = Q K^T, dP = dO V^T (TMEM) ->
+//                        dS = P * (dP - delta) * scale (bf16, shared memory) -> dQ += dS K.  Also computes
+//                        delta = rowsum(dO * O) and stores it for the second kernel.
+//   attn_bwd_dkv_kernel  CTA = 128 keys; per 64-query block: S^T = K Q^T, dP^T = V dO^T -> P^T and dS^T
+//                        (shared memory) -> dV += P^T dO, dK += dS^T Q.
+// Nothing is accumulated with atomics: results are deterministic.
+// =================================================================================================
+constexpr int kHalfTile = 64 * kHD * 2;  // 8 KB: one [64 x 64] bf16 tile
+
+struct AttnBwdArgs {
+  int B, H, Sq, Sk;
+  int causal;
+  float scale, scale_log2;
+  const uint8_t* key_mask;
+  const int32_t* key_len;
+  const float* stats;   // [B][H][Sq][2]
+  float* delta;         // [B][H][Sq]
+  __nv_bfloat16* dq; long long lddq, dq_sh, dq_sb;
+  __nv_bfloat16* dk; long long lddk, dk_sh, dk_sb;
+  __nv_bfloat16* dv; long long lddv, dv_sh, dv_sb;
+};
+
+struct BwdSmem {
+  uint64_t in_full, st_full[2], st_empty[2], sdp_full, s_empty, ds_full, ds_empty, acc_full;
+  uint32_t tmem_slot;
+  float stat[2][3][64];  // dkv kernel: per query block {max, 1/sum, delta}
+};
+
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+  return u;
+}
+__device__ __forceinline__ void store_row64(__nv_bfloat16* op, const uint32_t (&o0)[32], const uint32_t (&o1)[32], float f) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(o0[8 * q + 0]) * f, __uint_as_float(o0[8 * q + 1]) * f);
+    u.y = pack_bf16x2(__uint_as_float(o0[8 * q + 2]) * f, __uint_as_float(o0[8 * q + 3]) * f);
+    u.z = pack_bf16x2(__uint_as_float(o0[8 * q + 4]) * f, __uint_as_float(o0[8 * q + 5]) * f);
+    u.w = pack_bf16x2(__uint_as_float(o0[8 * q + 6]) * f, __uint_as_float(o0[8 * q + 7]) * f);
+    reinterpret_cast<uint4*>(op)[q] = u;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(o1[8 * q + 0]) * f, __uint_as_float(o1[8 * q + 1]) * f);
+    u.y = pack_bf16x2(__uint_as_float(o1[8 * q + 2]) * f, __uint_as_float(o1[8 * q + 3]) * f);
+    u.z = pack_bf16x2(__uint_as_float(o1[8 * q + 4]) * f, __uint_as_float(o1[8 * q + 5]) * f);
+    u.w = pack_bf16x2(__uint_as_float(o1[8 * q + 6]) * f, __uint_as_float(o1[8 * q + 7]) * f);
+    reinterpret_cast<uint4*>(op)[4 + q] = u;
+  }
+}
+
+__device__ __forceinline__ void bwd_init(BwdSmem* sh, int warp, int lane) {
+  if (warp == 0 && lane == 0) {
+    mbar_init(&sh->in_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sh->st_full[s], 1);
+      mbar_init(&sh->st_empty[s], 1);
+    }
+    mbar_init(&sh->sdp_full, 1);
+    mbar_init(&sh->s_empty, 128);
+    mbar_init(&sh->ds_full, 128);
+    mbar_init(&sh->ds_empty, 1);
+    mbar_init(&sh->acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sh->tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmO, const AttnBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                    // [128][64]
+  uint8_t* sDO = sQ + kTile;             // [128][64]
+  uint8_t* sDS = sDO + kTile;            // [128 rows][64 keys]; holds the O tile first (delta)
+  uint8_t* sKV = sDS + kTile;            // 2 stages x (K_j 8 KB | V_j 8 KB)
+  BwdSmem* sh = reinterpret_cast<BwdSmem*>(sKV + 2 * kTile);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * kAQ;
+  int kmax = a.Sk;
+  if (a.key_len != nullptr) {
+    const int kl = a.key_len[b];
+    if (kl > 0 && kl < kmax) kmax = kl;
+  }
+  if (a.causal) kmax = min(kmax, q0 + kAQ);
+  const int nkb = (kmax + 63) / 64;
+  bwd_init(sh, warp, lane);
+  const uint32_t tmem_base = sh->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      mbar_expect_tx(&sh->in_full, 3 * kTile);
+      tma_load_4d(sQ, &tmQ, &sh->in_full, 0, q0, h, b);
+      tma_load_4d(sDO, &tmDO, &sh->in_full, 0, q0, h, b);
+      tma_load_4d(sDS, &tmO, &sh->in_full, 0, q0, h, b);
+      for (int j = 0; j < nkb; ++j) {
+        const int st = j & 1;
+        mbar_wait(&sh->st_empty[st], ((j >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&sh->st_full[st], 2 * kHalfTile);
+        tma_load_4d(sKV + st * kTile, &tmK, &sh->st_full[st], 0, j * 64, h, b);
+        tma_load_4d(sKV + st * kTile + kHalfTile, &tmV, &sh->st_full[st], 0, j * 64, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kAQ, 64, 0, 0);
+      constexpr uint32_t idesc_q = make_idesc_bf16(kAQ, kHD, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
+      mbar_wait(&sh->in_full, 0);
+      for (int j = 0; j < nkb; ++j) {
+        const int st = j & 1;
+        mbar_wait(&sh->st_full[st], (j >> 1) & 1u);
+        mbar_wait(&sh->s_empty, (j & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + st * kTile), v_addr = k_addr + kHalfTile;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + 64, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&sh->sdp_full);
+        mbar_wait(&sh->ds_full, j & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // dQ += dS K_j : K = 64 keys, B = K_j [key][hd] (MN-major)
+          umma_bf16_ss(tmem_base + 128, make_smem_desc_sw128(ds_addr + kk * 32, 16, 1024),
+                       make_smem_desc_sw128(k_addr + kk * 2048, 64 * 128, 1024), idesc_q, (j | kk) != 0 ? 1u : 0u);
+        umma_commit(&sh->st_empty[st]);
+        umma_commit(&sh->ds_empty);
+      }
+      umma_commit(&sh->acc_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int row = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint8_t* mk = a.key_mask ? a.key_mask + static_cast<long long>(b) * a.Sk : nullptr;
+    const float c2 = a.scale_log2;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    // ---- delta = rowsum(dO * O)
+    mbar_wait(&sh->in_full, 0);
+    float delta = 0.f;
+    {
+      const uint32_t do_row = smem_u32(sDO) + r * 128, o_row = smem_u32(sDS) + r * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t off = (static_cast<uint32_t>(q) ^ sw) << 4;
+        float x[8], y[8];
+        const uint4 u = ld_shared_v4(do_row + off), w = ld_shared_v4(o_row + off);
+        float2 t;
+        t = unpack_bf16x2(u.x); x[0] = t.x; x[1] = t.y; t = unpack_bf16x2(u.y); x[2] = t.x; x[3] = t.y;
+        t = unpack_bf16x2(u.z); x[4] = t.x; x[5] = t.y; t = unpack_bf16x2(u.w); x[6] = t.x; x[7] = t.y;
+        t = unpack_bf16x2(w.x); y[0] = t.x; y[1] = t.y; t = unpack_bf16x2(w.y); y[2] = t.x; y[3] = t.y;
+        t = unpack_bf16x2(w.z); y[4] = t.x; y[5] = t.y; t = unpack_bf16x2(w.w); y[6] = t.x; y[7] = t.y;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) delta += x[e] * y[e];
+      }
+    }
+    float m = 0.f, inv_l = 0.f;
+    if (row < a.Sq) {
+      const long long si = (static_cast<long long>(b) * a.H + h) * a.Sq + row;
+      const float2 st = reinterpret_cast<const float2*>(a.stats)[si];
+      m = st.x;
+      inv_l = st.y;
+      a.delta[si] = delta;
+    }
+    const uint32_t ds_row = smem_u32(sDS) + r * 128;
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(&sh->sdp_full, j & 1u);
+      tc_fence_after();
+      if (j > 0) mbar_wait(&sh->ds_empty, (j - 1) & 1u);
+      const int kb0 = j * 64;
+      const bool need = (kb0 + 64 > a.Sk) || (a.causal && kb0 + 63 > q0) || mk != nullptr;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t xs[32], xp[32];
+        tmem_ld_32x32(tmem_base + lane_off + half * 32, xs);
+        tmem_ld_32x32(tmem_base + lane_off + 64 + half * 32, xp);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          mbar_arrive(&sh->s_empty);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = q * 8 + e;
+            const int key = kb0 + half * 32 + c;
+            float t = __uint_as_float(xs[c]) * c2;
+            if (need) {
+              if (key >= a.Sk) t = -INFINITY;
+              else if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) t = -FLT_MAX;
+            }
+            const float p = ex2f(t - m) * inv_l;
+            ds[e] = p * (__uint_as_float(xp[c]) - delta) * a.scale;
+          }
+          st_shared_v4(ds_row + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4), pack_bf16x2(ds[0], ds[1]),
+                       pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&sh->ds_full);
+    }
+    mbar_wait(&sh->acc_full, 0);
+    tc_fence_after();
+    uint32_t o0[32], o1[32];
+    tmem_ld_32x32(tmem_base + lane_off + 128, o0);
+    tmem_ld_32x32(tmem_base + lane_off + 160, o1);
+    tmem_ld_wait();
+    if (row < a.Sq)
+      store_row64(a.dq + static_cast<long long>(b) * a.dq_sb + h * a.dq_sh + static_cast<long long>(row) * a.lddq, o0, o1, 1.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                    const AttnBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sK = smem;                    // [128 keys][64]
+  uint8_t* sV = sK + kTile;
+  uint8_t* sPT = sV + kTile;             // [128 keys][64 queries]
+  uint8_t* sDST = sPT + kTile;
+  uint8_t* sQD = sDST + kTile;           // 2 stages x (Q_i 8 KB | dO_i 8 KB)
+  BwdSmem* sh = reinterpret_cast<BwdSmem*>(sQD + 2 * kTile);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = kb * kAK;
+  const int kl = a.key_len != nullptr ? a.key_len[b] : 0;
+  if (kl > 0 && k0 >= kl) {
+    // every key of this block is masked for every query: dK = dV = 0
+    if (warp >= 2) {
+      const int key = k0 + (warp - 2) * 32 + lane;
+      if (key < a.Sk) {
+        uint4* pk = reinterpret_cast<uint4*>(a.dk + static_cast<long long>(b) * a.dk_sb + h * a.dk_sh + static_cast<long long>(key) * a.lddk);
+        uint4* pv = reinterpret_cast<uint4*>(a.dv + static_cast<long long>(b) * a.dv_sb + h * a.dv_sh + static_cast<long long>(key) * a.lddv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { pk[q] = make_uint4(0, 0, 0, 0); pv[q] = make_uint4(0, 0, 0, 0); }
+      }
+    }
+    return;
+  }
+  const int i0 = a.causal ? k0 / 64 : 0;           // query blocks entirely above the diagonal contribute nothing
+  const int nqb = (a.Sq + 63) / 64;
+  bwd_init(sh, warp, lane);
+  const uint32_t tmem_base = sh->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmDO);
+      mbar_expect_tx(&sh->in_full, 2 * kTile);
+      tma_load_4d(sK, &tmK, &sh->in_full, 0, k0, h, b);
+      tma_load_4d(sV, &tmV, &sh->in_full, 0, k0, h, b);
+      for (int i = i0, n = 0; i < nqb; ++i, ++n) {
+        const int st = n & 1;
+        mbar_wait(&sh->st_empty[st], ((n >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&sh->st_full[st], 2 * kHalfTile);
+        tma_load_4d(sQD + st * kTile, &tmQ, &sh->st_full[st], 0, i * 64, h, b);
+        tma_load_4d(sQD + st * kTile + kHalfTile, &tmDO, &sh->st_full[st], 0, i * 64, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kAK, 64, 0, 0);
+      constexpr uint32_t idesc_g = make_idesc_bf16(kAK, kHD, 0, 1);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+      mbar_wait(&sh->in_full, 0);
+      for (int i = i0, n = 0; i < nqb; ++i, ++n) {
+        const int st = n & 1;
+        mbar_wait(&sh->st_full[st], (n >> 1) & 1u);
+        mbar_wait(&sh->s_empty, (n & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQD + st * kTile), do_addr = q_addr + kHalfTile;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S^T = K Q_i^T
+          umma_bf16_ss(tmem_base, make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(q_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP^T = V dO_i^T
+          umma_bf16_ss(tmem_base + 64, make_smem_desc_sw128(v_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(do_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&sh->sdp_full);
+        mbar_wait(&sh->ds_full, n & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_i
+          umma_bf16_ss(tmem_base + 128, make_smem_desc_sw128(pt_addr + kk * 32, 16, 1024),
+                       make_smem_desc_sw128(do_addr + kk * 2048, 64 * 128, 1024), idesc_g, (n | kk) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q_i
+          umma_bf16_ss(tmem_base + 192, make_smem_desc_sw128(dst_addr + kk * 32, 16, 1024),
+                       make_smem_desc_sw128(q_addr + kk * 2048, 64 * 128, 1024), idesc_g, (n | kk) != 0 ? 1u : 0u);
+        umma_commit(&sh->st_empty[st]);
+        umma_commit(&sh->ds_empty);
+      }
+      umma_commit(&sh->acc_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int key = k0 + r;
+    const int tid = threadIdx.x - 64;  // 0..127
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const bool key_oob = key >= a.Sk;
+    const bool key_masked = !key_oob && a.key_mask != nullptr && a.key_mask[static_cast<long long>(b) * a.Sk + key] == 0;
+    const float c2 = a.scale_log2;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    const uint32_t pt_row = smem_u32(sPT) + r * 128, dst_row = smem_u32(sDST) + r * 128;
+    const long long sbase = (static_cast<long long>(b) * a.H + h) * a.Sq;
+    for (int i = i0, n = 0; i < nqb; ++i, ++n) {
+      // stage the row statistics of the 64 queries of this block (double buffered; ds_empty(n-2) ordering is
+      // implied: buffer n&1 was last read in step n-2, whose writes all threads finished before ds_full(n-2))
+      float* stq = &sh->stat[n & 1][0][0];
+      if (tid < 64) {
+        const int qrow = i * 64 + tid;
+        float2 st = make_float2(0.f, 0.f);
+        float dl = 0.f;
+        if (qrow < a.Sq) {
+          st = reinterpret_cast<const float2*>(a.stats)[sbase + qrow];
+          dl = a.delta[sbase + qrow];
+        }
+        stq[tid] = st.x;
+        stq[64 + tid] = st.y;   // 0 for query rows beyond Sq -> p = 0
+        stq[128 + tid] = dl;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&sh->sdp_full, n & 1u);
+      tc_fence_after();
+      if (n > 0) mbar_wait(&sh->ds_empty, (n - 1) & 1u);
+      const int qb0 = i * 64;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t xs[32], xp[32];
+        tmem_ld_32x32(tmem_base + lane_off + half * 32, xs);
+        tmem_ld_32x32(tmem_base + lane_off + 64 + half * 32, xp);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          mbar_arrive(&sh->s_empty);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float pp[8], ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = half * 32 + q * 8 + e;
+            float t = __uint_as_float(xs[q * 8 + e]) * c2;
+            if (key_oob) t = -INFINITY;
+            else if (key_masked || (a.causal && key > qb0 + c)) t = -FLT_MAX;
+            const float p = ex2f(t - stq[c]) * stq[64 + c];
+            pp[e] = p;
+            ds[e] = p * (__uint_as_float(xp[q * 8 + e]) - stq[128 + c]) * a.scale;
+          }
+          const uint32_t off = (static_cast<uint32_t>(half * 4 + q) ^ sw) << 4;
+          st_shared_v4(pt_row + off, pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]), pack_bf16x2(pp[4], pp[5]),
+                       pack_bf16x2(pp[6], pp[7]));
+          st_shared_v4(dst_row + off, pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
+                       pack_bf16x2(ds[6], ds[7]));
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&sh->ds_full);
+    }
+    mbar_wait(&sh->acc_full, 0);
+    tc_fence_after();
+    uint32_t o0[32], o1[32];
+    tmem_ld_32x32(tmem_base + lane_off + 128, o0);
+    tmem_ld_32x32(tmem_base + lane_off + 160, o1);
+    tmem_ld_wait();
+    if (!key_oob)
+      store_row64(a.dv + static_cast<long long>(b) * a.dv_sb + h * a.dv_sh + static_cast<long long>(key) * a.lddv, o0, o1, 1.f);
+    tmem_ld_32x32(tmem_base + lane_off + 192, o0);
+    tmem_ld_32x32(tmem_base + lane_off + 224, o1);
+    tmem_ld_wait();
+    if (!key_oob)
+      store_row64(a.dk + static_cast<long long>(b) * a.dk_sb + h * a.dk_sh + static_cast<long long>(key) * a.lddk, o0, o1, 1.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+constexpr int kBwdDqSmemBytes = 5 * kTile + static_cast<int>(sizeof(BwdSmem)) + 1024;
+constexpr int kBwdDkvSmemBytes = 6 * kTile + static_cast<int>(sizeof(BwdSmem)) + 1024;
+
+constexpr int kAttnSmemBytes = kTile * (1 + kRing + 2) + static_cast<int>(sizeof(AttnSmem)) + 1024;
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vacnic_attn_fwd(const vacnic_attn_desc* d, void* stream) {
+  if (d == nullptr) return fail(VACNIC_EINVAL, "attn_fwd: null descriptor");
+  VB_REQUIRE(d->q && d->k && d->v && d->out, "attn_fwd: null pointer");
+  VB_REQUIRE(d->head_dim == 64, "attn_fwd: head_dim must be 64 (BART-base / BART-large)");
+  VB_REQUIRE(d->B > 0 && d->H > 0 && d->Sq > 0 && d->Sk > 0 && d->Sk <= kMaxKB * kAK, "attn_fwd: bad shape (Sk <= %d)", kMaxKB * kAK);
+  VB_REQUIRE(d->ldo % 8 == 0 && d->o_sb % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "attn_fwd: out must be 16-byte aligned");
+  CUtensorMap tq, tk, tv;
+  int rc = make_operand_map(&tq, d->q, false, d->Sq, 64, d->ldq, d->H, d->q_sh, d->B, d->q_sb, kAQ);
+  if (rc != VACNIC_OK) return rc;
+  rc = make_operand_map(&tk, d->k, false, d->Sk, 64, d->ldk, d->H, d->k_sh, d->B, d->k_sb, kAK);
+  if (rc != VACNIC_OK) return rc;
+  rc = make_operand_map(&tv, d->v, false, d->Sk, 64, d->ldv, d->H, d->v_sh, d->B, d->v_sb, kAK);
+  if (rc != VACNIC_OK) return rc;
+  AttnArgs a;
+  a.B = d->B; a.H = d->H; a.Sq = d->Sq; a.Sk = d->Sk; a.causal = d->causal;
+  a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(d->head_dim));
+  a.key_mask = d->key_mask; a.key_len = d->key_len;
+  a.out = static_cast<__nv_bfloat16*>(d->out); a.ldo = d->ldo; a.o_sb = d->o_sb;
+  a.stats = d->stats;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    if (e != cudaSuccess) return fail(VACNIC_ECUDA, "attn_fwd: cudaFuncSetAttribute(smem=%d): %s", kAttnSmemBytes, cudaGetErrorString(e));
+    configured = true;
+  }
+  const dim3 grid((d->Sq + kAQ - 1) / kAQ, d->H, d->B);
+  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+  count_launch();
+  return check_last("attn_fwd launch");
+}
+
+extern "C" int vacnic_attn_bwd(const vacnic_attn_desc* d, void* stream) {
+  if (d == nullptr) return fail(VACNIC_EINVAL, "attn_bwd: null descriptor");
+  VB_REQUIRE(d->q && d->k && d->v && d->out && d->dout && d->dq && d->dk && d->dv && d->stats && d->delta, "attn_bwd: null pointer");
+  VB_REQUIRE(d->head_dim == 64, "attn_bwd: head_dim must be 64");
+  VB_REQUIRE(d->B > 0 && d->H > 0 && d->Sq > 0 && d->Sk > 0, "attn_bwd: bad shape");
+  for (const void* p : {static_cast<const void*>(d->dq), static_cast<const void*>(d->dk), static_cast<const void*>(d->dv)})
+    VB_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "attn_bwd: gradient buffers must be 16-byte aligned");
+  VB_REQUIRE(d->lddq % 8 == 0 && d->lddk % 8 == 0 && d->lddv % 8 == 0 && d->dq_sh % 8 == 0 && d->dk_sh % 8 == 0 && d->dv_sh % 8 == 0 &&
+                 d->dq_sb % 8 == 0 && d->dk_sb % 8 == 0 && d->dv_sb % 8 == 0, "attn_bwd: gradient strides must be multiples of 8");
+  CUtensorMap q128, q64, k128, k64, v128, v64, do128, do64, o128;
+  int rc;
+#define VB_MAP(tm, base, rows, ld, sh, sb, box)                                                        \
+  rc = make_operand_map(&tm, base, false, rows, 64, ld, d->H, sh, d->B, sb, box);                      \
+  if (rc != VACNIC_OK) return rc;
+  VB_MAP(q128, d->q, d->Sq, d->ldq, d->q_sh, d->q_sb, 128)
+  VB_MAP(q64, d->q, d->Sq, d->ldq, d->q_sh, d->q_sb, 64)
+  VB_MAP(k128, d->k, d->Sk, d->ldk, d->k_sh, d->k_sb, 128)
+  VB_MAP(k64, d->k, d->Sk, d->ldk, d->k_sh, d->k_sb, 64)
+  VB_MAP(v128, d->v, d->Sk, d->ldv, d->v_sh, d->v_sb, 128)
+  VB_MAP(v64, d->v, d->Sk, d->ldv, d->v_sh, d->v_sb, 64)
+  VB_MAP(do128, d->dout, d->Sq, d->lddo, 64, d->do_sb, 128)
+  VB_MAP(do64, d->dout, d->Sq, d->lddo, 64, d->do_sb, 64)
+  VB_MAP(o128, d->out, d->Sq, d->ldo, 64, d->o_sb, 128)
+#undef VB_MAP
+  AttnBwdArgs a;
+  a.B = d->B; a.H = d->H; a.Sq = d->Sq; a.Sk = d->Sk; a.causal = d->causal;
+  a.scale = 1.0f / sqrtf(static_cast<float>(d->head_dim));
+  a.scale_log2 = 1.4426950408889634f * a.scale;
+  a.key_mask = d->key_mask; a.key_len = d->key_len; a.stats = d->stats; a.delta = d->delta;
+  a.dq = static_cast<__nv_bfloat16*>(d->dq); a.lddq = d->lddq; a.dq_sh = d->dq_sh; a.dq_sb = d->dq_sb;
+  a.dk = static_cast<__nv_bfloat16*>(d->dk); a.lddk = d->lddk; a.dk_sh = d->dk_sh; a.dk_sb = d->dk_sb;
+  a.dv = static_cast<__nv_bfloat16*>(d->dv); a.lddv = d->lddv; a.dv_sh = d->dv_sh; a.dv_sb = d->dv_sb;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdDqSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdDkvSmemBytes);
+    if (e != cudaSuccess) return fail(VACNIC_ECUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  attn_bwd_dq_kernel<<<dim3((d->Sq + kAQ - 1) / kAQ, d->H, d->B), kAttnThreads, kBwdDqSmemBytes, s>>>(q128, k64, v64, do128, o128, a);
+  count_launch();
+  rc = check_last("attn_bwd dq launch");
+  if (rc != VACNIC_OK) return rc;
+  attn_bwd_dkv_kernel<<<dim3((d->Sk + kAK - 1) / kAK, d->H, d->B), kAttnThreads, kBwdDkvSmemBytes, s>>>(q64, k128, v128, do64, a);
+  count_launch();
+  return check_last("attn_bwd dkv launch");
+}

@@ -359,9 +359,9 @@ static EncodeTiledFn get_encode_fn() {
 
 // Tensor map for one operand.  K-major: dims (K, rows, b0, b1), box (64, box_rows).
 // MN-major: dims (rows, K, b0, b1), box (64, 64).
-static int make_operand_map(CUtensorMap* tm, const void* base, bool mn_major, int rows, int K,
-                            long long ld, int batch0, long long sb0, int batch1, long long sb1,
-                            int box_rows) {
+int make_operand_map(CUtensorMap* tm, const void* base, bool mn_major, int rows, int K,
+                     long long ld, int batch0, long long sb0, int batch1, long long sb1,
+                     int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return fail(VACNIC_EDEVICE, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[4];

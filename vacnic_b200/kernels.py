@@ -8,7 +8,7 @@ import torch
 
 from . import lib as _l
 from .lib import (ACT_GELU, ACT_NONE, ACT_TANH, DT_BF16, DT_F32, MASK_CAUSAL, MASK_KEYPAD,  # noqa: F401
-                  MASK_NONE, GemmDesc, check, lib, ptr, stream_ptr)
+                  MASK_NONE, AttnDesc, GemmDesc, check, lib, ptr, stream_ptr)
 
 
 PROFILE = None  # set to a list to collect (flops, start_event, end_event, shape) per GEMM launch
@@ -375,3 +375,54 @@ def greedy_step(top_idx, seq, unfinished, flags, cur_len, rows, maxT, max_len, e
 
 def advance_len(cur_len):
     check(lib().vacnic_advance_len(ptr(cur_len), stream_ptr()), "vacnic_advance_len")
+
+
+# ------------------------------------------------------------------------------------------------
+# fused attention (csrc/attn_sm100.cu)
+# ------------------------------------------------------------------------------------------------
+def _attn_desc(q4, k4, v4, key_mask, key_len, causal):
+    B, H, Sq, hd = q4.shape
+    Sk = k4.shape[2]
+    for t in (q4, k4, v4):
+        if t.dtype != torch.bfloat16 or t.stride(3) != 1:
+            raise ValueError("attention operands must be bf16 [B,H,S,hd] views with innermost stride 1")
+    _require_cuda(q4, k4, v4, key_mask, key_len)
+    if key_mask is not None and (key_mask.dtype != torch.uint8 or tuple(key_mask.shape) != (B, Sk) or not key_mask.is_contiguous()):
+        raise ValueError(f"Attention mask should be of size {(B, 1, Sq, Sk)}: expected a contiguous uint8 key mask [{B}, {Sk}]")
+    d = AttnDesc()
+    d.B, d.H, d.Sq, d.Sk, d.head_dim, d.causal = B, H, Sq, Sk, hd, int(causal)
+    d.q, d.ldq, d.q_sh, d.q_sb = q4.data_ptr(), q4.stride(2), q4.stride(1), q4.stride(0)
+    d.k, d.ldk, d.k_sh, d.k_sb = k4.data_ptr(), k4.stride(2), k4.stride(1), k4.stride(0)
+    d.v, d.ldv, d.v_sh, d.v_sb = v4.data_ptr(), v4.stride(2), v4.stride(1), v4.stride(0)
+    d.key_mask, d.key_len = ptr(key_mask), ptr(key_len)
+    return d
+
+
+def attn_fwd(q4, k4, v4, key_mask=None, key_len=None, causal=False, want_stats=True):
+    """Fused softmax(q k^T * hd^-0.5 + mask) v.  q4 [B,H,Sq,64], k4/v4 [B,H,Sk,64] strided views.
+    Returns (O bf16 [B,Sq,H*64], stats fp32 [B,H,Sq,2] or None)."""
+    B, H, Sq, hd = q4.shape
+    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal)
+    out = torch.empty(B, Sq, H * hd, dtype=torch.bfloat16, device=q4.device)
+    stats = torch.empty(B, H, Sq, 2, dtype=torch.float32, device=q4.device) if want_stats else None
+    d.out, d.ldo, d.o_sb, d.stats = out.data_ptr(), out.stride(1), out.stride(0), ptr(stats)
+    check(lib().vacnic_attn_fwd(C.byref(d), stream_ptr()), "vacnic_attn_fwd")
+    return out, stats
+
+
+def attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, key_mask=None, key_len=None, causal=False):
+    """Gradients of attn_fwd.  dO / O bf16 [B,Sq,H*64] (row stride = stride(1), innermost 1); dq4/dk4/dv4 are
+    [B,H,S,64] strided views that receive the results (dq, dk include the hd^-0.5 factor)."""
+    B, H, Sq, hd = q4.shape
+    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal)
+    for t in (dO, O):
+        if t.dtype != torch.bfloat16 or t.stride(2) != 1 or tuple(t.shape) != (B, Sq, H * hd):
+            raise ValueError("attn_bwd: dO / O must be bf16 [B,Sq,H*hd] with innermost stride 1")
+    delta = torch.empty(B, H, Sq, dtype=torch.float32, device=q4.device)
+    d.out, d.ldo, d.o_sb, d.stats = O.data_ptr(), O.stride(1), O.stride(0), ptr(stats)
+    d.dout, d.lddo, d.do_sb = dO.data_ptr(), dO.stride(1), dO.stride(0)
+    d.dq, d.lddq, d.dq_sh, d.dq_sb = dq4.data_ptr(), dq4.stride(2), dq4.stride(1), dq4.stride(0)
+    d.dk, d.lddk, d.dk_sh, d.dk_sb = dk4.data_ptr(), dk4.stride(2), dk4.stride(1), dk4.stride(0)
+    d.dv, d.lddv, d.dv_sh, d.dv_sb = dv4.data_ptr(), dv4.stride(2), dv4.stride(1), dv4.stride(0)
+    d.delta = delta.data_ptr()
+    check(lib().vacnic_attn_bwd(C.byref(d), stream_ptr()), "vacnic_attn_bwd")

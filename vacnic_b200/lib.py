@@ -36,6 +36,22 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32), ("head_dim", C.c_int32), ("causal", C.c_int32),
+        ("q", C.c_void_p), ("ldq", C.c_int64), ("q_sh", C.c_int64), ("q_sb", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64), ("k_sh", C.c_int64), ("k_sb", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64), ("v_sh", C.c_int64), ("v_sb", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("o_sb", C.c_int64),
+        ("stats", C.c_void_p), ("key_mask", C.c_void_p), ("key_len", C.c_void_p),
+        ("dout", C.c_void_p), ("lddo", C.c_int64), ("do_sb", C.c_int64),
+        ("dq", C.c_void_p), ("lddq", C.c_int64), ("dq_sh", C.c_int64), ("dq_sb", C.c_int64),
+        ("dk", C.c_void_p), ("lddk", C.c_int64), ("dk_sh", C.c_int64), ("dk_sb", C.c_int64),
+        ("dv", C.c_void_p), ("lddv", C.c_int64), ("dv_sh", C.c_int64), ("dv_sb", C.c_int64),
+        ("delta", C.c_void_p),
+    ]
+
+
 def build(verbose: bool = False) -> str:
     """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4)]

@@ -251,7 +251,7 @@ class BartEncoder(nn.Module):
         B, L = input_ids.shape
         if attention_mask is None:
             attention_mask = torch.ones_like(input_ids)
-        key_mask = attention_mask.to(torch.uint8).contiguous()
+        key_mask = Bk.KeyMask(attention_mask)
         h = Bk.EmbedFn.apply(st.anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
                              self.ln_emb, 2, cfg.pad_token_id)
         img = face = ner = fn_mask = None
@@ -259,7 +259,7 @@ class BartEncoder(nn.Module):
             if not cfg.only_image:
                 ner = Bk.EmbedFn.apply(st.anchor, name_ids.contiguous(), rt, self.embed_tokens_ner.weight,
                                        self.embed_positions_ner.weight, self.ln_emb_ner, 2, cfg.pad_token_id)
-                fn_mask = torch.cat((face_mask, name_mask), dim=1).to(torch.uint8).contiguous()  # MFULL:1262
+                fn_mask = Bk.KeyMask(torch.cat((face_mask, name_mask), dim=1))  # MFULL:1262
                 face = Bk.LinearFn.apply(face_features.to(torch.bfloat16), st.anchor, rt, self.lin_face, torch.bfloat16, False, None,
                                          None)
             z = Bk.MlpBlockFn.apply(image_features.to(torch.bfloat16), st.anchor, rt, self.lin_p0, self.lin_p2, K.ACT_TANH, None)
@@ -315,8 +315,8 @@ class BartDecoder(nn.Module):
         d, H = cfg.d_model, cfg.heads
         x = Bk.EmbedFn.apply(st.anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
                              self.ln_emb, 2, cfg.pad_token_id)
-        enc_mask = None if encoder_attention_mask is None else encoder_attention_mask.to(torch.uint8).contiguous()
-        dec_mask = None if attention_mask is None else attention_mask.to(torch.uint8).contiguous()
+        enc_mask = None if encoder_attention_mask is None else Bk.KeyMask(encoder_attention_mask)
+        dec_mask = None if attention_mask is None else Bk.KeyMask(attention_mask)
         kv_all = Bk.LinearFn.apply(encoder_hidden_states, st.anchor, rt, self.lin_cross_kv, torch.bfloat16, True, None, None)
         dkv_all = torch.empty_like(kv_all) if (torch.is_grad_enabled() and kv_all.requires_grad) else None
         states = []
