@@ -10,9 +10,10 @@
 // finfo(float32).min (a fully masked row degenerates to a uniform row exactly like the reference),
 // keys beyond `key_len[b]` are skipped because they contribute exactly 0.
 //
-// CTA = 128 query rows of one (batch, head); 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM
-// allocator, warps 2..5 softmax/epilogue.  96 KB of shared memory and 256 TMEM columns per CTA, so two CTAs
-// share an SM and overlap each other's MMA and exp phases.
+// CTA = 128 query rows of one (batch, head); 320 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM
+// allocator, warps 2..9 softmax/epilogue (thread = one query row x one half of the key block's columns; the
+// two halves of a row meet only once per sweep, through shared memory).  96 KB of shared memory and 256
+// TMEM columns per CTA, so two CTAs share an SM and overlap each other's MMA and exp phases.
 #include <cuda.h>
 #include <float.h>
 
@@ -26,7 +27,9 @@ constexpr int kAK = 128;         // keys per block
 constexpr int kHD = 64;          // head dim
 constexpr int kTile = kAK * kHD * 2;  // 16 KB: one [128 x 64] bf16 tile
 constexpr int kRing = 3;
-constexpr int kAttnThreads = 192;
+constexpr int kCompWarps = 8;                        // softmax / elementwise warps: 2 per TMEM lane quadrant
+constexpr int kCompThreads = 32 * kCompWarps;         // each thread: one row, one half of the block's columns
+constexpr int kAttnThreads = 64 + kCompThreads;
 constexpr int kMaxKB = 40;       // key blocks per row (Sk <= 5120)
 
 struct AttnArgs {
@@ -44,6 +47,7 @@ struct AttnSmem {
   uint64_t q_full, ring_full[kRing], ring_empty[kRing], s_full, s_empty, p_full, p_empty, o_full;
   uint32_t tmem_slot;
   uint8_t blk_flag[kMaxKB];  // per key block: 0 = no masking needed, 1 = per-key checks needed
+  float xch[2][128];         // row max / row sum exchange between the two column halves
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -89,8 +93,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&sh->ring_empty[s], 1);
     }
     mbar_init(&sh->s_full, 1);
-    mbar_init(&sh->s_empty, 128);
-    mbar_init(&sh->p_full, 128);
+    mbar_init(&sh->s_empty, kCompThreads);
+    mbar_init(&sh->p_full, kCompThreads);
     mbar_init(&sh->p_empty, 1);
     mbar_init(&sh->o_full, 1);
     fence_mbar_init();
@@ -101,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (warp >= 2) {
     // classify the key blocks once: does any key of the block need a mask decision?
-    for (int j = threadIdx.x - 64; j < nkb; j += 128) {
+    for (int j = threadIdx.x - 64; j < nkb; j += kCompThreads) {
       const int k0 = j * kAK;
       bool need = (k0 + kAK > a.Sk) || (a.causal && k0 + kAK - 1 > q0);
       if (!need && a.key_mask != nullptr) {
@@ -180,11 +184,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_commit(&sh->o_full);
     }
   } else {
-    // ------------------------------------------------------------ softmax + epilogue: thread = query row
+    // ------------------------------------------------------------ softmax + epilogue
     const int quad = warp & 3;
-    const int r = quad * 32 + lane;   // row inside the tile == TMEM lane
+    const int half = (warp - 2) >> 2;  // which 64 of the block's 128 key columns
+    const int r = quad * 32 + lane;    // row inside the tile == TMEM lane
     const int row = q0 + r;
-    const uint32_t t_s = tmem_s + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t t_s = tmem_s + (static_cast<uint32_t>(quad * 32) << 16) + half * 64;
     const uint8_t* mk = a.key_mask ? a.key_mask + static_cast<long long>(b) * a.Sk : nullptr;
     const float c2 = a.scale_log2;
     uint32_t it = 0;
@@ -194,90 +199,85 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) return -FLT_MAX;
       return s * c2;
     };
-    // ---- sweep 1: row maximum
+    // ---- sweep 1: row maximum (over this thread's column half; the halves are merged after the sweep)
     float m = -INFINITY;
     for (int j = 0; j < nkb; ++j, ++it) {
       mbar_wait(&sh->s_full, it & 1u);
       tc_fence_after();
       const bool need = sh->blk_flag[j] != 0;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t x0[32], x1[32];
-        tmem_ld_32x32(t_s + half * 64, x0);
-        tmem_ld_32x32(t_s + half * 64 + 32, x1);
-        tmem_ld_wait();
-        if (!need) {
-          float mm = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) mm = fmaxf(mm, fmaxf(__uint_as_float(x0[c]), __uint_as_float(x1[c])));
-          m = fmaxf(m, mm * c2);  // c2 > 0: max commutes with the scaling
-        } else {
-          const int kb = j * kAK + half * 64;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            m = fmaxf(m, masked(__uint_as_float(x0[c]), kb + c));
-            m = fmaxf(m, masked(__uint_as_float(x1[c]), kb + 32 + c));
-          }
-        }
-      }
+      uint32_t x0[32], x1[32];
+      tmem_ld_32x32(t_s, x0);
+      tmem_ld_32x32(t_s + 32, x1);
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&sh->s_empty);
+      if (!need) {
+        float mm = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mm = fmaxf(mm, fmaxf(__uint_as_float(x0[c]), __uint_as_float(x1[c])));
+        m = fmaxf(m, mm * c2);  // c2 > 0: max commutes with the scaling
+      } else {
+        const int kb = j * kAK + half * 64;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          m = fmaxf(m, masked(__uint_as_float(x0[c]), kb + c));
+          m = fmaxf(m, masked(__uint_as_float(x1[c]), kb + 32 + c));
+        }
+      }
     }
-    // ---- sweep 2: p = 2^(t - m), row sum, P -> shared memory (bf16, SWIZZLE_128B K-major)
+    sh->xch[half][r] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(m, sh->xch[half ^ 1][r]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- sweep 2: p = 2^(t - m), row sum, P -> shared memory (bf16, SWIZZLE_128B K-major; half == atom)
     float l = 0.f;
-    const uint32_t p_row = smem_u32(sP) + r * 128;
+    const uint32_t atom = smem_u32(sP) + half * kTile + r * 128;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     for (int j = 0; j < nkb; ++j, ++it) {
       mbar_wait(&sh->s_full, it & 1u);
       tc_fence_after();
-      if (j > 0) mbar_wait(&sh->p_empty, (j - 1) & 1u);
       const bool need = sh->blk_flag[j] != 0;
+      const int kb = j * kAK + half * 64;
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t x0[32], x1[32];
-        tmem_ld_32x32(t_s + half * 64, x0);
-        tmem_ld_32x32(t_s + half * 64 + 32, x1);
+      for (int part = 0; part < 2; ++part) {
+        uint32_t x[32];
+        tmem_ld_32x32(t_s + part * 32, x);
         tmem_ld_wait();
-        if (half == 1) {  // all of S_j is in registers: the tensor pipe may overwrite it
+        if (part == 1) {  // all of S_j is in registers: the tensor pipe may overwrite it
           tc_fence_before();
           mbar_arrive(&sh->s_empty);
         }
-        const int kb = j * kAK + half * 64;
-        const uint32_t atom = p_row + half * kTile;
+        if (part == 0 && j > 0) mbar_wait(&sh->p_empty, (j - 1) & 1u);  // PV_{j-1} has consumed the P buffer
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {  // 8 chunks of 8 keys (16 B)
+        for (int q = 0; q < 4; ++q) {  // 4 chunks of 8 keys (16 B)
           float p[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int c = q * 8 + e;
-            const float s = __uint_as_float(c < 32 ? x0[c] : x1[c - 32]);
-            const float t = need ? masked(s, kb + c) : s * c2;
+            const float sv = __uint_as_float(x[c]);
+            const float t = need ? masked(sv, kb + part * 32 + c) : sv * c2;
             p[e] = ex2f(t - m);
+            l += p[e];
           }
-          const uint32_t w0 = pack_bf16x2(p[0], p[1]), w1 = pack_bf16x2(p[2], p[3]);
-          const uint32_t w2 = pack_bf16x2(p[4], p[5]), w3 = pack_bf16x2(p[6], p[7]);
-          float2 f;
-          f = unpack_bf16x2(w0); l += f.x + f.y;
-          f = unpack_bf16x2(w1); l += f.x + f.y;
-          f = unpack_bf16x2(w2); l += f.x + f.y;
-          f = unpack_bf16x2(w3); l += f.x + f.y;
-          st_shared_v4(atom + ((static_cast<uint32_t>(q) ^ sw) << 4), w0, w1, w2, w3);
+          st_shared_v4(atom + ((static_cast<uint32_t>(part * 4 + q) ^ sw) << 4), pack_bf16x2(p[0], p[1]),
+                       pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
         }
       }
       fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor pipe (async proxy)
       mbar_arrive(&sh->p_full);
     }
-    // ---- epilogue: O / l -> bf16
+    sh->xch[half][r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += sh->xch[half ^ 1][r];
+    // ---- epilogue: O / l -> bf16 (each half stores 32 of the 64 head-dim columns)
     mbar_wait(&sh->o_full, 0);
     tc_fence_after();
     const float inv = 1.f / l;
-    const uint32_t t_o = tmem_o + (static_cast<uint32_t>(quad * 32) << 16);
-    uint32_t o0[32], o1[32];
-    tmem_ld_32x32(t_o, o0);
-    tmem_ld_32x32(t_o + 32, o1);
+    uint32_t o0[32];
+    tmem_ld_32x32(tmem_o + (static_cast<uint32_t>(quad * 32) << 16) + half * 32, o0);
     tmem_ld_wait();
     if (row < a.Sq) {
-      __nv_bfloat16* op = a.out + static_cast<long long>(b) * a.o_sb + static_cast<long long>(row) * a.ldo + h * kHD;
+      __nv_bfloat16* op = a.out + static_cast<long long>(b) * a.o_sb + static_cast<long long>(row) * a.ldo + h * kHD + half * 32;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 u;
@@ -287,16 +287,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         u.w = pack_bf16x2(__uint_as_float(o0[8 * q + 6]) * inv, __uint_as_float(o0[8 * q + 7]) * inv);
         reinterpret_cast<uint4*>(op)[q] = u;
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(o1[8 * q + 0]) * inv, __uint_as_float(o1[8 * q + 1]) * inv);
-        u.y = pack_bf16x2(__uint_as_float(o1[8 * q + 2]) * inv, __uint_as_float(o1[8 * q + 3]) * inv);
-        u.z = pack_bf16x2(__uint_as_float(o1[8 * q + 4]) * inv, __uint_as_float(o1[8 * q + 5]) * inv);
-        u.w = pack_bf16x2(__uint_as_float(o1[8 * q + 6]) * inv, __uint_as_float(o1[8 * q + 7]) * inv);
-        reinterpret_cast<uint4*>(op)[4 + q] = u;
-      }
-      if (a.stats != nullptr)
+      if (a.stats != nullptr && half == 0)
         reinterpret_cast<float2*>(a.stats)[(static_cast<long long>(b) * a.H + h) * a.Sq + row] = make_float2(m, inv);
     }
   }
@@ -338,7 +329,8 @@ struct AttnBwdArgs {
 struct BwdSmem {
   uint64_t in_full, st_full[2], st_empty[2], sdp_full, s_empty, ds_full, ds_empty, acc_full;
   uint32_t tmem_slot;
-  float stat[2][3][64];  // dkv kernel: per query block {max, 1/sum, delta}
+  float4 stat[2][64];    // dkv kernel: per query of the block {max, 1/sum, delta, -}
+  uint8_t blk_flag[2 * kMaxKB];  // dq kernel: per 64-key block, 1 = per-key mask checks needed
 };
 
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
@@ -367,6 +359,18 @@ __device__ __forceinline__ void store_row64(__nv_bfloat16* op, const uint32_t (&
   }
 }
 
+__device__ __forceinline__ void store_row32(__nv_bfloat16* op, const uint32_t (&o0)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(o0[8 * q + 0]), __uint_as_float(o0[8 * q + 1]));
+    u.y = pack_bf16x2(__uint_as_float(o0[8 * q + 2]), __uint_as_float(o0[8 * q + 3]));
+    u.z = pack_bf16x2(__uint_as_float(o0[8 * q + 4]), __uint_as_float(o0[8 * q + 5]));
+    u.w = pack_bf16x2(__uint_as_float(o0[8 * q + 6]), __uint_as_float(o0[8 * q + 7]));
+    reinterpret_cast<uint4*>(op)[q] = u;
+  }
+}
+
 __device__ __forceinline__ void bwd_init(BwdSmem* sh, int warp, int lane) {
   if (warp == 0 && lane == 0) {
     mbar_init(&sh->in_full, 1);
@@ -375,8 +379,8 @@ __device__ __forceinline__ void bwd_init(BwdSmem* sh, int warp, int lane) {
       mbar_init(&sh->st_empty[s], 1);
     }
     mbar_init(&sh->sdp_full, 1);
-    mbar_init(&sh->s_empty, 128);
-    mbar_init(&sh->ds_full, 128);
+    mbar_init(&sh->s_empty, kCompThreads);
+    mbar_init(&sh->ds_full, kCompThreads);
     mbar_init(&sh->ds_empty, 1);
     mbar_init(&sh->acc_full, 1);
     fence_mbar_init();
@@ -466,13 +470,23 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;  // which 32 of the block's 64 key columns
     const int r = quad * 32 + lane;
     const int row = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint8_t* mk = a.key_mask ? a.key_mask + static_cast<long long>(b) * a.Sk : nullptr;
     const float c2 = a.scale_log2;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    // ---- delta = rowsum(dO * O)
+    // classify the 64-key blocks: does any key need a mask decision?
+    for (int j = threadIdx.x - 64; j < nkb; j += kCompThreads) {
+      const int kb0 = j * 64;
+      bool need = (kb0 + 64 > a.Sk) || (a.causal && kb0 + 63 > q0);
+      if (!need && mk != nullptr)
+        for (int c = 0; c < 64; ++c) need |= (mk[kb0 + c] == 0);
+      sh->blk_flag[j] = need ? 1 : 0;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- delta = rowsum(dO * O) (both column halves compute it; half 0 stores it)
     mbar_wait(&sh->in_full, 0);
     float delta = 0.f;
     {
@@ -491,61 +505,56 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int e = 0; e < 8; ++e) delta += x[e] * y[e];
       }
     }
-    float m = 0.f, inv_l = 0.f;
+    // every thread has read its O row before any thread overwrites the buffer with dS
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float m = 0.f, coef = 0.f;
     if (row < a.Sq) {
       const long long si = (static_cast<long long>(b) * a.H + h) * a.Sq + row;
       const float2 st = reinterpret_cast<const float2*>(a.stats)[si];
       m = st.x;
-      inv_l = st.y;
-      a.delta[si] = delta;
+      coef = st.y * a.scale;  // 1/rowsum * head_dim^-0.5
+      if (half == 0) a.delta[si] = delta;
     }
     const uint32_t ds_row = smem_u32(sDS) + r * 128;
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(&sh->sdp_full, j & 1u);
       tc_fence_after();
+      const int kb0 = j * 64 + half * 32;
+      const bool need = sh->blk_flag[j] != 0;
+      uint32_t xs[32], xp[32];
+      tmem_ld_32x32(tmem_base + lane_off + half * 32, xs);
+      tmem_ld_32x32(tmem_base + lane_off + 64 + half * 32, xp);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sh->s_empty);
       if (j > 0) mbar_wait(&sh->ds_empty, (j - 1) & 1u);
-      const int kb0 = j * 64;
-      const bool need = (kb0 + 64 > a.Sk) || (a.causal && kb0 + 63 > q0) || mk != nullptr;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t xs[32], xp[32];
-        tmem_ld_32x32(tmem_base + lane_off + half * 32, xs);
-        tmem_ld_32x32(tmem_base + lane_off + 64 + half * 32, xp);
-        tmem_ld_wait();
-        if (half == 1) {
-          tc_fence_before();
-          mbar_arrive(&sh->s_empty);
-        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float ds[8];
+      for (int q = 0; q < 4; ++q) {
+        float ds[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = q * 8 + e;
-            const int key = kb0 + half * 32 + c;
-            float t = __uint_as_float(xs[c]) * c2;
-            if (need) {
-              if (key >= a.Sk) t = -INFINITY;
-              else if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) t = -FLT_MAX;
-            }
-            const float p = ex2f(t - m) * inv_l;
-            ds[e] = p * (__uint_as_float(xp[c]) - delta) * a.scale;
+        for (int e = 0; e < 8; ++e) {
+          const int c = q * 8 + e;
+          float t = __uint_as_float(xs[c]) * c2;
+          if (need) {
+            const int key = kb0 + c;
+            if (key >= a.Sk) t = -INFINITY;
+            else if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) t = -FLT_MAX;
           }
-          st_shared_v4(ds_row + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4), pack_bf16x2(ds[0], ds[1]),
-                       pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+          ds[e] = ex2f(t - m) * (__uint_as_float(xp[c]) - delta) * coef;
         }
+        st_shared_v4(ds_row + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4), pack_bf16x2(ds[0], ds[1]),
+                     pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
       }
       fence_proxy_async_smem();
       mbar_arrive(&sh->ds_full);
     }
     mbar_wait(&sh->acc_full, 0);
     tc_fence_after();
-    uint32_t o0[32], o1[32];
-    tmem_ld_32x32(tmem_base + lane_off + 128, o0);
-    tmem_ld_32x32(tmem_base + lane_off + 160, o1);
+    uint32_t o0[32];
+    tmem_ld_32x32(tmem_base + lane_off + 128 + half * 32, o0);
     tmem_ld_wait();
     if (row < a.Sq)
-      store_row64(a.dq + static_cast<long long>(b) * a.dq_sb + h * a.dq_sh + static_cast<long long>(row) * a.lddq, o0, o1, 1.f);
+      store_row32(a.dq + static_cast<long long>(b) * a.dq_sb + h * a.dq_sh + static_cast<long long>(row) * a.lddq + half * 32, o0);
   }
   tc_fence_before();
   __syncthreads();
@@ -575,7 +584,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int kl = a.key_len != nullptr ? a.key_len[b] : 0;
   if (kl > 0 && k0 >= kl) {
     // every key of this block is masked for every query: dK = dV = 0
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
       const int key = k0 + (warp - 2) * 32 + lane;
       if (key < a.Sk) {
         uint4* pk = reinterpret_cast<uint4*>(a.dk + static_cast<long long>(b) * a.dk_sb + h * a.dk_sh + static_cast<long long>(key) * a.lddk);
@@ -644,9 +653,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else {
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;  // which 32 of the block's 64 query columns
     const int r = quad * 32 + lane;
     const int key = k0 + r;
-    const int tid = threadIdx.x - 64;  // 0..127
+    const int tid = threadIdx.x - 64;  // 0..255
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const bool key_oob = key >= a.Sk;
     const bool key_masked = !key_oob && a.key_mask != nullptr && a.key_mask[static_cast<long long>(b) * a.Sk + key] == 0;
@@ -655,55 +665,48 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t pt_row = smem_u32(sPT) + r * 128, dst_row = smem_u32(sDST) + r * 128;
     const long long sbase = (static_cast<long long>(b) * a.H + h) * a.Sq;
     for (int i = i0, n = 0; i < nqb; ++i, ++n) {
-      // stage the row statistics of the 64 queries of this block (double buffered; ds_empty(n-2) ordering is
-      // implied: buffer n&1 was last read in step n-2, whose writes all threads finished before ds_full(n-2))
-      float* stq = &sh->stat[n & 1][0][0];
+      // stage the row statistics of the 64 queries of this block (double buffered: buffer n&1 was last read in
+      // step n-2, which every thread finished before passing the named barrier of step n-1)
+      float4* stq = sh->stat[n & 1];
       if (tid < 64) {
         const int qrow = i * 64 + tid;
-        float2 st = make_float2(0.f, 0.f);
-        float dl = 0.f;
+        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);  // query rows beyond Sq: 1/sum = 0 -> p = 0
         if (qrow < a.Sq) {
-          st = reinterpret_cast<const float2*>(a.stats)[sbase + qrow];
-          dl = a.delta[sbase + qrow];
+          const float2 s2 = reinterpret_cast<const float2*>(a.stats)[sbase + qrow];
+          st = make_float4(s2.x, s2.y, a.delta[sbase + qrow], 0.f);
         }
-        stq[tid] = st.x;
-        stq[64 + tid] = st.y;   // 0 for query rows beyond Sq -> p = 0
-        stq[128 + tid] = dl;
+        stq[tid] = st;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&sh->sdp_full, n & 1u);
       tc_fence_after();
+      const int qb0 = i * 64 + half * 32;
+      uint32_t xs[32], xp[32];
+      tmem_ld_32x32(tmem_base + lane_off + half * 32, xs);
+      tmem_ld_32x32(tmem_base + lane_off + 64 + half * 32, xp);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sh->s_empty);
       if (n > 0) mbar_wait(&sh->ds_empty, (n - 1) & 1u);
-      const int qb0 = i * 64;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t xs[32], xp[32];
-        tmem_ld_32x32(tmem_base + lane_off + half * 32, xs);
-        tmem_ld_32x32(tmem_base + lane_off + 64 + half * 32, xp);
-        tmem_ld_wait();
-        if (half == 1) {
-          tc_fence_before();
-          mbar_arrive(&sh->s_empty);
-        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float pp[8], ds[8];
+      for (int q = 0; q < 4; ++q) {
+        float pp[8], ds[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = half * 32 + q * 8 + e;
-            float t = __uint_as_float(xs[q * 8 + e]) * c2;
-            if (key_oob) t = -INFINITY;
-            else if (key_masked || (a.causal && key > qb0 + c)) t = -FLT_MAX;
-            const float p = ex2f(t - stq[c]) * stq[64 + c];
-            pp[e] = p;
-            ds[e] = p * (__uint_as_float(xp[q * 8 + e]) - stq[128 + c]) * a.scale;
-          }
-          const uint32_t off = (static_cast<uint32_t>(half * 4 + q) ^ sw) << 4;
-          st_shared_v4(pt_row + off, pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]), pack_bf16x2(pp[4], pp[5]),
-                       pack_bf16x2(pp[6], pp[7]));
-          st_shared_v4(dst_row + off, pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
-                       pack_bf16x2(ds[6], ds[7]));
+        for (int e = 0; e < 8; ++e) {
+          const int c = q * 8 + e;
+          const float4 st = stq[half * 32 + c];
+          float t = __uint_as_float(xs[c]) * c2;
+          if (key_oob) t = -INFINITY;
+          else if (key_masked || (a.causal && key > qb0 + c)) t = -FLT_MAX;
+          const float p = ex2f(t - st.x) * st.y;
+          pp[e] = p;
+          ds[e] = p * (__uint_as_float(xp[c]) - st.z) * a.scale;
         }
+        const uint32_t off = (static_cast<uint32_t>(half * 4 + q) ^ sw) << 4;
+        st_shared_v4(pt_row + off, pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]), pack_bf16x2(pp[4], pp[5]),
+                     pack_bf16x2(pp[6], pp[7]));
+        st_shared_v4(dst_row + off, pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
+                     pack_bf16x2(ds[6], ds[7]));
       }
       fence_proxy_async_smem();
       mbar_arrive(&sh->ds_full);
@@ -711,16 +714,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_wait(&sh->acc_full, 0);
     tc_fence_after();
     uint32_t o0[32], o1[32];
-    tmem_ld_32x32(tmem_base + lane_off + 128, o0);
-    tmem_ld_32x32(tmem_base + lane_off + 160, o1);
+    tmem_ld_32x32(tmem_base + lane_off + 128 + half * 32, o0);
+    tmem_ld_32x32(tmem_base + lane_off + 192 + half * 32, o1);
     tmem_ld_wait();
-    if (!key_oob)
-      store_row64(a.dv + static_cast<long long>(b) * a.dv_sb + h * a.dv_sh + static_cast<long long>(key) * a.lddv, o0, o1, 1.f);
-    tmem_ld_32x32(tmem_base + lane_off + 192, o0);
-    tmem_ld_32x32(tmem_base + lane_off + 224, o1);
-    tmem_ld_wait();
-    if (!key_oob)
-      store_row64(a.dk + static_cast<long long>(b) * a.dk_sb + h * a.dk_sh + static_cast<long long>(key) * a.lddk, o0, o1, 1.f);
+    if (!key_oob) {
+      store_row32(a.dv + static_cast<long long>(b) * a.dv_sb + h * a.dv_sh + static_cast<long long>(key) * a.lddv + half * 32, o0);
+      store_row32(a.dk + static_cast<long long>(b) * a.dk_sb + h * a.dk_sh + static_cast<long long>(key) * a.lddk + half * 32, o1);
+    }
   }
   tc_fence_before();
   __syncthreads();
