@@ -248,7 +248,7 @@ def run_infer(args, rank, world, dev, pk):
         e0.record()
         for i in range(n_rep):  # every layer's K/V in turn: 12 x cross_bytes >> L2, no reuse between launches
             l = i % cfg.dec_layers
-            K.decode_cross_attn(engine.qb, engine.cross_kv[l], cfg.d_model, engine.key_mask, engine.key_len, engine.attn, C, nb, L, cfg.heads)
+            K.decode_cross_attn(engine.qb, engine.cross_kv[l, :, 0], engine.cross_kv[l, :, 1], engine.key_mask, engine.key_len, engine.attn, nb)
         e1.record()
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / n_rep

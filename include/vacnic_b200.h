@@ -61,8 +61,9 @@ int64_t vacnic_launch_count(void);
  *   v = act(v);  if (dact) v *= act'(aux_in[m,n])   (GELU': aux_in = pre-activation,
  *                                                    TANH': aux_in = activation output);
  *   if (accumulate) v += C[m,n];   C[m,n] = (c_dtype) v
- * C / aux_out / aux_in share ldc, c_sb0, c_sb1 (element strides).
- * Requirements: a, b 16-byte aligned, lda/ldb/batch strides multiples of 8 elements.
+ * C / aux_out / aux_in share ldc, c_sb0, c_sb1, c_chunk_stride (element strides).
+ * Requirements: a, b 16-byte aligned, lda/ldb/batch strides multiples of 8 elements.  A batch stride of 0
+ * broadcasts that operand over the batch dimension (one weight matrix for every batch).
  * ------------------------------------------------------------------------------------------ */
 typedef struct vacnic_gemm_desc {
   int32_t M, N, K;
@@ -84,6 +85,10 @@ typedef struct vacnic_gemm_desc {
   int32_t dact;
   int32_t accumulate;
   int32_t tile_n; /* 0 = choose; else 64 / 128 / 256 */
+  /* != 0: output column n is stored at (n / 64) * c_chunk_stride + (n % 64) instead of n, i.e. every
+   * 64-column group (one attention head) becomes its own [rows][64] block with row stride ldc: the
+   * head-major layout of the decode-time cross-attention K/V cache. */
+  int64_t c_chunk_stride;
 } vacnic_gemm_desc;
 
 int vacnic_gemm(const vacnic_gemm_desc* d, void* stream);
@@ -206,12 +211,12 @@ int vacnic_decode_embed_ln(const int32_t* seq, const int32_t* cur_len, const voi
 int vacnic_decode_self_attn(const void* qkv, void* kcache, void* vcache, const int32_t* anc, const int32_t* cur_len,
                             void* out, int32_t R, int32_t H, int32_t head_dim, int32_t maxT, void* stream);
 /* Cross-attention of the nq beams of each caption over its L encoder keys (MFULL:474-479): q bf16
- * row (c*nq+i) at q + row*ldq; k row (c*L+s) at kv + row*ldkv, v at + v_off; key_mask uint8 [captions][L]
- * (1 = attend) and key_len int32 [captions] (keys >= key_len are skipped; see vacnic_mask_key_len) may
- * be null.  out row stride ldo. */
-int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t v_off,
-                             const uint8_t* key_mask, const int32_t* key_len, void* out, int64_t ldo, int32_t captions,
-                             int32_t nq, int32_t L, int32_t H, int32_t head_dim, void* stream);
+ * row (c*nq+i) at q + row*ldq; K(c,h,s,:) = k[c*kv_cs + h*kv_hs + s*ldkv + 0..63], same strides for v;
+ * key_mask uint8 [captions][L] (1 = attend) and key_len int32 [captions] (keys >= key_len are skipped;
+ * see vacnic_mask_key_len) may be null.  out row stride ldo. */
+int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int64_t kv_hs,
+                             int64_t kv_cs, const uint8_t* key_mask, const int32_t* key_len, void* out, int64_t ldo,
+                             int32_t captions, int32_t nq, int32_t L, int32_t H, int32_t head_dim, void* stream);
 int vacnic_mask_key_len(const uint8_t* mask, int32_t* key_len, int32_t B, int32_t L, void* stream);
 /* Per row of fp32 logits [rows][ld]: log-softmax statistics and the K best entries, sorted (ties: lower
  * index).  top_lp[r][k] = logit - logsumexp(row). */

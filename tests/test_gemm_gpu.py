@@ -109,3 +109,19 @@ def test_gemm_rejects_cpu_tensors():
     a = torch.zeros(8, 8, dtype=torch.bfloat16)
     with pytest.raises(VacnicError):
         k.gemm(a, a)
+
+
+@pytest.mark.gpu
+def test_gemm_head_major_output_and_broadcast_weight(cuda_device):
+    """Batched GEMM with one weight matrix broadcast over the batch (zero batch stride) whose output columns are
+    scattered head-major: [batch][64-column group][rows][64] — the decode-time cross K/V cache layout."""
+    from vacnic_b200 import kernels as K
+    torch.manual_seed(1)
+    C, L, d, H = 3, 200, 256, 8
+    h = torch.randn(C, L, d, device=cuda_device).bfloat16()
+    w = (torch.randn(2 * H * 64, d, device=cuda_device) * 0.1).bfloat16()
+    bias = torch.randn(2 * H * 64, device=cuda_device)
+    out = torch.zeros(C, 2, H, L, 64, device=cuda_device, dtype=torch.bfloat16)
+    K.gemm(h, w.unsqueeze(0).expand(C, -1, -1), out=out, bias=bias, head_major=(64, 2 * H * 64 * L, 0, L * 64))
+    ref = (h.float() @ w.float().t() + bias).view(C, L, 2, H, 64).permute(0, 2, 3, 1, 4)
+    assert (out.float() - ref).abs().max().item() <= 3e-2

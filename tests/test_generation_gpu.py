@@ -152,7 +152,14 @@ def test_decode_cross_attention_matches_torch(cuda_device):
         if L > 20:
             mask[0, 3] = 0  # a hole inside the valid range
         out = torch.empty(C * nq, d, dtype=torch.bfloat16, device=dev)
-        K.decode_cross_attn(q, kv, d, mask, K.mask_key_len(mask), out, C, nq, L, H)
+        # interleaved [C*L, 2d] layout viewed per head, and the head-major layout of the generator
+        k4 = kv.as_strided((C, H, L, 64), (L * 2 * d, 64, 2 * d, 1), 0)
+        v4 = kv.as_strided((C, H, L, 64), (L * 2 * d, 64, 2 * d, 1), d)
+        K.decode_cross_attn(q, k4, v4, mask, K.mask_key_len(mask), out, nq)
+        hm = torch.stack((k4, v4), dim=1).contiguous()  # [C, 2, H, L, 64]
+        out_hm = torch.empty_like(out)
+        K.decode_cross_attn(q, hm[:, 0], hm[:, 1], mask, K.mask_key_len(mask), out_hm, nq)
+        assert torch.equal(out_hm, out)
         qf = q.float().view(C, nq, H, 64).permute(0, 2, 1, 3)
         kf = kv[:, :d].float().view(C, L, H, 64).permute(0, 2, 1, 3)
         vf = kv[:, d:].float().view(C, L, H, 64).permute(0, 2, 1, 3)
@@ -162,7 +169,7 @@ def test_decode_cross_attention_matches_torch(cuda_device):
         assert (out.float() - ref).abs().max().item() <= 2e-2, (C, nq, L, H)
         # without the length hint the result is the same
         out2 = torch.empty_like(out)
-        K.decode_cross_attn(q, kv, d, mask, None, out2, C, nq, L, H)
+        K.decode_cross_attn(q, k4, v4, mask, None, out2, nq)
         assert (out2.float() - out.float()).abs().max().item() <= 1e-2
 
 

@@ -33,7 +33,7 @@ SIGNATURES = {
     "vacnic_secla_bwd": [P, P, P, F32, P, I32, I32, I32, I32, I32, P],
     "vacnic_decode_embed_ln": [P, P, P, P, P, P, P, I32, I32, I32, I32, I32, F32, P],
     "vacnic_decode_self_attn": [P, P, P, P, P, P, I32, I32, I32, I32, P],
-    "vacnic_decode_cross_attn": [P, I64, P, I64, I32, P, P, P, I64, I32, I32, I32, I32, I32, P],
+    "vacnic_decode_cross_attn": [P, I64, P, P, I64, I64, I64, P, P, P, I64, I32, I32, I32, I32, I32, P],
     "vacnic_mask_key_len": [P, P, I32, I32, P],
     "vacnic_decode_topk": [P, I64, I32, I32, I32, P, P, P],
     "vacnic_beam_step": [P, P, P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, F32, P],

@@ -160,10 +160,10 @@ decode_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 // ------------------------------------------------------------------------------------------------
 template <int NQ>
 __global__ void __launch_bounds__(128)
-decode_cross_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kv,
-                         long long ldkv, int v_off, const uint8_t* __restrict__ key_mask,
-                         const int32_t* __restrict__ key_len, __nv_bfloat16* __restrict__ out, long long ldo, int nq,
-                         int L, float scale) {
+decode_cross_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kp,
+                         const __nv_bfloat16* __restrict__ vp, long long ldkv, long long kv_hs, long long kv_cs,
+                         const uint8_t* __restrict__ key_mask, const int32_t* __restrict__ key_len,
+                         __nv_bfloat16* __restrict__ out, long long ldo, int nq, int L, float scale) {
   extern __shared__ float dsm[];
   float* sc = dsm;                 // [NQ][L]
   float* red = dsm + NQ * L;       // [4 warps][NQ][64] partial outputs (also used for max / sum)
@@ -185,9 +185,9 @@ decode_cross_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, con
       for (int e = 0; e < 8; ++e) qf[i][e] = 0.f;
     }
   }
-  const __nv_bfloat16* kbase = kv + static_cast<long long>(c) * L * ldkv + h * 64;
+  const __nv_bfloat16* kbase = kp + static_cast<long long>(c) * kv_cs + h * kv_hs;
   // ---- pass 1: scores
-  constexpr int UN = 4;
+  constexpr int UN = 8;
   for (int kb = 0; kb < Lc; kb += 16 * UN) {  // block-uniform trip count: the shuffles below need full warps
     const int k0 = kb + warp * 4 + g;
     uint4 kk[UN];
@@ -250,7 +250,7 @@ decode_cross_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, con
   for (int i = 0; i < NQ; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[i][e] = 0.f;
-  const __nv_bfloat16* vbase = kbase + v_off;
+  const __nv_bfloat16* vbase = vp + static_cast<long long>(c) * kv_cs + h * kv_hs;
   for (int kb = 0; kb < Lc; kb += 16 * UN) {
     const int k0 = kb + warp * 4 + g;
     uint4 vv[UN];
@@ -648,9 +648,9 @@ extern "C" int vacnic_decode_self_attn(const void* qkv, void* kcache, void* vcac
 }
 
 template <int NQ>
-static int launch_cross(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t v_off, const uint8_t* key_mask,
-                        const int32_t* key_len, void* out, int64_t ldo, int32_t captions, int32_t nq, int32_t L,
-                        int32_t H, float scale, cudaStream_t s) {
+static int launch_cross(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int64_t kv_hs, int64_t kv_cs,
+                        const uint8_t* key_mask, const int32_t* key_len, void* out, int64_t ldo, int32_t captions, int32_t nq,
+                        int32_t L, int32_t H, float scale, cudaStream_t s) {
   const size_t smem = (static_cast<size_t>(NQ) * L + 4 * NQ * 64) * sizeof(float);
   auto kern = decode_cross_attn_kernel<NQ>;
   static size_t configured = 0;
@@ -659,28 +659,31 @@ static int launch_cross(const void* q, int64_t ldq, const void* kv, int64_t ldkv
     if (e != cudaSuccess) return fail(VACNIC_ECUDA, "decode_cross_attn: smem %zu: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  kern<<<dim3(H, captions), 128, smem, s>>>(static_cast<const __nv_bfloat16*>(q), ldq,
-                                            static_cast<const __nv_bfloat16*>(kv), ldkv, v_off, key_mask, key_len,
+  kern<<<dim3(H, captions), 128, smem, s>>>(static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
+                                            static_cast<const __nv_bfloat16*>(v), ldkv, kv_hs, kv_cs, key_mask, key_len,
                                             static_cast<__nv_bfloat16*>(out), ldo, nq, L, scale);
   count_launch();
   return check_last("decode_cross_attn");
 }
 
-extern "C" int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t v_off,
-                                        const uint8_t* key_mask, const int32_t* key_len, void* out, int64_t ldo,
-                                        int32_t captions, int32_t nq, int32_t L, int32_t H, int32_t head_dim,
-                                        void* stream) {
-  VB_REQUIRE(q && kv && out, "decode_cross_attn: null pointer");
+extern "C" int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                                        int64_t kv_hs, int64_t kv_cs, const uint8_t* key_mask, const int32_t* key_len,
+                                        void* out, int64_t ldo, int32_t captions, int32_t nq, int32_t L, int32_t H,
+                                        int32_t head_dim, void* stream) {
+  VB_REQUIRE(q && k && v && out, "decode_cross_attn: null pointer");
   VB_REQUIRE(head_dim == 64, "decode_cross_attn: head_dim must be 64");
   VB_REQUIRE(captions > 0 && nq >= 1 && nq <= 8 && L > 0 && L <= 4096 && H > 0, "decode_cross_attn: bad shape (nq <= 8, L <= 4096)");
-  VB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && v_off % 8 == 0, "decode_cross_attn: strides must be multiples of 8 elements");
-  VB_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0, "decode_cross_attn: misaligned");
+  VB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && kv_hs % 8 == 0 && kv_cs % 8 == 0, "decode_cross_attn: strides must be multiples of 8 elements");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(v) & 15) == 0, "decode_cross_attn: misaligned");
   const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (nq == 1) return launch_cross<1>(q, ldq, kv, ldkv, v_off, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s);
-  if (nq == 2) return launch_cross<2>(q, ldq, kv, ldkv, v_off, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s);
-  if (nq <= 4) return launch_cross<4>(q, ldq, kv, ldkv, v_off, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s);
-  return launch_cross<8>(q, ldq, kv, ldkv, v_off, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s);
+#define VB_CROSS(NQ) launch_cross<NQ>(q, ldq, k, v, ldkv, kv_hs, kv_cs, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s)
+  if (nq == 1) return VB_CROSS(1);
+  if (nq == 2) return VB_CROSS(2);
+  if (nq <= 4) return VB_CROSS(4);
+  return VB_CROSS(8);
+#undef VB_CROSS
 }
 
 extern "C" int vacnic_mask_key_len(const uint8_t* mask, int32_t* key_len, int32_t B, int32_t L, void* stream) {

@@ -32,6 +32,8 @@ struct GemmArgs {
   int c_dtype, act, dact, accumulate;
   int vec_ok;  // 16-byte vector access allowed on C / aux rows
   int bias_vec;  // bias pointer 16-byte aligned
+  int a_m0, a_m1, b_m0, b_m1;  // batch-coordinate multipliers: 0 = operand is broadcast over that batch dim
+  long long c_chunk;  // != 0: column n lives at (n / 64) * c_chunk + (n % 64) (head-major outputs)
 };
 
 constexpr int kBM = 128;
@@ -83,7 +85,7 @@ __device__ __forceinline__ void epilogue_row_chunk(const GemmArgs& g, float (&v)
     for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
   }
   const bool full = (nvalid == 32) && g.vec_ok;
-  const long long off = row_off + n0;
+  const long long off = row_off + (g.c_chunk != 0 ? static_cast<long long>(n0 >> 6) * g.c_chunk + (n0 & 63) : n0);
   if (g.aux_out != nullptr) {
     __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(g.aux_out) + off;
     if (full) {
@@ -231,18 +233,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = kb * kBK;
           if constexpr (!A_MN) {
-            tma_load_4d(sa, &tmA, &full_bar[stage], k0, m0, b0, b1);
+            tma_load_4d(sa, &tmA, &full_bar[stage], k0, m0, b0 * g.a_m0, b1 * g.a_m1);
           } else {
 #pragma unroll
             for (int c = 0; c < kBM / 64; ++c)
-              tma_load_4d(sa + c * (64 * kBK * 2), &tmA, &full_bar[stage], m0 + c * 64, k0, b0, b1);
+              tma_load_4d(sa + c * (64 * kBK * 2), &tmA, &full_bar[stage], m0 + c * 64, k0, b0 * g.a_m0, b1 * g.a_m1);
           }
           if constexpr (!B_MN) {
-            tma_load_4d(sb, &tmB, &full_bar[stage], k0, n0, b0, b1);
+            tma_load_4d(sb, &tmB, &full_bar[stage], k0, n0, b0 * g.b_m0, b1 * g.b_m1);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_4d(sb + c * (64 * kBK * 2), &tmB, &full_bar[stage], n0 + c * 64, k0, b0, b1);
+              tma_load_4d(sb + c * (64 * kBK * 2), &tmB, &full_bar[stage], n0 + c * 64, k0, b0 * g.b_m0, b1 * g.b_m1);
           }
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -473,22 +475,28 @@ extern "C" int vacnic_gemm(const vacnic_gemm_desc* d, void* stream_v) {
   g.bias = d->bias; g.aux_out = d->aux_out; g.aux_in = d->aux_in;
   g.alpha = d->alpha; g.c_dtype = d->c_dtype; g.act = d->act; g.dact = d->dact;
   g.accumulate = d->accumulate;
+  g.c_chunk = d->c_chunk_stride;
   // Vector (16 B) row access needs every row start of C / aux to be 16-byte aligned.
   const int c_es = d->c_dtype == VACNIC_DT_F32 ? 4 : 2;
   auto aligned = [&](const void* p, int es) {
     return p == nullptr ||
-           ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (d->ldc * es) % 16 == 0 &&
+           ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (d->ldc * es) % 16 == 0 && (d->c_chunk_stride * es) % 16 == 0 &&
             (d->c_sb0 * es) % 16 == 0 && (d->c_sb1 * es) % 16 == 0);
   };
   g.vec_ok = aligned(d->c, c_es) && aligned(d->aux_out, 2) && aligned(d->aux_in, 2) ? 1 : 0;
   g.bias_vec = (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0 ? 1 : 0;
 
+  // a zero batch stride means "the same matrix for every batch": the map gets extent 1 and the coordinate is pinned to 0
+  g.a_m0 = (d->batch0 > 1 && d->a_sb0 == 0) ? 0 : 1;
+  g.a_m1 = (d->batch1 > 1 && d->a_sb1 == 0) ? 0 : 1;
+  g.b_m0 = (d->batch0 > 1 && d->b_sb0 == 0) ? 0 : 1;
+  g.b_m1 = (d->batch1 > 1 && d->b_sb1 == 0) ? 0 : 1;
   CUtensorMap tmA, tmB;
-  int rc = make_operand_map(&tmA, d->a, d->a_mn_major != 0, d->M, d->K, d->lda, d->batch0, d->a_sb0,
-                            d->batch1, d->a_sb1, kBM);
+  int rc = make_operand_map(&tmA, d->a, d->a_mn_major != 0, d->M, d->K, d->lda, g.a_m0 ? d->batch0 : 1, d->a_sb0,
+                            g.a_m1 ? d->batch1 : 1, d->a_sb1, kBM);
   if (rc != VACNIC_OK) return rc;
-  rc = make_operand_map(&tmB, d->b, d->b_mn_major != 0, d->N, d->K, d->ldb, d->batch0, d->b_sb0,
-                        d->batch1, d->b_sb1, bn);
+  rc = make_operand_map(&tmB, d->b, d->b_mn_major != 0, d->N, d->K, d->ldb, g.b_m0 ? d->batch0 : 1, d->b_sb0,
+                        g.b_m1 ? d->batch1 : 1, d->b_sb1, bn);
   if (rc != VACNIC_OK) return rc;
 
   const bool a_mn = d->a_mn_major != 0, b_mn = d->b_mn_major != 0;

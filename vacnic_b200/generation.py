@@ -54,7 +54,8 @@ class Generator:
         self.logits = buf(R, self.ldp, dtype=f32)
         self.kc = buf(nl, R, self.maxT, d)
         self.vc = buf(nl, R, self.maxT, d)
-        self.cross_kv = buf(nl, captions * L, 2 * d)
+        # cross K/V, head-major: [layer][caption][k|v][head][L][64] -> each (caption, head) streams one contiguous block
+        self.cross_kv = buf(nl, captions, 2, cfg.heads, L, 64)
         self.key_mask = buf(captions, L, dtype=u8)
         self.key_len = buf(captions, dtype=i32)
         self.Kc = 2 * beams if beams > 1 else 1
@@ -114,9 +115,9 @@ class Generator:
             self.key_mask.copy_(mask.to(torch.uint8))
         self.key_len.copy_(K.mask_key_len(self.key_mask))
         lin = model.model.decoder.lin_cross_kv  # rows [l*2d, (l+1)*2d) = [k_l ; v_l]
-        h2 = h.reshape(C * L, d)
-        for l in range(cfg.dec_layers):
-            K.gemm(h2, lin.w16[l * 2 * d:(l + 1) * 2 * d], out=self.cross_kv[l], bias=lin.b32[l * 2 * d:(l + 1) * 2 * d])
+        for l in range(cfg.dec_layers):  # batch dim = caption; 64-column groups (heads) scatter to their own [L][64] blocks
+            K.gemm(h, lin.w16[l * 2 * d:(l + 1) * 2 * d].unsqueeze(0).expand(C, 2 * d, d), out=self.cross_kv[l],
+                   bias=lin.b32[l * 2 * d:(l + 1) * 2 * d], head_major=(64, 2 * d * L, 0, L * 64))
         return enc
 
     # ------------------------------------------------------------------ one decoding step (capturable)
@@ -139,7 +140,8 @@ class Generator:
             K.add_layernorm_fwd(self.proj, x, a.ln.g, a.ln.b, out=x2, want_stats=False)
             a = layer.encoder_attn
             K.gemm(x2, a.lin_q.w16, out=self.qb, bias=a.lin_q.b32)
-            K.decode_cross_attn(self.qb, self.cross_kv[l], d, self.key_mask, self.key_len, self.attn, self.C, self.nb, self.L, H)
+            K.decode_cross_attn(self.qb, self.cross_kv[l, :, 0], self.cross_kv[l, :, 1], self.key_mask, self.key_len, self.attn,
+                                self.nb)
             K.gemm(self.attn, a.lin_o.w16, out=self.proj, bias=a.lin_o.b32)
             K.add_layernorm_fwd(self.proj, x2, a.ln.g, a.ln.b, out=x, want_stats=False)
             K.gemm(x, layer.lin_fc1.w16, out=self.h, bias=layer.lin_fc1.b32, act=K.ACT_GELU)

@@ -31,7 +31,8 @@ def _as4(t: torch.Tensor) -> torch.Tensor:
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a_mn: bool = False,
          b_mn: bool = False, bias: torch.Tensor | None = None, alpha: float = 1.0, act: int = ACT_NONE,
          aux_out: torch.Tensor | None = None, aux_in: torch.Tensor | None = None, dact: int = ACT_NONE,
-         accumulate: bool = False, out_dtype: torch.dtype = torch.bfloat16, tile_n: int = 0) -> torch.Tensor:
+         accumulate: bool = False, out_dtype: torch.dtype = torch.bfloat16, tile_n: int = 0,
+         head_major: tuple | None = None) -> torch.Tensor:
     """out[..., m, n] = epilogue(sum_k A[..., m, k] * B[..., n, k]) for up to two batch dims.
 
     a: [..., M, K] (or [..., K, M] when a_mn), b: [..., N, K] (or [..., K, N] when b_mn); bf16, innermost
@@ -57,7 +58,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     nb1, nb0 = a4.shape[0], a4.shape[1]
     if out is None:
         out = torch.empty(tuple(a.shape[:-2]) + (M, N), dtype=out_dtype, device=a.device)
-    o4 = _as4(out)
+    if head_major is not None:  # scattered (head-major) output: `out` only supplies base pointer, dtype and capacity
+        if aux_out is not None or aux_in is not None or out.numel() < nb1 * nb0 * M * N:
+            raise ValueError("gemm head_major output: no aux tensors, and out must hold batch*M*N elements")
+        o4 = torch.empty_strided((nb1, nb0, M, N), (0, 0, 0, 1), dtype=out.dtype, device="meta")  # shape carrier only
+    else:
+        o4 = _as4(out)
     if tuple(o4.shape) != (nb1, nb0, M, N) or o4.stride(3) != 1:
         raise ValueError(f"gemm out has shape {tuple(out.shape)}, expected batch+({M},{N}) with innermost stride 1")
     for aux in (aux_out, aux_in):
@@ -71,7 +77,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     d.M, d.N, d.K, d.batch0, d.batch1 = M, N, K, nb0, nb1
     d.a, d.lda, d.a_sb0, d.a_sb1 = a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0)
     d.b, d.ldb, d.b_sb0, d.b_sb1 = b4.data_ptr(), b4.stride(2), b4.stride(1), b4.stride(0)
-    d.c, d.ldc, d.c_sb0, d.c_sb1 = o4.data_ptr(), o4.stride(2), o4.stride(1), o4.stride(0)
+    d.c, d.ldc, d.c_sb0, d.c_sb1 = out.data_ptr(), o4.stride(2), o4.stride(1), o4.stride(0)
     d.bias, d.aux_out, d.aux_in = ptr(bias), ptr(aux_out), ptr(aux_in)
     d.alpha = alpha
     d.a_mn_major, d.b_mn_major = int(a_mn), int(b_mn)
@@ -79,6 +85,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     if out.dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("gemm out must be bf16 or fp32")
     d.act, d.dact, d.accumulate, d.tile_n = act, dact, int(accumulate), tile_n
+    if head_major is not None:
+        # `out` only supplies the base pointer: element (b0, m, n) goes to b0*sb0 + m*ldc + (n // 64)*chunk + n % 64
+        d.ldc, d.c_sb0, d.c_sb1, d.c_chunk_stride = head_major
     if PROFILE is not None:  # bench.py roofline pass: CUDA events around every launch, on the launching stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -339,12 +348,14 @@ def decode_self_attn(qkv, kcache, vcache, anc, cur_len, out, H, maxT):
     return out
 
 
-def decode_cross_attn(q, kv, v_off, key_mask, key_len, out, captions, nq, L, H):
-    """q [captions*nq, d] (row stride q.stride(0)), kv [captions*L, >= 2d] with k at column 0, v at v_off."""
-    d = out.shape[1]
-    check(lib().vacnic_decode_cross_attn(ptr(q), q.stride(0), ptr(kv), kv.stride(0), v_off, ptr(key_mask), ptr(key_len),
-                                         ptr(out), out.stride(0), captions, nq, L, H, d // H, stream_ptr()),
-          "vacnic_decode_cross_attn")
+def decode_cross_attn(q, k4, v4, key_mask, key_len, out, nq):
+    """q [captions*nq, d]; k4 / v4 [captions, H, L, 64] views (any caption / head / row strides, innermost 1)."""
+    captions, H, L, hd = k4.shape
+    if k4.stride() != v4.stride() or k4.stride(3) != 1:
+        raise ValueError("decode_cross_attn: k and v views must share strides, innermost stride 1")
+    check(lib().vacnic_decode_cross_attn(ptr(q), q.stride(0), k4.data_ptr(), v4.data_ptr(), k4.stride(2), k4.stride(1),
+                                         k4.stride(0), ptr(key_mask), ptr(key_len), ptr(out), out.stride(0), captions, nq, L,
+                                         H, hd, stream_ptr()), "vacnic_decode_cross_attn")
     return out
 
 
