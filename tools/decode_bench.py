@@ -62,3 +62,19 @@ for n in ws:
     t = graph_time(run) / nl
     wb = ws[n][0].numel() * 2
     print(f"decode gemm {n:4s} M={R} N={ws[n][0].shape[0]} K={ws[n][0].shape[1]}: {t * 1e3:.1f} us, weights {wb / 1e9 / (t / 1e3):.0f} GB/s")
+
+# the fused tcgen05 attention kernel used for the decode cross-attention (Sq = beams)
+q4 = q.view(C, nb, H, 64).permute(0, 2, 1, 3)
+for l in range(1):
+    o, _ = K.attn_fwd(q4, kv[l, :, 0], kv[l, :, 1], mask, kl, False, want_stats=False)
+K.decode_cross_attn(q, kv[0, :, 0], kv[0, :, 1], mask, kl, out, nb)
+print("fused vs streaming max diff", (o.view(R, d).float() - out.float()).abs().max().item())
+
+
+def fused_all():
+    for l in range(nl):
+        K.attn_fwd(q4, kv[l, :, 0], kv[l, :, 1], mask, kl, False, want_stats=False)
+
+
+t = graph_time(fused_all) / nl
+print(f"attn_fwd as decode cross-attention: {t * 1e3:.1f} us/launch, {bytes_per / 1e9 / (t / 1e3):.0f} GB/s (algorithmic bytes)")

@@ -356,6 +356,29 @@ class FanoutFn(torch.autograd.Function):
         return acc, None
 
 
+class GradMarkFn(torch.autograd.Function):
+    """Identity whose backward calls `hook(tag)`: it sits on the residual stream at a layer boundary, so when its
+    backward runs every parameter gradient of the layers after the boundary is final and their data-parallel
+    all-reduce can start while the rest of the backward pass continues (vacnic_b200.dp / trainer)."""
+
+    @staticmethod
+    def forward(ctx, x, hook, tag):
+        ctx.hook, ctx.tag = hook, tag
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.hook(ctx.tag)
+        return g, None, None
+
+
+def grad_mark(x, rt: Runtime, tag):
+    hook = getattr(rt, "grad_hook", None)
+    if hook is None or not x.requires_grad:
+        return x
+    return GradMarkFn.apply(x, hook, tag)
+
+
 def fanout(x, n):
     if n == 1 or not x.requires_grad:
         return (x,) * n

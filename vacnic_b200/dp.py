@@ -1,0 +1,120 @@
+"""Data-parallel gradient exchange for the VACNIC training step (the reference wraps the model in
+DistributedDataParallel, TRAIN:87; gradients are averaged over ranks before optimizer.step()).
+
+One process per GPU.  All gradients live in ONE flat fp32 buffer (store.ParamStore), so the exchange is a
+handful of in-place NCCL all-reduces (sum) over address ranges of that buffer, issued on a communication
+stream as soon as the backward pass has finished the parameters of a bucket — the decoder + LM head first,
+then the encoder layers in groups, last the embeddings / prefix modules whose gradients complete at the very
+end.  The 1/world factor is folded into the fused AdamW kernel (hyper[7]), never applied to the buffer.
+
+The bucket bookkeeping is plain tensor / process-group code with no CUDA dependency so that it is covered by
+world-size-2 gloo tests on CPU (tests/test_dp_cpu.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def merge_ranges(ranges: Sequence[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """Sort and coalesce half-open [a, b) ranges."""
+    out: List[Tuple[int, int]] = []
+    for a, b in sorted(r for r in ranges if r[1] > r[0]):
+        if out and a <= out[-1][1]:
+            out[-1] = (out[-1][0], max(out[-1][1], b))
+        else:
+            out.append((a, b))
+    return out
+
+
+def complement(ranges: Sequence[Tuple[int, int]], total: int) -> List[Tuple[int, int]]:
+    out, pos = [], 0
+    for a, b in merge_ranges(ranges):
+        if a > pos:
+            out.append((pos, a))
+        pos = max(pos, b)
+    if pos < total:
+        out.append((pos, total))
+    return out
+
+
+class GradBuckets:
+    """Address-range buckets over a flat gradient buffer.
+
+    `spans`: parameter name -> (offset, numel) in the flat buffer; `bucket_prefixes`: for each bucket, the
+    name prefixes of the parameters it owns, in the order the backward pass completes them.  Everything not
+    claimed by a bucket forms the final bucket reduced by `finish()`."""
+
+    def __init__(self, grad: torch.Tensor, spans: Dict[str, Tuple[int, int]], bucket_prefixes: Sequence[Sequence[str]],
+                 group=None, max_gap: int = 63):
+        self.grad, self.group = grad, group
+        self.world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
+        self.buckets: List[List[Tuple[int, int]]] = []
+        claimed: List[Tuple[int, int]] = []
+        for prefixes in bucket_prefixes:
+            rs = [(o, o + n) for name, (o, n) in spans.items() if any(name.startswith(p) for p in prefixes)]
+            rs = merge_ranges(rs)
+            # alignment padding (< 64 elements) between neighbouring parameters: bridge it so a layer is one range
+            bridged: List[Tuple[int, int]] = []
+            for a, b in rs:
+                if bridged and a - bridged[-1][1] <= max_gap and not self._overlaps(claimed, bridged[-1][1], a):
+                    bridged[-1] = (bridged[-1][0], b)
+                else:
+                    bridged.append((a, b))
+            self.buckets.append(bridged)
+            claimed += bridged
+        srt = sorted(claimed)
+        if any(srt[i][0] < srt[i - 1][1] for i in range(1, len(srt))):
+            raise ValueError("gradient buckets overlap")
+        self.rest = complement(claimed, grad.numel())
+        self.done = [False] * len(self.buckets)
+        self.bytes_reduced = 0
+
+    @staticmethod
+    def _overlaps(ranges, a, b) -> bool:
+        return any(x < b and a < y for x, y in ranges)
+
+    def _reduce(self, ranges):
+        for a, b in ranges:
+            if self.world > 1 or self.group is not None:  # an explicit group is always exercised (1-GPU debugging)
+                dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.SUM, group=self.group)
+            self.bytes_reduced += (b - a) * self.grad.element_size()
+
+    def begin_step(self):
+        self.done = [False] * len(self.buckets)
+        self.bytes_reduced = 0
+
+    def reduce_bucket(self, i: int):
+        if self.done[i]:
+            raise RuntimeError(f"gradient bucket {i} reduced twice in one step")
+        self.done[i] = True
+        self._reduce(self.buckets[i])
+
+    def finish(self):
+        """Reduce whatever has not been reduced yet (buckets whose hook never fired + the unclaimed remainder)."""
+        for i, d in enumerate(self.done):
+            if not d:
+                self.reduce_bucket(i)
+        self._reduce(self.rest)
+
+
+def vacnic_bucket_prefixes(enc_layers: int, dec_layers: int, group_size: int = 3) -> List[List[str]]:
+    """Bucket 0: LM head + every decoder layer (complete once the decoder backward is done); then the encoder
+    layers from the last group to the first.  Embeddings, the ClipCap prefix MLP, visual_map and the face linear
+    receive gradient until the very end of the backward pass and stay in the remainder."""
+    buckets = [["lm_head."] + [f"model.decoder.layers.{i}." for i in range(dec_layers)]]
+    hi = enc_layers
+    while hi > 0:
+        lo = max(0, hi - group_size)
+        buckets.append([f"model.encoder.layers.{i}." for i in range(lo, hi)])
+        hi = lo
+    return buckets
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard of `n_items` independent items (captions at inference) owned by `rank`."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)

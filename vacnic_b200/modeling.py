@@ -267,9 +267,10 @@ class BartEncoder(nn.Module):
             if cfg.d_model == 1024:
                 img = Bk.LinearFn.apply(img, st.anchor, rt, self.lin_vmap, torch.bfloat16, True, None, None)
         states = []
-        for layer in self.layers:
+        for i, layer in enumerate(self.layers):
             if output_hidden_states:
                 states.append(h)
+            h = Bk.grad_mark(h, rt, ("enc", i))  # backward: gradients of encoder layers >= i are final
             h, face, ner, img = layer(h, key_mask, img, face, ner, fn_mask)
         if output_hidden_states:
             states.append(h)
@@ -317,6 +318,8 @@ class BartDecoder(nn.Module):
                              self.ln_emb, 2, cfg.pad_token_id)
         enc_mask = None if encoder_attention_mask is None else Bk.KeyMask(encoder_attention_mask)
         dec_mask = None if attention_mask is None else Bk.KeyMask(attention_mask)
+        # backward: once this marker fires, the decoder (incl. the hoisted cross K/V projection) and the LM head are done
+        encoder_hidden_states = Bk.grad_mark(encoder_hidden_states, rt, ("dec", 0))
         kv_all = Bk.LinearFn.apply(encoder_hidden_states, st.anchor, rt, self.lin_cross_kv, torch.bfloat16, True, None, None)
         dkv_all = torch.empty_like(kv_all) if (torch.is_grad_enabled() and kv_all.requires_grad) else None
         states = []

@@ -9,12 +9,14 @@ hyper-parameters (lr and Adam bias corrections), replay.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
 
 from . import blocks as Bk
 from . import kernels as K
+from .dp import GradBuckets, vacnic_bucket_prefixes
 from .modeling import VacnicBart, shift_tokens_right
 
 
@@ -49,15 +51,46 @@ class TrainStep:
         self.static: Dict[str, torch.Tensor] = {}
         self.losses: Dict[str, torch.Tensor] = {}
         self.launches_per_step = 0
+        self.buckets: Optional[GradBuckets] = None
+        if self.world > 1 or (process_group is not None and os.environ.get("VACNIC_DP_FORCE")):
+            # data-parallel exchange: bucketed in-place all-reduce of the flat gradient buffer on a side stream,
+            # started from markers in the backward pass (vacnic_b200.dp, blocks.GradMarkFn)
+            spans = {n: (st.offsets[n], p.numel()) for n, p in st.params.items()}
+            prefixes = vacnic_bucket_prefixes(self.cfg.enc_layers, self.cfg.dec_layers, group_size=3)
+            self.buckets = GradBuckets(st.grad, spans, prefixes, group=process_group)
+            self.comm_stream = torch.cuda.Stream(device=dev)
+            self._tag_to_bucket = {("dec", 0): 0}
+            hi, k = self.cfg.enc_layers, 1
+            while hi > 0:
+                lo = max(0, hi - 3)
+                self._tag_to_bucket[("enc", lo)] = k
+                hi, k = lo, k + 1
         self._g_txt = torch.ones(1, device=dev)
         self._g_margin = torch.full((1,), alpha, device=dev)
         self._g_secla = torch.full((1,), secla_weight, device=dev)
+
+    def _on_grad_ready(self, tag):
+        """Backward-pass marker (runs inside the autograd engine): the gradients of bucket `tag` are final at this point
+        of the compute stream.  Only an event is recorded here; the all-reduce that waits for it is enqueued on the
+        communication stream by `_body` right after the (asynchronous) backward pass has been enqueued, so on the GPU
+        timeline it still overlaps the remaining backward kernels — and no NCCL call is made from an engine thread."""
+        i = self._tag_to_bucket.get(tag)
+        if i is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._ready.append((i, ev))
 
     # ------------------------------------------------------------------ the step body (capturable)
     def _body(self, b: Dict[str, torch.Tensor]):
         model, guide, cfg = self.model, self.guide, self.cfg
         st = model.store
         st.begin_step()
+        # the backward-pass markers call into THIS step object (another TrainStep may share the model)
+        model.rt.grad_hook = self._on_grad_ready if self.buckets is not None else None
+        if self.buckets is not None:
+            self.buckets.begin_step()
+            self._ready = []
         model.rt.rng.advance()
         src, tgt = b["article_ids"], b["caption_ids"]
         dec_in = b["decoder_input_ids"]
@@ -85,8 +118,16 @@ class TrainStep:
             losses["secla"] = secla
         torch.autograd.backward(heads, grads)
         st.finish_backward()
-        if self.world > 1:
-            torch.distributed.all_reduce(st.grad, group=self.pg)  # sum; the 1/world mean is folded into hyper[7]
+        if self.buckets is not None:  # sum over ranks; the 1/world mean is folded into hyper[7]
+            for i, ev in self._ready:  # bucket i only depends on the point of the backward pass where it became final
+                if not self.buckets.done[i]:
+                    self.comm_stream.wait_event(ev)
+                    with torch.cuda.stream(self.comm_stream):
+                        self.buckets.reduce_bucket(i)
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.buckets.finish()  # embeddings / prefix modules + any bucket whose marker did not fire
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
         K.adamw(st.master, st.grad, self.m, self.v, st.shadow, self.hyper)
         return losses
 
