@@ -159,6 +159,10 @@ int vacnic_colsum(const void* x, float* out, int64_t rows, int32_t n, int64_t ld
 int vacnic_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int vacnic_concat_rows(const void* a, const void* b, void* out, int32_t B, int64_t rows_a, int64_t rows_b, int32_t d,
                        void* stream); /* out[B, ra+rb, d] = cat(a[B,ra,d], b[B,rb,d]) : MFULL:668, 691 */
+/* dst[r, 0..ld_dst) = {src[r, 0..n), 0 ...} (bf16): re-pitch rows for TMA (16-byte row pitch). */
+int vacnic_pad_rows(const void* src, void* dst, int64_t rows, int32_t n, int32_t ld_dst, void* stream);
+/* dst[j] (+)= sum_p src[p*len + j] (fp32): reduces split partial weight gradients. */
+int vacnic_sum_partials(const float* src, float* dst, int32_t parts, int64_t len, int32_t accumulate, void* stream);
 int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream); /* out = a + b (+ c) */
 /* Fused AdamW over a flat parameter buffer (TRAIN:91-107,371-373).  hyper (device, fp32[8]) =
  * {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}; also refreshes the bf16

@@ -285,33 +285,51 @@ class EmbedFn(torch.autograd.Function):
 
 
 class NerMapFn(torch.autograd.Function):
-    """prefix = LN(reshape(gelu(reshape(ner) W_up^T + b) W_down^T + b))  (MFULL:682-688): [B,E,d] -> [B,G,d]."""
+    """prefix = LN(reshape(gelu(reshape(ner) W_up^T + b) W_down^T + b))  (MFULL:682-688): [B,E,d] -> [B,G,d].
+
+    The reference's reshape(B, d, E) is a memory REINTERPRETATION of the contiguous [B, E, d] buffer, so the two
+    linears are plain GEMMs over R = B*d rows of E = 80 contiguous elements (K = 80, N = 80 / 20): they run on the
+    tcgen05 GEMM (TMA zero-fills the ragged K / N edges).  Only the 20-wide tensors (40-byte rows) need a re-pitch
+    before TMA can read them back in the backward pass."""
+    SPLIT = 64  # weight gradients: R rows are reduced in SPLIT independent slabs, then summed (deterministic)
 
     @staticmethod
     def forward(ctx, ner, rt: Runtime, up: Lin, down: Lin, ln: LN):
         B, E, d = ner.shape
         G = down.out_f
         x_rows = ner.reshape(B * d, E)
-        z1, z2 = K.ner_map_fwd(x_rows, up.w16, up.b32, down.w16, down.b32)
+        z1 = torch.empty(B * d, up.out_f, dtype=torch.bfloat16, device=ner.device)
+        y1 = K.gemm(x_rows, up.w16, bias=up.b32, act=K.ACT_GELU, aux_out=z1)
+        z2 = K.gemm(y1, down.w16, bias=down.b32)
         z2r = z2.view(B * G, d)
         y, mean, rstd = K.add_layernorm_fwd(z2r, None, ln.g, ln.b)
         ctx.rt, ctx.up, ctx.down, ctx.ln = rt, up, down, ln
-        ctx.saved = (x_rows, z1, z2r, mean, rstd)
+        ctx.saved = (x_rows, z1, y1, z2r, mean, rstd)
         ctx.dims = (B, E, d, G)
         return y.view(B, G, d)
 
     @staticmethod
     def backward(ctx, dy):
         rt, up, down, ln = ctx.rt, ctx.up, ctx.down, ctx.ln
-        x_rows, z1, z2r, mean, rstd = ctx.saved
+        x_rows, z1, y1, z2r, mean, rstd = ctx.saved
         B, E, d, G = ctx.dims
+        R, U = B * d, up.out_f
         dz2, _ = K.add_layernorm_bwd(dy.contiguous().view(B * G, d), z2r, None, ln.g, mean, rstd, ln.gg, ln.gb)
-        # the NER-map weight gradients live in the atomically accumulated (zeroed each step) region? No:
-        # they are 2-D, so zero them on first touch, then accumulate atomically.
-        for lin in (up, down):
-            if not rt.store.touch(lin.key):
-                lin.gw.zero_()
-        dx = K.ner_map_bwd(dz2.view(B * d, G), z1, x_rows, up.w16, down.w16, up.gw, up.gb, down.gw, down.gb)
+        Gp = (G + 7) // 8 * 8
+        dz2p = K.pad_rows(dz2.view(R, G), Gp)[:, :G]  # 16-byte row pitch for TMA
+        # dz1 = (dz2 W_down) * gelu'(z1) ; dx = dz1 W_up
+        dz1 = K.gemm(dz2p, down.w16, b_mn=True, dact=K.ACT_GELU, aux_in=z1)
+        dx = K.gemm(dz1, up.w16, b_mn=True)
+        # weight gradients: [S, R/S, .]^T [S, R/S, .] partial products, then a fixed-order sum over the S slabs
+        S = NerMapFn.SPLIT if R % NerMapFn.SPLIT == 0 and (R // NerMapFn.SPLIT) % 8 == 0 else 1
+        part_up = torch.empty(S, U, E, dtype=torch.float32, device=dy.device)
+        K.gemm(dz1.view(S, R // S, U), x_rows.view(S, R // S, E), out=part_up, a_mn=True, b_mn=True)
+        K.sum_partials(part_up.view(S, U * E), up.gw, accumulate=rt.store.touch(up.key))
+        part_dn = torch.empty(S, G, U, dtype=torch.float32, device=dy.device)
+        K.gemm(dz2p.unflatten(0, (S, R // S)), y1.view(S, R // S, U), out=part_dn, a_mn=True, b_mn=True)
+        K.sum_partials(part_dn.view(S, G * U), down.gw, accumulate=rt.store.touch(down.key))
+        K.colsum_into(dz1, up.gb)
+        K.colsum_into(dz2p, down.gb)
         ctx.saved = None
         return dx.view(B, E, d), None, None, None, None
 

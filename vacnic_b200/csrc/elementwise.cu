@@ -144,6 +144,28 @@ concat_rows_kernel(const uint4* __restrict__ a, const uint4* __restrict__ c, uin
 
 __global__ void rng_advance_kernel(unsigned long long* state) { *state += 0x9E3779B97F4A7C15ull; }
 
+
+// dst[r, 0..ld_dst) = {src[r, 0..n), 0...}: re-pitches rows whose byte length is not a multiple of 16 so that TMA can
+// read them (the NER-map gradient dz2 has 20-element = 40-byte rows)
+__global__ void __launch_bounds__(256)
+pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int n, int ld_dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= rows * ld_dst) return;
+  const long long r = i / ld_dst;
+  const int c = static_cast<int>(i % ld_dst);
+  dst[i] = c < n ? src[r * n + c] : __float2bfloat16_rn(0.f);
+}
+
+// dst[j] (+)= sum_p src[p, j]: reduction of split-K partial weight gradients (fp32)
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const float* __restrict__ src, float* __restrict__ dst, int parts, long long len, int accumulate) {
+  const long long j = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (j >= len) return;
+  float s = accumulate ? dst[j] : 0.f;
+  for (int p = 0; p < parts; ++p) s += __ldg(src + p * len + j);
+  dst[j] = s;
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -224,4 +246,21 @@ extern "C" int vacnic_rng_advance(uint64_t* state, void* stream) {
   rng_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(state));
   count_launch();
   return check_last("rng_advance");
+}
+
+extern "C" int vacnic_pad_rows(const void* src, void* dst, int64_t rows, int32_t n, int32_t ld_dst, void* stream) {
+  VB_REQUIRE(src && dst && rows > 0 && n > 0 && ld_dst >= n, "pad_rows: bad arguments");
+  const long long total = rows * ld_dst;
+  pad_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, n, ld_dst);
+  count_launch();
+  return check_last("pad_rows");
+}
+
+extern "C" int vacnic_sum_partials(const float* src, float* dst, int32_t parts, int64_t len, int32_t accumulate, void* stream) {
+  VB_REQUIRE(src && dst && parts > 0 && len > 0, "sum_partials: bad arguments");
+  sum_partials_kernel<<<static_cast<unsigned>((len + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, parts, len,
+                                                                                                          accumulate);
+  count_launch();
+  return check_last("sum_partials");
 }

@@ -236,6 +236,20 @@ def add_bf16(a, b, c=None, out=None):
     return out
 
 
+def pad_rows(src2d, ld_dst):
+    """bf16 [rows, n] contiguous -> [rows, ld_dst] zero padded (TMA needs a 16-byte row pitch)."""
+    rows, n = src2d.shape
+    dst = torch.empty(rows, ld_dst, dtype=torch.bfloat16, device=src2d.device)
+    check(lib().vacnic_pad_rows(ptr(src2d), ptr(dst), rows, n, ld_dst, stream_ptr()), "vacnic_pad_rows")
+    return dst
+
+
+def sum_partials(parts2d, dst, accumulate):
+    """dst (+)= parts2d.sum(0); fp32."""
+    check(lib().vacnic_sum_partials(ptr(parts2d), ptr(dst), parts2d.shape[0], dst.numel(), int(accumulate), stream_ptr()),
+          "vacnic_sum_partials")
+
+
 def adamw(p, g, m, v, p16, hyper):
     check(lib().vacnic_adamw(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p16), p.numel(), ptr(hyper), stream_ptr()), "vacnic_adamw")
 
