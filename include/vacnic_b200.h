@@ -89,6 +89,11 @@ typedef struct vacnic_gemm_desc {
    * 64-column group (one attention head) becomes its own [rows][64] block with row stride ldc: the
    * head-major layout of the decode-time cross-attention K/V cache. */
   int64_t c_chunk_stride;
+  /* Optional split-K scratch (device memory, zero-initialised ONCE by the caller, >= 64 KiB + partial tiles; reused
+   * by every call on the same stream): lets problems with few output tiles and a long K spread over idle SMs.
+   * The reduction order is fixed, so results are deterministic.  Null = never split. */
+  void* workspace;
+  int64_t workspace_bytes;
 } vacnic_gemm_desc;
 
 int vacnic_gemm(const vacnic_gemm_desc* d, void* stream);

@@ -21,6 +21,11 @@ struct GemmArgs {
   int vec_ok;  // 16-byte vector access allowed on C / aux rows
   int bias_vec;  // bias pointer 16-byte aligned
   int a_m0, a_m1, b_m0, b_m1;  // batch-coordinate multipliers: 0 = operand is broadcast over that batch dim
+  // split-K (single-CTA kernel): work item = (tile, split); partial accumulators go through `ws`, the last CTA to
+  // finish a tile (ws_count) sums them in split order and runs the epilogue
+  int splits, kb_per_split;
+  float* ws;
+  int* ws_count;
   long long c_chunk;  // != 0: column n lives at (n / 64) * c_chunk + (n % 64) (head-major outputs)
 };
 

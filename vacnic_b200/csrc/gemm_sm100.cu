@@ -33,11 +33,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_k = (g.K + kBK - 1) / kBK;
   const long long tiles_per_batch = static_cast<long long>(g.num_m) * g.num_n;
+  const long long total_work = g.total_tiles * g.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -66,14 +68,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+      for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const long long t = w / g.splits;
+        const int kb0 = static_cast<int>(w % g.splits) * g.kb_per_split;
+        const int kb1 = min(num_k, kb0 + g.kb_per_split);
         const int batch = static_cast<int>(t / tiles_per_batch);
         const int r = static_cast<int>(t % tiles_per_batch);
         const int m0 = (r % g.num_m) * kBM;
         const int n0 = (r / g.num_m) * BN;
         const int b0 = batch % g.batch0;
         const int b1 = batch / g.batch0;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -111,13 +116,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++it) {
+      for (long long w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        const int kb0 = static_cast<int>(w % g.splits) * g.kb_per_split;
+        const int kb1 = min(num_k, kb0 + g.kb_per_split);
         const uint32_t as = it & 1u;
         const uint32_t aphase = (it >> 1) & 1u;
         mbar_wait(&tempty_bar[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -126,7 +133,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * kStepA, kLboA, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * kStepB, kLboB, 1024);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
           if (++stage == Cfg::kStages) {
@@ -142,7 +149,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;  // which half of the tile's columns
     uint32_t it = 0;
-    for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++it) {
+    for (long long w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const long long t = w / g.splits;
+      const int sp = static_cast<int>(w % g.splits);
       const int batch = static_cast<int>(t / tiles_per_batch);
       const int r = static_cast<int>(t % tiles_per_batch);
       const int m0 = (r % g.num_m) * kBM;
@@ -158,22 +167,73 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 static_cast<long long>(b1) * g.c_sb1 +
                                 static_cast<long long>(row) * g.ldc;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      if (g.splits == 1) {
 #pragma unroll 1
-      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
-        if (n0 + c * 32 >= g.N) break;
-        uint32_t r32[32];
-        tmem_ld_32x32(taddr + c * 32, r32);
-        tmem_ld_wait();
-        if (row < g.M) {
-          float v[32];
+        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+          if (n0 + c * 32 >= g.N) break;
+          uint32_t r32[32];
+          tmem_ld_32x32(taddr + c * 32, r32);
+          tmem_ld_wait();
+          if (row < g.M) {
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r32[j]);
-          epilogue_row_chunk(g, v, row_off, n0 + c * 32);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r32[j]);
+            epilogue_row_chunk(g, v, row_off, n0 + c * 32);
+          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      } else {
+        // ---- split-K: publish the raw partial tile, the last split to arrive reduces in split order
+        float* wtile = g.ws + (t * g.splits) * (kBM * BN) + static_cast<long long>(quad * 32 + lane) * BN;
+        float* wmine = wtile + static_cast<long long>(sp) * (kBM * BN);
+#pragma unroll 1
+        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+          uint32_t r32[32];
+          tmem_ld_32x32(taddr + c * 32, r32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            __stcg(reinterpret_cast<float4*>(wmine + c * 32) + q,
+                   make_float4(__uint_as_float(r32[4 * q]), __uint_as_float(r32[4 * q + 1]), __uint_as_float(r32[4 * q + 2]),
+                               __uint_as_float(r32[4 * q + 3])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int old = atomicAdd(g.ws_count + t, 1);
+          const int last = (old == g.splits - 1) ? 1 : 0;
+          if (last) g.ws_count[t] = 0;  // self-resetting: the next launch finds zeros
+          *last_flag = last;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (*last_flag) {
+          __threadfence();
+#pragma unroll 1
+          for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+            if (n0 + c * 32 >= g.N) break;
+            if (row < g.M) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              for (int s2 = 0; s2 < g.splits; ++s2) {
+                const float4* src = reinterpret_cast<const float4*>(wtile + static_cast<long long>(s2) * (kBM * BN) + c * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 f = __ldcg(src + q);
+                  v[4 * q] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
+                }
+              }
+              epilogue_row_chunk(g, v, row_off, n0 + c * 32);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // last_flag is rewritten by the next work item
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
   }
 
@@ -263,7 +323,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int sms = sm_count();
   if (sms <= 0) return fail(VACNIC_EDEVICE, "gemm: no CUDA device");
-  const int grid = static_cast<int>(g.total_tiles < sms ? g.total_tiles : sms);
+  const long long work = g.total_tiles * g.splits;
+  const int grid = static_cast<int>(work < sms ? work : sms);
   kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, g);
   count_launch();
   return check_last("gemm launch");
@@ -329,9 +390,27 @@ extern "C" int vacnic_gemm(const vacnic_gemm_desc* d, void* stream_v) {
   // tile_n: 0 = choose; 64 / 128 / 256 = single-CTA kernel with that tile width; 1128 / 1256 = CTA-pair kernel
   int bn = d->tile_n;
   int pair_bn = 0;
+  int splits = 1;
+  const int num_k_blocks = (d->K + kBK - 1) / kBK;
   if (bn == 0) {
     pair_bn = choose_pair_tile_n(d, sms);
     bn = pair_bn != 0 ? pair_bn : choose_tile_n(d, sms);
+    if (pair_bn == 0 && d->workspace != nullptr && num_k_blocks >= 4) {
+      // few output tiles and a long reduction: spread K over otherwise idle SMs (wide tiles keep the L2 -> smem
+      // traffic per FLOP low, split-K supplies the parallelism)
+      const int wide = d->N >= 256 ? 256 : (d->N >= 128 ? 128 : 64);
+      const long long tiles = static_cast<long long>(d->batch0) * d->batch1 * ((d->M + kBM - 1) / kBM) * ((d->N + wide - 1) / wide);
+      if (tiles * 2 <= sms) {
+        int s = static_cast<int>(sms / tiles);
+        if (s > 8) s = 8;
+        if (s > num_k_blocks / 2) s = num_k_blocks / 2;
+        const long long need = 65536 + tiles * s * kBM * wide * 4;
+        if (s >= 2 && tiles <= 16384 && need <= d->workspace_bytes) {
+          bn = wide;
+          splits = s;
+        }
+      }
+    }
   } else if (bn == 1128 || bn == 1256) {
     pair_bn = bn - 1000;
     bn = pair_bn;
@@ -349,6 +428,10 @@ extern "C" int vacnic_gemm(const vacnic_gemm_desc* d, void* stream_v) {
   g.alpha = d->alpha; g.c_dtype = d->c_dtype; g.act = d->act; g.dact = d->dact;
   g.accumulate = d->accumulate;
   g.c_chunk = d->c_chunk_stride;
+  g.kb_per_split = (num_k_blocks + splits - 1) / splits;
+  g.splits = (num_k_blocks + g.kb_per_split - 1) / g.kb_per_split;  // every split owns at least one k-block
+  g.ws_count = static_cast<int*>(d->workspace);
+  g.ws = d->workspace ? reinterpret_cast<float*>(static_cast<char*>(d->workspace) + 65536) : nullptr;
   // Vector (16 B) row access needs every row start of C / aux to be 16-byte aligned.
   const int c_es = d->c_dtype == VACNIC_DT_F32 ? 4 : 2;
   auto aligned = [&](const void* p, int es) {

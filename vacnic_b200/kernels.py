@@ -11,6 +11,22 @@ from .lib import (ACT_GELU, ACT_NONE, ACT_TANH, DT_BF16, DT_F32, MASK_CAUSAL, MA
                   MASK_NONE, AttnDesc, GemmDesc, check, lib, ptr, stream_ptr)
 
 
+_WORKSPACES = {}  # device index -> zero-initialised split-K scratch of vacnic_gemm (GEMMs of one device are
+# issued on one stream at a time: eager stream, capture stream and graph replays never overlap)
+SPLIT_K_BYTES = 64 << 20
+
+
+def _gemm_workspace(device):
+    key = device.index
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None  # never allocate + memset inside a capture: this launch simply does not split
+        ws = torch.zeros(SPLIT_K_BYTES, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 PROFILE = None  # set to a list to collect (flops, start_event, end_event, shape) per GEMM launch
 
 
@@ -32,7 +48,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
          b_mn: bool = False, bias: torch.Tensor | None = None, alpha: float = 1.0, act: int = ACT_NONE,
          aux_out: torch.Tensor | None = None, aux_in: torch.Tensor | None = None, dact: int = ACT_NONE,
          accumulate: bool = False, out_dtype: torch.dtype = torch.bfloat16, tile_n: int = 0,
-         head_major: tuple | None = None) -> torch.Tensor:
+         head_major: tuple | None = None, split_k: bool = False) -> torch.Tensor:
     """out[..., m, n] = epilogue(sum_k A[..., m, k] * B[..., n, k]) for up to two batch dims.
 
     a: [..., M, K] (or [..., K, M] when a_mn), b: [..., N, K] (or [..., K, N] when b_mn); bf16, innermost
@@ -85,6 +101,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     if out.dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("gemm out must be bf16 or fp32")
     d.act, d.dact, d.accumulate, d.tile_n = act, dact, int(accumulate), tile_n
+    # split-K is opt-in: measured on B200 the partial-tile round trip through L2 costs more than it saves for the
+    # K <= 4096 problems of this model (decode fc2 23 -> 60 us), so no hot-path call site enables it
+    ws = _gemm_workspace(a.device) if (split_k and tile_n == 0) else None
+    if ws is not None:
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     if head_major is not None:
         # `out` only supplies the base pointer: element (b0, m, n) goes to b0*sb0 + m*ldc + (n // 64)*chunk + n % 64
         d.ldc, d.c_sb0, d.c_sb1, d.c_chunk_stride = head_major
