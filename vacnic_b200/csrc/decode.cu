@@ -153,152 +153,208 @@ decode_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cross-attention of NQ query rows (the beams of one caption) over that caption's L cached keys
-// (MFULL:474-479 cache branch).  grid (H, captions), 128 threads; two streaming passes: K -> scores in
-// shared memory -> exact max-subtracted softmax -> V.  Keys at or beyond key_len[c] and keys whose mask
-// byte is 0 contribute exactly 0 in the reference (exp(finfo.min - max) == 0), so they are skipped.
+// Cross-attention of the beams of one caption over that caption's L cached keys (MFULL:474-479 cache branch):
+// grid (H, captions), 128 threads.  HBM-bound streaming of K then V, exact max-subtracted softmax through shared
+// memory in between.  Keys at or beyond key_len[c] contribute exactly 0 in the reference (exp(finfo.min - max) == 0)
+// and are skipped.  The dot products run on the tensor cores (warp-level mma.sync m16n8k16, bf16 x bf16 -> fp32; a
+// CUDA-core version was issue-bound at 2.8 TB/s): K / V tiles of 16 keys are staged through per-warp 6-deep
+// cp.async rings in XOR-swizzled shared memory and consumed with ldmatrix:
+//   pass 1   S^T[key][q]  = K_tile[key][dim] . Q^T[dim][q]      A = K (row-major), B = Q^T in registers
+//   softmax  exact, over shared-memory scores (as above)
+//   pass 2   O^T[dim][q] += V_tile^T[dim][key] . P^T[key][q]    A = V via ldmatrix.trans, B = P from shared memory
+// Up to 8 queries (beams) per caption ride in the n = 8 dimension of one instruction.
 // ------------------------------------------------------------------------------------------------
-template <int NQ>
+constexpr int kXTile = 16;                    // keys per tile: one m16n8k16 row block per warp step
+constexpr int kXStages = 6;                   // cp.async ring depth PER WARP
+constexpr int kXTileBytes = kXTile * 128;     // 2 KB
+constexpr int kXWarpRing = kXStages * kXTileBytes;  // 12 KB
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Each of the 4 warps streams its own contiguous quarter of the caption's keys through a private ring (no block-wide
+// barrier inside the streaming loops); the warps meet only for the softmax statistics and the final reduction.
 __global__ void __launch_bounds__(128)
-decode_cross_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kp,
-                         const __nv_bfloat16* __restrict__ vp, long long ldkv, long long kv_hs, long long kv_cs,
-                         const uint8_t* __restrict__ key_mask, const int32_t* __restrict__ key_len,
-                         __nv_bfloat16* __restrict__ out, long long ldo, int nq, int L, float scale) {
-  extern __shared__ float dsm[];
-  float* sc = dsm;                 // [NQ][L]
-  float* red = dsm + NQ * L;       // [4 warps][NQ][64] partial outputs (also used for max / sum)
-  __shared__ float stat[2][NQ][4];
+decode_cross_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kp,
+                             const __nv_bfloat16* __restrict__ vp, long long ldkv, long long kv_hs, long long kv_cs,
+                             const uint8_t* __restrict__ key_mask, const int32_t* __restrict__ key_len,
+                             __nv_bfloat16* __restrict__ out, long long ldo, int nq, int L, float scale) {
+  extern __shared__ __align__(128) uint8_t xsm[];
+  float* sc = reinterpret_cast<float*>(xsm + 4 * kXWarpRing);  // [nq][Lp]
+  float* red = reinterpret_cast<float*>(xsm);                  // [4][64][8] partial O^T, aliases the rings after pass 2
+  __shared__ float stat[2][8][4];
   const int h = blockIdx.x, c = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 3, dl = lane & 7;
-  const int Lc = key_len ? min(L, key_len[c]) : L;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  // key_len == 0 (no valid key at all): every key keeps finfo.min and the row degenerates to uniform, as in the reference
+  const int Lc = (key_len && key_len[c] > 0) ? min(L, key_len[c]) : L;
+  const int per = (Lc + 63) / 64 * kXTile;  // keys per warp (multiple of 16)
+  const int ntw = per / kXTile;             // tiles per warp
+  const int Lp = 4 * per;                   // score row pitch
+  const int wkey0 = warp * per;
   const uint8_t* mk = key_mask ? key_mask + static_cast<long long>(c) * L : nullptr;
-  float qf[NQ][8];
+  const __nv_bfloat16* kbase = kp + static_cast<long long>(c) * kv_cs + h * kv_hs;
+  const __nv_bfloat16* vbase = vp + static_cast<long long>(c) * kv_cs + h * kv_hs;
+  uint8_t* wring = xsm + warp * kXWarpRing;
+  const uint32_t ring_u = smem_u32(wring);
+
+  // tile loader (one warp): 16 rows x 8 chunks of 16 B; lane i moves chunks i, i+32, i+64, i+96
+  auto load_tile = [&](const __nv_bfloat16* base, int tile, int stage) {
 #pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    if (i < nq) {
-      unpack8f(__ldg(reinterpret_cast<const uint4*>(q + (static_cast<long long>(c) * nq + i) * ldq + h * 64) + dl), qf[i]);
+    for (int j = 0; j < 4; ++j) {
+      const int idx = lane + 32 * j;
+      const int row = idx >> 3, ch = idx & 7;
+      const int key = wkey0 + tile * kXTile + row;
+      const int off = stage * kXTileBytes + row * 128 + ((ch ^ (row & 7)) << 4);
+      if (key < Lc) cp_async16(ring_u + off, base + static_cast<long long>(key) * ldkv + ch * 8);
+      else *reinterpret_cast<uint4*>(wring + off) = make_uint4(0, 0, 0, 0);
+    }
+  };
+
+  // Q^T fragments: b[ks][0..1] for k-steps of 16 dims; query n = g (zero rows beyond nq)
+  uint32_t qb[4][2];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) qf[i][e] *= scale;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) qf[i][e] = 0.f;
+  for (int ks = 0; ks < 4; ++ks) {
+    qb[ks][0] = qb[ks][1] = 0u;
+    if (g < nq) {
+      const __nv_bfloat16* qr = q + (static_cast<long long>(c) * nq + g) * ldq + h * 64 + ks * 16 + 2 * t4;
+      qb[ks][0] = *reinterpret_cast<const uint32_t*>(qr);
+      qb[ks][1] = *reinterpret_cast<const uint32_t*>(qr + 8);
     }
   }
-  const __nv_bfloat16* kbase = kp + static_cast<long long>(c) * kv_cs + h * kv_hs;
-  // ---- pass 1: scores
-  constexpr int UN = 8;
-  for (int kb = 0; kb < Lc; kb += 16 * UN) {  // block-uniform trip count: the shuffles below need full warps
-    const int k0 = kb + warp * 4 + g;
-    uint4 kk[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int key = k0 + 16 * u;
-      kk[u] = key < Lc ? __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<long long>(key) * ldkv) + dl)
-                       : make_uint4(0, 0, 0, 0);
+
+  // ---------------- pass 1: scores of this warp's keys
+  for (int s = 0; s < kXStages - 1; ++s) {
+    if (s < ntw) load_tile(kbase, s, s);
+    cp_async_commit();
+  }
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;  // ldmatrix row (non-transposed A)
+  for (int tile = 0; tile < ntw; ++tile) {
+    cp_async_wait<kXStages - 2>();
+    __syncwarp();
+    {  // refill the stage consumed in the previous iteration
+      const int nxt = tile + kXStages - 1;
+      if (nxt < ntw) load_tile(kbase, nxt, nxt % kXStages);
+      cp_async_commit();
     }
+    const uint32_t tb = ring_u + (tile % kXStages) * kXTileBytes;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int key = k0 + 16 * u;
-      float f[8];
-      unpack8f(kk[u], f);
-      float dot[NQ];
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[4];
+      const int ch = ks * 2 + (lane >> 4);
+      ldmatrix_x4(tb + arow * 128 + ((ch ^ (arow & 7)) << 4), a);
+      mma_bf16_16816(acc, a, qb[ks][0], qb[ks][1]);
+    }
+    // C fragment: keys g, g+8 of the tile; queries 2*t4, 2*t4+1
+    const int key0 = wkey0 + tile * kXTile + g;
 #pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        float s = 0.f;
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int key = key0 + hrow * 8;
+      const bool oob = key >= Lc;
+      const bool masked = !oob && mk != nullptr && mk[key] == 0;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s += qf[i][e] * f[e];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        dot[i] = s;
-      }
-      if (dl == 0 && key < Lc) {
-        const bool ok = mk == nullptr || mk[key] != 0;
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) sc[i * L + key] = ok ? dot[i] : -INFINITY;
+      for (int e = 0; e < 2; ++e) {
+        const int qi = 2 * t4 + e;
+        if (qi < nq) sc[qi * Lp + key] = oob ? -INFINITY : (masked ? -FLT_MAX : acc[hrow * 2 + e] * scale);
       }
     }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  // prefetch the first V tiles of this warp while the softmax runs
+  for (int s = 0; s < kXStages - 1; ++s) {
+    if (s < ntw) load_tile(vbase, s, s);
+    cp_async_commit();
   }
   __syncthreads();
-  // ---- exact softmax statistics per query
-  float mx[NQ];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
+  // ---------------- exact softmax statistics per query (probabilities stay unnormalised in sc)
+  for (int i = 0; i < nq; ++i) {
     float m = -INFINITY;
-    for (int k = threadIdx.x; k < Lc; k += 128) m = fmaxf(m, sc[i * L + k]);
+    for (int k = tid; k < Lp; k += 128) m = fmaxf(m, sc[i * Lp + k]);
     m = warp_max(m);
     if (lane == 0) stat[0][i][warp] = m;
   }
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    mx[i] = fmaxf(fmaxf(stat[0][i][0], stat[0][i][1]), fmaxf(stat[0][i][2], stat[0][i][3]));
-    float s = 0.f;
-    for (int k = threadIdx.x; k < Lc; k += 128) {
-      const float e = __expf(sc[i * L + k] - mx[i]);
-      sc[i * L + k] = e;
-      s += e;
+  for (int i = 0; i < nq; ++i) {
+    const float m = fmaxf(fmaxf(stat[0][i][0], stat[0][i][1]), fmaxf(stat[0][i][2], stat[0][i][3]));
+    float sum = 0.f;
+    for (int k = tid; k < Lp; k += 128) {
+      const float e = __expf(sc[i * Lp + k] - m);
+      sc[i * Lp + k] = e;
+      sum += e;
     }
-    s = warp_sum(s);
-    if (lane == 0) stat[1][i][warp] = s;
+    sum = warp_sum(sum);
+    if (lane == 0) stat[1][i][warp] = sum;
   }
   __syncthreads();
-  // ---- pass 2: P V
-  float o[NQ][8];
+  // ---------------- pass 2: O^T[dim][q] += V^T P^T over this warp's keys
+  float o[4][4];
 #pragma unroll
-  for (int i = 0; i < NQ; ++i)
+  for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[i][e] = 0.f;
-  const __nv_bfloat16* vbase = vp + static_cast<long long>(c) * kv_cs + h * kv_hs;
-  for (int kb = 0; kb < Lc; kb += 16 * UN) {
-    const int k0 = kb + warp * 4 + g;
-    uint4 vv[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int key = k0 + 16 * u;
-      vv[u] = key < Lc ? __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<long long>(key) * ldkv) + dl)
-                       : make_uint4(0, 0, 0, 0);
+    for (int e = 0; e < 4; ++e) o[mt][e] = 0.f;
+  const int krow = (lane & 7) + (lane >> 4) * 8;  // key row for ldmatrix.trans
+  for (int tile = 0; tile < ntw; ++tile) {
+    cp_async_wait<kXStages - 2>();
+    __syncwarp();
+    {
+      const int nxt = tile + kXStages - 1;
+      if (nxt < ntw) load_tile(vbase, nxt, nxt % kXStages);
+      cp_async_commit();
+    }
+    const uint32_t tb = ring_u + (tile % kXStages) * kXTileBytes;
+    // B fragment: P[q = g][keys 2*t4, 2*t4+1] and [+8, +9] of the tile
+    uint32_t pb0 = 0u, pb1 = 0u;
+    if (g < nq) {
+      const float* pr = sc + g * Lp + wkey0 + tile * kXTile + 2 * t4;
+      const float2 p01 = *reinterpret_cast<const float2*>(pr);
+      const float2 p89 = *reinterpret_cast<const float2*>(pr + 8);
+      pb0 = pack_bf16x2(p01.x, p01.y);
+      pb1 = pack_bf16x2(p89.x, p89.y);
     }
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int key = k0 + 16 * u;
-      if (key < Lc) {
-        float f[8];
-        unpack8f(vv[u], f);
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-          const float p = sc[i * L + key];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[i][e] += p * f[e];
-        }
-      }
+    for (int mt = 0; mt < 4; ++mt) {
+      uint32_t a[4];
+      const int ch = mt * 2 + ((lane >> 3) & 1);
+      ldmatrix_x4_trans(tb + krow * 128 + ((ch ^ (krow & 7)) << 4), a);
+      mma_bf16_16816(o[mt], a, pb0, pb1);
     }
+    __syncwarp();
   }
-  // reduce over the 4 key sub-groups of the warp, then over the 4 warps
+  cp_async_wait<0>();
+  __syncthreads();  // every warp is done with its ring: reuse the space for the cross-warp reduction
 #pragma unroll
-  for (int i = 0; i < NQ; ++i)
+  for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = o[i][e];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      o[i][e] = v;
+    for (int e = 0; e < 4; ++e) {
+      const int dim = mt * 16 + g + (e >> 1) * 8, qi = 2 * t4 + (e & 1);
+      red[(warp * 64 + dim) * 8 + qi] = o[mt][e];
     }
-  if (g == 0) {
-#pragma unroll
-    for (int i = 0; i < NQ; ++i)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) red[(warp * NQ + i) * 64 + dl * 8 + e] = o[i][e];
-  }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < nq * 64; idx += 128) {
+  for (int idx = tid; idx < nq * 64; idx += 128) {
     const int i = idx >> 6, dim = idx & 63;
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) v += red[(w * NQ + i) * 64 + dim];
-    const float s = stat[1][i][0] + stat[1][i][1] + stat[1][i][2] + stat[1][i][3];
-    out[(static_cast<long long>(c) * nq + i) * ldo + h * 64 + dim] = __float2bfloat16_rn(v / s);
+    const float v = red[(0 * 64 + dim) * 8 + i] + red[(1 * 64 + dim) * 8 + i] + red[(2 * 64 + dim) * 8 + i] + red[(3 * 64 + dim) * 8 + i];
+    const float ssum = stat[1][i][0] + stat[1][i][1] + stat[1][i][2] + stat[1][i][3];
+    out[(static_cast<long long>(c) * nq + i) * ldo + h * 64 + dim] = __float2bfloat16_rn(v / ssum);
   }
 }
 
@@ -647,25 +703,6 @@ extern "C" int vacnic_decode_self_attn(const void* qkv, void* kcache, void* vcac
   return check_last("decode_self_attn");
 }
 
-template <int NQ>
-static int launch_cross(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int64_t kv_hs, int64_t kv_cs,
-                        const uint8_t* key_mask, const int32_t* key_len, void* out, int64_t ldo, int32_t captions, int32_t nq,
-                        int32_t L, int32_t H, float scale, cudaStream_t s) {
-  const size_t smem = (static_cast<size_t>(NQ) * L + 4 * NQ * 64) * sizeof(float);
-  auto kern = decode_cross_attn_kernel<NQ>;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(VACNIC_ECUDA, "decode_cross_attn: smem %zu: %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
-  kern<<<dim3(H, captions), 128, smem, s>>>(static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
-                                            static_cast<const __nv_bfloat16*>(v), ldkv, kv_hs, kv_cs, key_mask, key_len,
-                                            static_cast<__nv_bfloat16*>(out), ldo, nq, L, scale);
-  count_launch();
-  return check_last("decode_cross_attn");
-}
-
 extern "C" int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                                         int64_t kv_hs, int64_t kv_cs, const uint8_t* key_mask, const int32_t* key_len,
                                         void* out, int64_t ldo, int32_t captions, int32_t nq, int32_t L, int32_t H,
@@ -678,12 +715,23 @@ extern "C" int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* 
                  (reinterpret_cast<uintptr_t>(v) & 15) == 0, "decode_cross_attn: misaligned");
   const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define VB_CROSS(NQ) launch_cross<NQ>(q, ldq, k, v, ldkv, kv_hs, kv_cs, key_mask, key_len, out, ldo, captions, nq, L, H, scale, s)
-  if (nq == 1) return VB_CROSS(1);
-  if (nq == 2) return VB_CROSS(2);
-  if (nq <= 4) return VB_CROSS(4);
-  return VB_CROSS(8);
-#undef VB_CROSS
+  {
+    // tensor-core streaming kernel (mma.sync over cp.async-staged tiles)
+    const int Lp = (L + 63) / 64 * 64;
+    const size_t smem = 4 * static_cast<size_t>(kXWarpRing) + static_cast<size_t>(nq) * Lp * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {  // static (8.4 KB) + dynamic shared memory crosses the 48 KB opt-in line early: always opt in
+      cudaError_t e = cudaFuncSetAttribute(decode_cross_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return fail(VACNIC_ECUDA, "decode_cross_attn: smem %zu: %s", smem, cudaGetErrorString(e));
+      configured = smem;
+    }
+    VB_REQUIRE(smem <= 200 * 1024, "decode_cross_attn: nq * L too large for the shared-memory score buffer");
+    decode_cross_attn_mma_kernel<<<dim3(H, captions), 128, smem, s>>>(
+        static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), ldkv,
+        kv_hs, kv_cs, key_mask, key_len, static_cast<__nv_bfloat16*>(out), ldo, nq, L, scale);
+    count_launch();
+    return check_last("decode_cross_attn");
+  }
 }
 
 extern "C" int vacnic_mask_key_len(const uint8_t* mask, int32_t* key_len, int32_t B, int32_t L, void* stream) {
