@@ -255,7 +255,7 @@ def run_infer(args, rank, world, dev, pk):
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / n_rep
         ach = cross_bytes_launch / 1e9 / (k_ms / 1e3)
-        roof = {"bound": "hbm", "kernel": "decode_cross_attn_kernel<4> (beams of a caption over its shared encoder K/V)",
+        roof = {"bound": "hbm", "kernel": "decode_cross_attn_mma_kernel (beams of a caption over its shared encoder K/V; mma.sync + cp.async rings)",
                 "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 # dram__bytes_read + write of this kernel at this shape (64 captions), profiles/r1_ncu_decode_cross_attn.md
                 "traffic": 214.4e6 * C / 64 if (L == 1024 and not args.small) else None,
@@ -277,7 +277,8 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "train-vis"],
+                    help="train = BASELINE configs[1] (headline); infer = configs[2]; train-vis = configs[4] (only-visual-prompt model, CE only)")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--article-len", type=int, default=1024)
     ap.add_argument("--caption-len", type=int, default=64)
@@ -292,8 +293,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    metric = "train_samples_per_sec" if args.workload == "train" else "beam4_captions_per_sec"
-    unit = "samples/s" if args.workload == "train" else "captions/s"
+    vis = args.workload == "train-vis"
+    if vis:  # run_onlyvis_train.sh: GoodNews shapes, batch 32 per GPU, 512 article tokens, CE only, no guide
+        args.batch = 32 if args.batch == 16 else args.batch
+        args.article_len = 512 if args.article_len == 1024 else args.article_len
+        args.no_infer = True
+    metric = "beam4_captions_per_sec" if args.workload == "infer" else "train_samples_per_sec"
+    unit = "captions/s" if args.workload == "infer" else "samples/s"
     config = {"workload": "BART-large VACNIC full-model training step (BASELINE.json configs[1]): bf16 compute, "
                           f"batch {args.batch}/GPU, L={args.article_len} article tokens + P=20 ClipCap prefix, T={args.caption_len}, "
                           "CE + 0.5*CoLaM(margin 1.0, frozen BART-large guide) + SECLA(F=4,N=8), dropout 0.1, AdamW",
@@ -356,14 +362,18 @@ def main():
         return
 
     if args.small:
-        cfg = spec.bart_base()
+        cfg = spec.bart_base(only_image=vis)
         gcfg = spec.bart_base(stock=True)
     else:
-        cfg = spec.bart_large()
+        cfg = spec.bart_large(only_image=vis)
         gcfg = spec.VacnicConfig(stock=True)
     B, L, T = args.batch, args.article_len, args.caption_len
+    if vis:
+        config["workload"] = (f"BART-large only-visual-prompt VACNIC training step (BASELINE.json configs[4], MVIS / TRAINVIS): bf16, "
+                              f"batch {B}/GPU, L={L} article tokens + P=20 ClipCap prefix, T={T}, token CE only, dropout 0.1, AdamW")
+        config["global_batch"] = B * world
     model = VacnicBart(cfg, device=dev, p_drop=0.1, seed=684331)          # seed of run_full_train.sh:2
-    guide = VacnicBart(gcfg, device=dev, p_drop=0.0, seed=7, frozen=True)
+    guide = None if vis else VacnicBart(gcfg, device=dev, p_drop=0.0, seed=7, frozen=True)
     ts = TrainStep(model, guide, lr=3e-5, weight_decay=0.01, warmup_steps=100, total_steps=100000, margin=1.0, alpha=0.5,
                    use_graph=not args.no_graph, process_group=pg)
 
@@ -409,7 +419,7 @@ def main():
     value = B * world * args.steps / (ms_dev / 1e3)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
     pk = peaks()
-    flops_sample, fwd_f, guide_f = train_flops_per_sample(cfg, L, T)
+    flops_sample, fwd_f, guide_f = train_flops_per_sample(cfg, L, T, with_guide=not vis)
     step_tflops = flops_sample * B / 1e12
 
     # ---- roofline of the dominant kernel (gemm_sm100_kernel): one eager, event-instrumented step
@@ -438,7 +448,7 @@ def main():
         torch.distributed.barrier()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not vis:
         threads = os.cpu_count() or 1
         v, ms, sample = cpu_reference_train(threads, 1, 0)
         cpu = {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample}
