@@ -329,9 +329,24 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     pg = None
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: the JSON line must stand alone
     if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
-        pg = torch.distributed.group.WORLD
+        # NCCL / c10d print a version banner on stdout when the first communicator is created: route fd 1 to stderr until
+        # then, so that the JSON result line is the only thing this script writes to stdout
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.distributed.init_process_group("nccl", device_id=dev)
+            pg = torch.distributed.group.WORLD
+            warm = torch.zeros(1, device=dev)
+            torch.distributed.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from vacnic_b200 import kernels as K
     from vacnic_b200 import spec, synthetic
@@ -357,8 +372,7 @@ def main():
                 "e2e": {"value": r["e2e"], "unit": unit, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                         "ms_per_step": r["ms_e2e"] / args.steps},
                 "gpu_launches": n_launch, "roofline": r["roofline"], "cpu_baseline": cpu}))
-        if world > 1:
-            torch.distributed.destroy_process_group()
+        finish(world)
         return
 
     if args.small:
@@ -475,8 +489,19 @@ def main():
                         "last_txt_loss": last_loss},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "infer": infer}
         print(json.dumps(line))
+    finish(world)
+
+
+def finish(world):
+    """Multi-rank runs: leave together and skip interpreter teardown (destroying NCCL communicators while captured
+    graphs that contain collectives are being garbage-collected was observed to hang a 4-GPU run AFTER its result line)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":
