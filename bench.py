@@ -283,6 +283,7 @@ def main():
     ap.add_argument("--article-len", type=int, default=1024)
     ap.add_argument("--caption-len", type=int, default=64)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pipeline-opt", action="store_true", help="one fused AdamW launch after the gradient exchange instead of per-bucket updates")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="BART-base config-1 shapes (debug)")
     ap.add_argument("--captions", type=int, default=128, help="captions per GPU (infer workload)")
@@ -389,7 +390,7 @@ def main():
     model = VacnicBart(cfg, device=dev, p_drop=0.1, seed=684331)          # seed of run_full_train.sh:2
     guide = None if vis else VacnicBart(gcfg, device=dev, p_drop=0.0, seed=7, frozen=True)
     ts = TrainStep(model, guide, lr=3e-5, weight_decay=0.01, warmup_steps=100, total_steps=100000, margin=1.0, alpha=0.5,
-                   use_graph=not args.no_graph, process_group=pg)
+                   use_graph=not args.no_graph, process_group=pg, pipeline_optimizer=False if args.no_pipeline_opt else None)
 
     n_batches = 4
     host = [TrainStep.prepare(synthetic.make_batch(B=B, L=L, T=T, seed=1000 * rank + i), cfg) for i in range(n_batches)]

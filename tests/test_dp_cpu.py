@@ -46,7 +46,9 @@ def _worker(rank, world, port, tmp):
         grad = torch.randn(total, generator=g)
         mine = grad.clone()
         prefixes = dp.vacnic_bucket_prefixes(cfg.enc_layers, cfg.dec_layers, group_size=2)
-        b = dp.GradBuckets(grad, spans, prefixes)
+        b = dp.GradBuckets(grad, spans, prefixes, group=dist.group.WORLD)
+        solo = dp.GradBuckets(grad.clone(), spans, prefixes)  # no group: never communicates
+        assert solo.world == 1
         assert b.world == world and len(b.buckets) == 1 + 3
         # the decoder bucket owns the hoisted cross k/v block at the front of the buffer as well as the decoder layers
         assert b.buckets[0][0][0] == 0

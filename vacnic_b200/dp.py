@@ -50,7 +50,9 @@ class GradBuckets:
     def __init__(self, grad: torch.Tensor, spans: Dict[str, Tuple[int, int]], bucket_prefixes: Sequence[Sequence[str]],
                  group=None, max_gap: int = 63):
         self.grad, self.group = grad, group
-        self.world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
+        # only an EXPLICIT group communicates: a step object without one never issues a collective, even inside a
+        # multi-rank job (e.g. a rank-local profiling pass)
+        self.world = dist.get_world_size(group) if group is not None else 1
         self.buckets: List[List[Tuple[int, int]]] = []
         claimed: List[Tuple[int, int]] = []
         for prefixes in bucket_prefixes:
@@ -86,18 +88,23 @@ class GradBuckets:
         self.done = [False] * len(self.buckets)
         self.bytes_reduced = 0
 
-    def reduce_bucket(self, i: int):
+    def reduce_bucket(self, i: int) -> List[Tuple[int, int]]:
+        """All-reduce bucket i in place; returns its address ranges (the optimizer may update them right away)."""
         if self.done[i]:
             raise RuntimeError(f"gradient bucket {i} reduced twice in one step")
         self.done[i] = True
         self._reduce(self.buckets[i])
+        return self.buckets[i]
 
-    def finish(self):
-        """Reduce whatever has not been reduced yet (buckets whose hook never fired + the unclaimed remainder)."""
+    def finish(self) -> List[Tuple[int, int]]:
+        """Reduce whatever has not been reduced yet (buckets whose hook never fired + the unclaimed remainder);
+        returns those ranges."""
+        out: List[Tuple[int, int]] = []
         for i, d in enumerate(self.done):
             if not d:
-                self.reduce_bucket(i)
+                out += self.reduce_bucket(i)
         self._reduce(self.rest)
+        return out + list(self.rest)
 
 
 def vacnic_bucket_prefixes(enc_layers: int, dec_layers: int, group_size: int = 3) -> List[List[str]]:

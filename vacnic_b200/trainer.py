@@ -31,7 +31,7 @@ class TrainStep:
     def __init__(self, model: VacnicBart, guide: Optional[VacnicBart], lr: float = 3e-5, weight_decay: float = 0.01,
                  betas=(0.9, 0.999), eps: float = 1e-8, warmup_steps: int = 0, total_steps: int = 1_000_000,
                  margin: float = 1.0, alpha: float = 0.5, secla_weight: float = 1.0, use_graph: bool = True,
-                 process_group=None):
+                 process_group=None, pipeline_optimizer: Optional[bool] = None):
         self.model, self.guide = model, guide
         self.cfg = model.cfg
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
@@ -52,12 +52,19 @@ class TrainStep:
         self.losses: Dict[str, torch.Tensor] = {}
         self.launches_per_step = 0
         self.buckets: Optional[GradBuckets] = None
-        if self.world > 1 or (process_group is not None and os.environ.get("VACNIC_DP_FORCE")):
-            # data-parallel exchange: bucketed in-place all-reduce of the flat gradient buffer on a side stream,
-            # started from markers in the backward pass (vacnic_b200.dp, blocks.GradMarkFn)
+        if pipeline_optimizer is None:
+            # measured on B200: per-bucket updates behind the backward pass gain 0.6 % at 2 GPUs (the fused update no
+            # longer waits for the last all-reduce) and lose 1 % on one GPU (HBM contention with the backward GEMMs)
+            pipeline_optimizer = self.world > 1
+        if pipeline_optimizer or self.world > 1:
+            # Address-range buckets of the flat gradient buffer, completed from markers in the backward pass
+            # (vacnic_b200.dp, blocks.GradMarkFn).  On a side stream each bucket is all-reduced in place (world > 1) and
+            # then UPDATED by the fused AdamW kernel right away, while the backward pass of the earlier layers is still
+            # running: a finished layer's weights are not read again in this step.
             spans = {n: (st.offsets[n], p.numel()) for n, p in st.params.items()}
             prefixes = vacnic_bucket_prefixes(self.cfg.enc_layers, self.cfg.dec_layers, group_size=3)
-            self.buckets = GradBuckets(st.grad, spans, prefixes, group=process_group)
+            self.buckets = GradBuckets(st.grad, spans, prefixes, group=process_group if self.world > 1 or
+                                       os.environ.get("VACNIC_DP_FORCE") else None)
             self.comm_stream = torch.cuda.Stream(device=dev)
             self._tag_to_bucket = {("dec", 0): 0}
             hi, k = self.cfg.enc_layers, 1
@@ -123,13 +130,20 @@ class TrainStep:
                 if not self.buckets.done[i]:
                     self.comm_stream.wait_event(ev)
                     with torch.cuda.stream(self.comm_stream):
-                        self.buckets.reduce_bucket(i)
+                        self._adamw_ranges(self.buckets.reduce_bucket(i))
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
-                self.buckets.finish()  # embeddings / prefix modules + any bucket whose marker did not fire
+                # embeddings / prefix modules + any bucket whose marker did not fire
+                self._adamw_ranges(self.buckets.finish())
             torch.cuda.current_stream().wait_stream(self.comm_stream)
-        K.adamw(st.master, st.grad, self.m, self.v, st.shadow, self.hyper)
+        else:
+            K.adamw(st.master, st.grad, self.m, self.v, st.shadow, self.hyper)
         return losses
+
+    def _adamw_ranges(self, ranges):
+        st = self.model.store
+        for a, b in ranges:
+            K.adamw(st.master[a:b], st.grad[a:b], self.m[a:b], self.v[a:b], st.shadow[a:b], self.hyper)
 
     # ------------------------------------------------------------------ host side
     @staticmethod
