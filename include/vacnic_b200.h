@@ -164,6 +164,9 @@ int vacnic_colsum(const void* x, float* out, int64_t rows, int32_t n, int64_t ld
 int vacnic_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int vacnic_concat_rows(const void* a, const void* b, void* out, int32_t B, int64_t rows_a, int64_t rows_b, int32_t d,
                        void* stream); /* out[B, ra+rb, d] = cat(a[B,ra,d], b[B,rb,d]) : MFULL:668, 691 */
+/* dst[r, 0..ld_dst) = bf16({src[r, 0..n), 0 ...}), src rows ld_src floats apart: fp32 gradients coming back from torch
+ * ops (script-level losses, TRAIN:287) -> TMA-readable bf16 operands. */
+int vacnic_cast_rows_f32_bf16(const float* src, void* dst, int64_t rows, int32_t n, int64_t ld_src, int32_t ld_dst, void* stream);
 /* dst[r, 0..ld_dst) = {src[r, 0..n), 0 ...} (bf16): re-pitch rows for TMA (16-byte row pitch). */
 int vacnic_pad_rows(const void* src, void* dst, int64_t rows, int32_t n, int32_t ld_dst, void* stream);
 /* dst[j] (+)= sum_p src[p*len + j] (fp32): reduces split partial weight gradients. */

@@ -24,6 +24,7 @@ SIGNATURES = {
     "vacnic_concat_rows": [P, P, P, I32, I64, I64, I32, P],
     "vacnic_add_bf16": [P, P, P, P, I64, P],
     "vacnic_pad_rows": [P, P, I64, I32, I32, P],
+    "vacnic_cast_rows_f32_bf16": [P, P, I64, I32, I64, I32, P],
     "vacnic_sum_partials": [P, P, I32, I64, I32, P],
     "vacnic_adamw": [P, P, P, P, P, I64, P, P],
     "vacnic_rng_advance": [P, P],

@@ -251,11 +251,10 @@ class LinearFn(torch.autograd.Function):
         else:
             dy2 = dy.reshape(x2.shape[0], -1)
             if dy2.dtype != torch.bfloat16:
-                d16 = torch.empty(dy2.shape, dtype=torch.bfloat16, device=dy2.device)
-                K.cast_bf16(dy2.contiguous(), d16)
-                dy2 = d16
-            elif dy2.stride(-1) != 1:
-                dy2 = dy2.contiguous()
+                # e.g. the fp32 gradient of a script-level torch loss on the logits (TRAIN:287): bf16, TMA-friendly pitch
+                dy2 = K.cast_rows_bf16(dy2.float() if dy2.dtype != torch.float32 else (dy2 if dy2.stride(-1) == 1 else dy2.contiguous()))
+            elif dy2.stride(-1) != 1 or (dy2.stride(0) * 2) % 16 != 0:
+                dy2 = K.pad_rows(dy2.contiguous(), (dy2.shape[1] + 7) // 8 * 8)[:, :dy2.shape[1]]
         _wgrad(rt, lin, dy2, x2, bias_from=dy2 if lin.gb is not None else None)
         dx = K.gemm(dy2, lin.w16, b_mn=True).view(ctx.shp) if (ctx.need_dx and ctx.needs_input_grad[0]) else None
         return (dx,) + (None,) * 7

@@ -156,6 +156,19 @@ pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict
   dst[i] = c < n ? src[r * n + c] : __float2bfloat16_rn(0.f);
 }
 
+
+// dst[r, c] = bf16(src[r, c]) for c < n, rows re-pitched from ld_src to ld_dst (pad columns zero): gradients handed back
+// by torch ops (e.g. the script-level CrossEntropyLoss on [rows, 50267] logits) become TMA-readable GEMM operands
+__global__ void __launch_bounds__(256)
+cast_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int n, long long ld_src,
+                 int ld_dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= rows * ld_dst) return;
+  const long long r = i / ld_dst;
+  const int c = static_cast<int>(i % ld_dst);
+  dst[i] = __float2bfloat16_rn(c < n ? src[r * ld_src + c] : 0.f);
+}
+
 // dst[j] (+)= sum_p src[p, j]: reduction of split-K partial weight gradients (fp32)
 __global__ void __launch_bounds__(256)
 sum_partials_kernel(const float* __restrict__ src, float* __restrict__ dst, int parts, long long len, int accumulate) {
@@ -263,4 +276,14 @@ extern "C" int vacnic_sum_partials(const float* src, float* dst, int32_t parts, 
                                                                                                           accumulate);
   count_launch();
   return check_last("sum_partials");
+}
+
+extern "C" int vacnic_cast_rows_f32_bf16(const float* src, void* dst, int64_t rows, int32_t n, int64_t ld_src, int32_t ld_dst,
+                                         void* stream) {
+  VB_REQUIRE(src && dst && rows > 0 && n > 0 && ld_src >= n && ld_dst >= n, "cast_rows: bad arguments");
+  const long long total = rows * ld_dst;
+  cast_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), rows, n, ld_src, ld_dst);
+  count_launch();
+  return check_last("cast_rows");
 }

@@ -265,6 +265,18 @@ def pad_rows(src2d, ld_dst):
     return dst
 
 
+def cast_rows_bf16(src2d):
+    """fp32 [rows, n] (row stride arbitrary, innermost 1) -> bf16 [rows, n] view of a buffer with a 16-byte row pitch."""
+    rows, n = src2d.shape
+    if src2d.dtype != torch.float32 or src2d.stride(1) != 1:
+        raise ValueError("cast_rows_bf16: fp32 rows with innermost stride 1 expected")
+    ld = (n + 7) // 8 * 8
+    dst = torch.empty(rows, ld, dtype=torch.bfloat16, device=src2d.device)
+    check(lib().vacnic_cast_rows_f32_bf16(ptr(src2d), ptr(dst), rows, n, src2d.stride(0), ld, stream_ptr()),
+          "vacnic_cast_rows_f32_bf16")
+    return dst[:, :n]
+
+
 def sum_partials(parts2d, dst, accumulate):
     """dst (+)= parts2d.sum(0); fp32."""
     check(lib().vacnic_sum_partials(ptr(parts2d), ptr(dst), parts2d.shape[0], dst.numel(), int(accumulate), stream_ptr()),

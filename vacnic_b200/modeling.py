@@ -410,6 +410,7 @@ class VacnicBart(nn.Module):
     def train(self, mode: bool = True):
         super().train(mode)
         self.rt.training = mode
+        self.store._shadow_version = -1  # `.data` edits (TRAIN:758) do not bump version counters: re-cast on the next forward
         return self
 
     def get_encoder(self):
@@ -438,6 +439,11 @@ class VacnicBart(nn.Module):
             raise NotImplementedError("attention maps are not materialised by the fused path")
         if self.store.dirty_shadow:
             self.store.refresh_shadow()
+        if torch.is_grad_enabled() and self.training and not self.store.frozen and not self.store.external_step:
+            # the unchanged reference loop (forward, loss.backward(), optimizer.step(), zero_grad; TRAIN:281-374): every
+            # training forward starts a fresh gradient step in the flat buffer (p.grad views are re-attached after
+            # zero_grad(set_to_none=True)); gradient accumulation over several forwards needs vacnic_b200.trainer
+            self.store.begin_step()
         if labels is not None and decoder_input_ids is None:
             decoder_input_ids = shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
         if decoder_input_ids is None:

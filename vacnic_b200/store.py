@@ -83,7 +83,8 @@ class ParamStore:
                     m._parameters[k] = remap[id(p)]
         self._touched = set()
         self._lin_span: Dict[str, tuple] = {}
-        self.dirty_shadow = True
+        self._shadow_version = -1  # version counter of `master` when the bf16 shadow was last refreshed
+        self.external_step = False  # True while a TrainStep drives begin_step / finish_backward itself
         # requires-grad anchor so that autograd records the first block of a forward pass
         self.anchor = torch.zeros(1, device=self.device, requires_grad=not frozen)
 
@@ -154,9 +155,16 @@ class ParamStore:
         self._touched.add(key)
         return seen
 
+    @property
+    def dirty_shadow(self) -> bool:
+        """True when the fp32 master changed through torch (optimizer.step(), load_state_dict, p.data edits made through
+        the parameter views all bump the shared version counter) since the bf16 compute shadow was refreshed.  The fused
+        AdamW kernel writes both copies itself and does not count."""
+        return self.master._version != self._shadow_version
+
     def refresh_shadow(self):
         K.cast_bf16(self.master, self.shadow)
-        self.dirty_shadow = False
+        self._shadow_version = self.master._version
 
     def load_state_dict_flat(self, sd: Dict[str, torch.Tensor], strict: bool = True):
         missing = []

@@ -92,6 +92,7 @@ class TrainStep:
     def _body(self, b: Dict[str, torch.Tensor]):
         model, guide, cfg = self.model, self.guide, self.cfg
         st = model.store
+        st.external_step = True
         st.begin_step()
         # the backward-pass markers call into THIS step object (another TrainStep may share the model)
         model.rt.grad_hook = self._on_grad_ready if self.buckets is not None else None
