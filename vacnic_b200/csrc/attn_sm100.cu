@@ -4,15 +4,17 @@
 // cross-thread reductions), probabilities go to 128B-swizzled shared memory as bf16 and feed the second
 // tcgen05.mma (O += P V) whose accumulator also lives in TMEM.
 //
-// Exact (non-online) softmax in two sweeps over the key blocks: sweep 1 computes the row maxima (QK^T is
-// recomputed in sweep 2: K = 64, the tensor pipe has the headroom), sweep 2 computes exp(s - max), the row
-// sums and O.  No rescaling of O is ever needed.  Masks follow the reference: masked keys get
+// One sweep over the key blocks with a LAZILY updated reference maximum: the first block fixes m_ref = its row maximum;
+// a later block only raises m_ref (and rescales the running sum and the O accumulator in TMEM, tcgen05.ld/st) when its
+// maximum exceeds m_ref by more than 2^8 — rare after the first blocks — otherwise p = 2^(s - m_ref) <= 256 is simply
+// carried in bf16 / fp32.  The result is the exact softmax (any reference point cancels in O / l).  Masks follow the
+// reference: masked keys get
 // finfo(float32).min (a fully masked row degenerates to a uniform row exactly like the reference),
 // keys beyond `key_len[b]` are skipped because they contribute exactly 0.
 //
 // CTA = 128 query rows of one (batch, head); 320 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM
 // allocator, warps 2..9 softmax/epilogue (thread = one query row x one half of the key block's columns; the
-// two halves of a row meet only once per sweep, through shared memory).  96 KB of shared memory and 256
+// two halves of a row exchange their block maxima through shared memory).  96 KB of shared memory and 256
 // TMEM columns per CTA, so two CTAs share an SM and overlap each other's MMA and exp phases.
 #include <cuda.h>
 #include <float.h>
@@ -47,7 +49,7 @@ struct AttnSmem {
   uint64_t q_full, ring_full[kRing], ring_empty[kRing], s_full, s_empty, p_full, p_empty, o_full;
   uint32_t tmem_slot;
   uint8_t blk_flag[kMaxKB];  // per key block: 0 = no masking needed, 1 = per-key checks needed
-  float xch[2][128];         // row max / row sum exchange between the two column halves
+  float xch[2][2][128];      // [block parity][column half][row]: block maxima / final row sums exchanged between halves
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -135,9 +137,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_4d(sRing + slot * kTile, tm, &sh->ring_full[slot], 0, row0, h, b);
         if (++slot == kRing) { slot = 0; phase ^= 1u; }
       };
-      for (int j = 0; j < nkb; ++j) push(&tmK, j * kAK);  // sweep 1: keys only
-      for (int j = 0; j < nkb; ++j) {                     // sweep 2: keys and values in consumption order
-        push(&tmK, j * kAK);
+      // consumption order of the MMA thread, which runs QK^T one block ahead of PV: K0, K1, V0, K2, V1, ...
+      push(&tmK, 0);
+      for (int j = 0; j < nkb; ++j) {
+        if (j + 1 < nkb) push(&tmK, (j + 1) * kAK);
         push(&tmV, j * kAK);
       }
     }
@@ -152,34 +155,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&sh->q_full, 0);
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
-      for (int sweep = 0; sweep < 2; ++sweep) {
-        for (int j = 0; j < nkb; ++j, ++it) {
-          mbar_wait(&sh->ring_full[slot], phase);
-          mbar_wait(&sh->s_empty, (it & 1u) ^ 1u);
-          tc_fence_after();
-          const uint32_t k_addr = smem_u32(sRing + slot * kTile);
+      auto issue_s = [&]() {  // S = Q K^T for the next key block (waits for its K tile and for S to be drained)
+        mbar_wait(&sh->ring_full[slot], phase);
+        mbar_wait(&sh->s_empty, (it & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sRing + slot * kTile);
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k)
-            umma_bf16_ss(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(&sh->ring_empty[slot]);
-          umma_commit(&sh->s_full);
-          if (++slot == kRing) { slot = 0; phase ^= 1u; }
-          if (sweep == 1) {
-            mbar_wait(&sh->ring_full[slot], phase);
-            mbar_wait(&sh->p_full, j & 1u);
-            tc_fence_after();
-            const uint32_t v_addr = smem_u32(sRing + slot * kTile);
+        for (int k = 0; k < kHD / 16; ++k)
+          umma_bf16_ss(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&sh->ring_empty[slot]);
+        umma_commit(&sh->s_full);
+        if (++slot == kRing) { slot = 0; phase ^= 1u; }
+        ++it;
+      };
+      issue_s();
+      for (int j = 0; j < nkb; ++j) {
+        // QK^T of block j+1 is issued as soon as the softmax warps have pulled S_j out of TMEM, i.e. it runs while they
+        // compute the exponentials of block j
+        if (j + 1 < nkb) issue_s();
+        mbar_wait(&sh->ring_full[slot], phase);
+        mbar_wait(&sh->p_full, j & 1u);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sRing + slot * kTile);
 #pragma unroll
-            for (int kk = 0; kk < kAK / 16; ++kk)
-              umma_bf16_ss(tmem_o, make_smem_desc_sw128(p_addr + (kk >> 2) * kTile + (kk & 3) * 32, 16, 1024),
-                           make_smem_desc_sw128(v_addr + kk * 2048, kAK * 128, 1024), idesc_o,
-                           (j | kk) != 0 ? 1u : 0u);
-            umma_commit(&sh->ring_empty[slot]);
-            umma_commit(&sh->p_empty);
-            if (++slot == kRing) { slot = 0; phase ^= 1u; }
-          }
-        }
+        for (int kk = 0; kk < kAK / 16; ++kk)
+          umma_bf16_ss(tmem_o, make_smem_desc_sw128(p_addr + (kk >> 2) * kTile + (kk & 3) * 32, 16, 1024),
+                       make_smem_desc_sw128(v_addr + kk * 2048, kAK * 128, 1024), idesc_o, (j | kk) != 0 ? 1u : 0u);
+        umma_commit(&sh->ring_empty[slot]);
+        umma_commit(&sh->p_empty);
+        if (++slot == kRing) { slot = 0; phase ^= 1u; }
       }
       umma_commit(&sh->o_full);
     }
@@ -199,76 +204,94 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) return -FLT_MAX;
       return s * c2;
     };
-    // ---- sweep 1: row maximum (over this thread's column half; the halves are merged after the sweep)
-    float m = -INFINITY;
-    for (int j = 0; j < nkb; ++j, ++it) {
-      mbar_wait(&sh->s_full, it & 1u);
-      tc_fence_after();
-      const bool need = sh->blk_flag[j] != 0;
-      uint32_t x0[32], x1[32];
-      tmem_ld_32x32(t_s, x0);
-      tmem_ld_32x32(t_s + 32, x1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&sh->s_empty);
-      if (!need) {
-        float mm = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) mm = fmaxf(mm, fmaxf(__uint_as_float(x0[c]), __uint_as_float(x1[c])));
-        m = fmaxf(m, mm * c2);  // c2 > 0: max commutes with the scaling
-      } else {
-        const int kb = j * kAK + half * 64;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          m = fmaxf(m, masked(__uint_as_float(x0[c]), kb + c));
-          m = fmaxf(m, masked(__uint_as_float(x1[c]), kb + 32 + c));
-        }
-      }
-    }
-    sh->xch[half][r] = m;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    m = fmaxf(m, sh->xch[half ^ 1][r]);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    // ---- sweep 2: p = 2^(t - m), row sum, P -> shared memory (bf16, SWIZZLE_128B K-major; half == atom)
+    // ---- single sweep: block maximum -> (rare) rescale -> p = 2^(t - m_ref), row sum, P -> shared memory
+    float m = -INFINITY;  // m_ref
     float l = 0.f;
     const uint32_t atom = smem_u32(sP) + half * kTile + r * 128;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
+    const uint32_t t_o = tmem_o + (static_cast<uint32_t>(quad * 32) << 16) + half * 32;  // this thread's 32 O columns
     for (int j = 0; j < nkb; ++j, ++it) {
       mbar_wait(&sh->s_full, it & 1u);
       tc_fence_after();
       const bool need = sh->blk_flag[j] != 0;
       const int kb = j * kAK + half * 64;
-#pragma unroll 1
-      for (int part = 0; part < 2; ++part) {
-        uint32_t x[32];
-        tmem_ld_32x32(t_s + part * 32, x);
-        tmem_ld_wait();
-        if (part == 1) {  // all of S_j is in registers: the tensor pipe may overwrite it
-          tc_fence_before();
-          mbar_arrive(&sh->s_empty);
-        }
-        if (part == 0 && j > 0) mbar_wait(&sh->p_empty, (j - 1) & 1u);  // PV_{j-1} has consumed the P buffer
+      uint32_t x0[32], x1[32];
+      tmem_ld_32x32(t_s, x0);
+      tmem_ld_32x32(t_s + 32, x1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sh->s_empty);  // all of S_j is in registers: the tensor pipe may overwrite it
+      // scores in the log2 domain (masked), block maximum of this half
+      float bm = -INFINITY;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {  // 4 chunks of 8 keys (16 B)
-          float p[8];
+      for (int c = 0; c < 32; ++c) {
+        float t0 = __uint_as_float(x0[c]), t1 = __uint_as_float(x1[c]);
+        if (need) { t0 = masked(t0, kb + c); t1 = masked(t1, kb + 32 + c); }
+        else { t0 *= c2; t1 *= c2; }
+        x0[c] = __float_as_uint(t0);
+        x1[c] = __float_as_uint(t1);
+        bm = fmaxf(bm, fmaxf(t0, t1));
+      }
+      sh->xch[j & 1][half][r] = bm;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      bm = fmaxf(bm, sh->xch[j & 1][half ^ 1][r]);
+      // reference maximum: fixed by block 0, raised later only where a row's block maximum exceeds it by more than 2^8
+      // (both halves of a row see the same maxima, so they agree)
+      float f = 1.0f;
+      bool mine = false;
+      if (j == 0) {
+        m = bm;
+      } else if (bm > m + 8.0f) {
+        mine = true;
+        f = ex2f(m - bm);
+        m = bm;
+        l *= f;
+      }
+      // exponentials in place (registers), before waiting for PV_{j-1}
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = q * 8 + e;
-            const float sv = __uint_as_float(x[c]);
-            const float t = need ? masked(sv, kb + part * 32 + c) : sv * c2;
-            p[e] = ex2f(t - m);
-            l += p[e];
-          }
-          st_shared_v4(atom + ((static_cast<uint32_t>(part * 4 + q) ^ sw) << 4), pack_bf16x2(p[0], p[1]),
-                       pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+      for (int c = 0; c < 32; ++c) {
+        const float p0 = ex2f(__uint_as_float(x0[c]) - m), p1 = ex2f(__uint_as_float(x1[c]) - m);
+        l += p0 + p1;
+        x0[c] = __float_as_uint(p0);
+        x1[c] = __float_as_uint(p1);
+      }
+      if (j > 0) {
+        mbar_wait(&sh->p_empty, (j - 1) & 1u);  // PV_{j-1} retired: P buffer free, O quiescent
+        tc_fence_after();
+        // tcgen05.ld/st are warp-collective: the whole warp rescales its O slices if any lane raised its maximum
+        // (the other lanes multiply by exactly 1)
+        if (__any_sync(0xffffffffu, mine)) {
+          uint32_t o[32];
+          tmem_ld_32x32(t_o, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+          tmem_st_32x32(t_o, o);
+          tmem_st_wait();
         }
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        st_shared_v4(atom + ((static_cast<uint32_t>(q) ^ sw) << 4),
+                     pack_bf16x2(__uint_as_float(x0[8 * q]), __uint_as_float(x0[8 * q + 1])),
+                     pack_bf16x2(__uint_as_float(x0[8 * q + 2]), __uint_as_float(x0[8 * q + 3])),
+                     pack_bf16x2(__uint_as_float(x0[8 * q + 4]), __uint_as_float(x0[8 * q + 5])),
+                     pack_bf16x2(__uint_as_float(x0[8 * q + 6]), __uint_as_float(x0[8 * q + 7])));
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        st_shared_v4(atom + ((static_cast<uint32_t>(4 + q) ^ sw) << 4),
+                     pack_bf16x2(__uint_as_float(x1[8 * q]), __uint_as_float(x1[8 * q + 1])),
+                     pack_bf16x2(__uint_as_float(x1[8 * q + 2]), __uint_as_float(x1[8 * q + 3])),
+                     pack_bf16x2(__uint_as_float(x1[8 * q + 4]), __uint_as_float(x1[8 * q + 5])),
+                     pack_bf16x2(__uint_as_float(x1[8 * q + 6]), __uint_as_float(x1[8 * q + 7])));
+      tc_fence_before();
       fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor pipe (async proxy)
       mbar_arrive(&sh->p_full);
     }
-    sh->xch[half][r] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    l += sh->xch[half ^ 1][r];
+    sh->xch[0][half][r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += sh->xch[0][half ^ 1][r];
     // ---- epilogue: O / l -> bf16 (each half stores 32 of the 64 head-dim columns)
     mbar_wait(&sh->o_full, 0);
     tc_fence_after();
@@ -329,7 +352,7 @@ struct AttnBwdArgs {
 struct BwdSmem {
   uint64_t in_full, st_full[2], st_empty[2], sdp_full, s_empty, ds_full, ds_empty, acc_full;
   uint32_t tmem_slot;
-  float4 stat[2][64];    // dkv kernel: per query of the block {max, 1/sum, delta, -}
+  float4 stat[2][64];    // dkv kernel: per query of the block {max, 1/sum, delta, scale/sum}
   uint8_t blk_flag[2 * kMaxKB];  // dq kernel: per 64-key block, 1 = per-key mask checks needed
 };
 
@@ -442,7 +465,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t idesc_q = make_idesc_bf16(kAQ, kHD, 0, 1);
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
       mbar_wait(&sh->in_full, 0);
-      for (int j = 0; j < nkb; ++j) {
+      auto issue_sdp = [&](int j) {  // S = Q K_j^T and dP = dO V_j^T (waits for the tiles and for S / dP to be drained)
         const int st = j & 1;
         mbar_wait(&sh->st_full[st], (j >> 1) & 1u);
         mbar_wait(&sh->s_empty, (j & 1u) ^ 1u);
@@ -457,6 +480,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_bf16_ss(tmem_base + 64, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
                        make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&sh->sdp_full);
+      };
+      issue_sdp(0);
+      for (int j = 0; j < nkb; ++j) {
+        const int st = j & 1;
+        if (j + 1 < nkb) issue_sdp(j + 1);  // runs while the elementwise warps turn block j into dS
+        const uint32_t k_addr = smem_u32(sKV + st * kTile);
         mbar_wait(&sh->ds_full, j & 1u);
         tc_fence_after();
 #pragma unroll
@@ -527,24 +556,29 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&sh->s_empty);
-      if (j > 0) mbar_wait(&sh->ds_empty, (j - 1) & 1u);
+      uint32_t dsp[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float ds[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int c = q * 8 + e;
-          float t = __uint_as_float(xs[c]) * c2;
+          float t = fmaf(__uint_as_float(xs[c]), c2, -m);  // log2-domain score minus the row maximum
           if (need) {
             const int key = kb0 + c;
             if (key >= a.Sk) t = -INFINITY;
-            else if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) t = -FLT_MAX;
+            else if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) t = -FLT_MAX - m;
           }
-          ds[e] = ex2f(t - m) * (__uint_as_float(xp[c]) - delta) * coef;
+          ds[e] = ex2f(t) * (__uint_as_float(xp[c]) - delta) * coef;
         }
-        st_shared_v4(ds_row + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4), pack_bf16x2(ds[0], ds[1]),
-                     pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dsp[q * 4 + e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
       }
+      if (j > 0) mbar_wait(&sh->ds_empty, (j - 1) & 1u);  // dQ MMA of block j-1 has consumed the dS buffer
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        st_shared_v4(ds_row + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4), dsp[q * 4], dsp[q * 4 + 1], dsp[q * 4 + 2],
+                     dsp[q * 4 + 3]);
       fence_proxy_async_smem();
       mbar_arrive(&sh->ds_full);
     }
@@ -621,21 +655,28 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       constexpr uint32_t idesc_g = make_idesc_bf16(kAK, kHD, 0, 1);
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
       mbar_wait(&sh->in_full, 0);
-      for (int i = i0, n = 0; i < nqb; ++i, ++n) {
+      auto issue_sdp = [&](int n) {  // S^T = K Q_i^T and dP^T = V dO_i^T for step n
         const int st = n & 1;
         mbar_wait(&sh->st_full[st], (n >> 1) & 1u);
         mbar_wait(&sh->s_empty, (n & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t q_addr = smem_u32(sQD + st * kTile), do_addr = q_addr + kHalfTile;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // S^T = K Q_i^T
+        for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tmem_base, make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
                        make_smem_desc_sw128(q_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // dP^T = V dO_i^T
+        for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tmem_base + 64, make_smem_desc_sw128(v_addr + k * 32, 16, 1024),
                        make_smem_desc_sw128(do_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&sh->sdp_full);
+      };
+      const int nsteps = nqb - i0;
+      if (nsteps > 0) issue_sdp(0);
+      for (int n = 0; n < nsteps; ++n) {
+        const int st = n & 1;
+        if (n + 1 < nsteps) issue_sdp(n + 1);  // runs while the elementwise warps turn step n into P^T / dS^T
+        const uint32_t q_addr = smem_u32(sQD + st * kTile), do_addr = q_addr + kHalfTile;
         mbar_wait(&sh->ds_full, n & 1u);
         tc_fence_after();
 #pragma unroll
@@ -673,7 +714,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float4 st = make_float4(0.f, 0.f, 0.f, 0.f);  // query rows beyond Sq: 1/sum = 0 -> p = 0
         if (qrow < a.Sq) {
           const float2 s2 = reinterpret_cast<const float2*>(a.stats)[sbase + qrow];
-          st = make_float4(s2.x, s2.y, a.delta[sbase + qrow], 0.f);
+          st = make_float4(s2.x, s2.y, a.delta[sbase + qrow], s2.y * a.scale);
         }
         stq[tid] = st;
       }
@@ -687,7 +728,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&sh->s_empty);
-      if (n > 0) mbar_wait(&sh->ds_empty, (n - 1) & 1u);
+      uint32_t ppk[16], dsk[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float pp[8], ds[8];
@@ -702,11 +743,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           pp[e] = p;
           ds[e] = p * (__uint_as_float(xp[c]) - st.z) * a.scale;
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ppk[q * 4 + e] = pack_bf16x2(pp[2 * e], pp[2 * e + 1]);
+          dsk[q * 4 + e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
+        }
+      }
+      if (n > 0) mbar_wait(&sh->ds_empty, (n - 1) & 1u);  // the dV / dK MMAs of step n-1 have consumed both buffers
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
         const uint32_t off = (static_cast<uint32_t>(half * 4 + q) ^ sw) << 4;
-        st_shared_v4(pt_row + off, pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]), pack_bf16x2(pp[4], pp[5]),
-                     pack_bf16x2(pp[6], pp[7]));
-        st_shared_v4(dst_row + off, pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
-                     pack_bf16x2(ds[6], ds[7]));
+        st_shared_v4(pt_row + off, ppk[q * 4], ppk[q * 4 + 1], ppk[q * 4 + 2], ppk[q * 4 + 3]);
+        st_shared_v4(dst_row + off, dsk[q * 4], dsk[q * 4 + 1], dsk[q * 4 + 2], dsk[q * 4 + 3]);
       }
       fence_proxy_async_smem();
       mbar_arrive(&sh->ds_full);
