@@ -157,6 +157,22 @@ colam_bwd_kernel(const float* __restrict__ pooled_a, const float* __restrict__ p
 // names fp32 [B, N, d] (no grad), face bf16 [B, F, d].  One block.  Workspace (fp32):
 //   M  [B*N, B*F] similarity, dM [B*N, B*F] its gradient.
 // loss[0] = CE_rows(A) + CE_rows(C), A[i,j] = mean_n max_f M[(i,n),(j,f)], C[i,j] = mean_f max_n M[(j,n),(i,f)].
+// M[(b,n), (b',f)] = names[b,n,:] . face[b',f,:]   — one warp per entry, spread over the whole GPU
+__global__ void __launch_bounds__(256)
+secla_sim_kernel(const float* __restrict__ names, const __nv_bfloat16* __restrict__ face, float* __restrict__ Mw,
+                 float* __restrict__ dM, int BN, int BF, int d) {
+  const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= BN * BF) return;
+  const int r = e / BF, c = e % BF;
+  const float* np = names + static_cast<long long>(r) * d;
+  const __nv_bfloat16* fp = face + static_cast<long long>(c) * d;
+  float s = 0.f;
+  for (int k = lane; k < d; k += 32) s += np[k] * __bfloat162float(fp[k]);
+  s = warp_sum(s);
+  if (lane == 0) { Mw[e] = s; dM[e] = 0.f; }
+}
+
 __global__ void __launch_bounds__(1024)
 secla_fwd_kernel(const float* __restrict__ names, const __nv_bfloat16* __restrict__ face, float* __restrict__ Mw,
                  float* __restrict__ dM, float* __restrict__ loss, int B, int N, int F, int d) {
@@ -164,16 +180,8 @@ secla_fwd_kernel(const float* __restrict__ names, const __nv_bfloat16* __restric
   float* A = sm;               // [B, B]
   float* C = A + B * B;        // [B, B]
   float* red = C + B * B;      // [32]
-  const int BN = B * N, BF = B * F;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int e = warp; e < BN * BF; e += nw) {
-    const int r = e / BF, c = e % BF;
-    float s = 0.f;
-    for (int k = lane; k < d; k += 32) s += names[static_cast<long long>(r) * d + k] * __bfloat162float(face[static_cast<long long>(c) * d + k]);
-    s = warp_sum(s);
-    if (lane == 0) { Mw[e] = s; dM[e] = 0.f; }
-  }
-  __syncthreads();
+  const int BF = B * F;
+  // Mw / dM were filled by secla_sim_kernel (previous launch on the same stream)
   for (int e = threadIdx.x; e < B * B; e += blockDim.x) {
     const int i = e / B, j = e % B;
     float a = 0.f;
@@ -308,6 +316,9 @@ extern "C" int vacnic_secla_fwd(const float* names, const void* face, float* wor
   const size_t smem = (2 * B * B + 32) * sizeof(float);
   float* Mw = workspace;
   float* dM = workspace + static_cast<long long>(B) * N * B * F;
+  secla_sim_kernel<<<(B * N * B * F + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      names, static_cast<const __nv_bfloat16*>(face), Mw, dM, B * N, B * F, d);
+  count_launch();
   secla_fwd_kernel<<<1, 1024, smem, static_cast<cudaStream_t>(stream)>>>(
       names, static_cast<const __nv_bfloat16*>(face), Mw, dM, loss, B, N, F, d);
   count_launch();
