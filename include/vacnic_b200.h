@@ -94,6 +94,7 @@ typedef struct vacnic_gemm_desc {
    * The reduction order is fixed, so results are deterministic.  Null = never split. */
   void* workspace;
   int64_t workspace_bytes;
+  int32_t split_k_min_blocks; /* split only when K spans at least this many 64-wide blocks (0 = 4) */
 } vacnic_gemm_desc;
 
 int vacnic_gemm(const vacnic_gemm_desc* d, void* stream);

@@ -43,7 +43,7 @@ if os.environ.get("GEMM_SHAPES"):
     torch.cuda.synchronize()
     prof, K.PROFILE = K.PROFILE, None
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
-    for fl, e0, e1, shape in prof:
+    for fl, e0, e1, shape, _pair in prof:
         a = agg[shape]
         a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl
     tot = sum(a[1] for a in agg.values())

@@ -395,7 +395,7 @@ extern "C" int vacnic_gemm(const vacnic_gemm_desc* d, void* stream_v) {
   if (bn == 0) {
     pair_bn = choose_pair_tile_n(d, sms);
     bn = pair_bn != 0 ? pair_bn : choose_tile_n(d, sms);
-    if (pair_bn == 0 && d->workspace != nullptr && num_k_blocks >= 4) {
+    if (pair_bn == 0 && d->workspace != nullptr && num_k_blocks >= (d->split_k_min_blocks > 0 ? d->split_k_min_blocks : 4)) {
       // few output tiles and a long reduction: spread K over otherwise idle SMs (wide tiles keep the L2 -> smem
       // traffic per FLOP low, split-K supplies the parallelism)
       const int wide = d->N >= 256 ? 256 : (d->N >= 128 ? 128 : 64);

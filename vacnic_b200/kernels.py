@@ -27,6 +27,16 @@ def _gemm_workspace(device):
     return ws
 
 
+def uses_pair_kernel(M: int, N: int, batch: int, tile_n: int = 0, sms: int = 148) -> bool:
+    """Mirror of choose_pair_tile_n (csrc/gemm_sm100.cu): does vacnic_gemm route this problem to the CTA-pair kernel?"""
+    if tile_n in (1128, 1256):
+        return True
+    if tile_n != 0 or M < 256:
+        return False
+    num_m = (M + 255) // 256
+    return any(N >= bn and batch * num_m * ((N + bn - 1) // bn) >= sms // 2 for bn in (256, 128))
+
+
 PROFILE = None  # set to a list to collect (flops, start_event, end_event, shape) per GEMM launch
 
 
@@ -101,11 +111,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     if out.dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("gemm out must be bf16 or fp32")
     d.act, d.dact, d.accumulate, d.tile_n = act, dact, int(accumulate), tile_n
-    # split-K is opt-in: measured on B200 the partial-tile round trip through L2 costs more than it saves for the
-    # K <= 4096 problems of this model (decode fc2 23 -> 60 us), so no hot-path call site enables it
-    ws = _gemm_workspace(a.device) if (split_k and tile_n == 0) else None
+    # split-K: measured on B200 the partial-tile round trip + the serial last-arriver reduction cost more than they save for
+    # the K <= 4096 problems of this model (decode fc2: 23 -> 60 us), but pay off for weight gradients whose reduction runs
+    # over all B*L rows with only a few output tiles (1024x1024 with K = 16384: 75 -> ~35 us).  Hence: automatic for the
+    # wgrad form (both operands MN-major) with K >= 8192, explicit (`split_k=True`) otherwise.
+    auto_split = a_mn and b_mn and K >= 8192 and tile_n == 0
+    ws = _gemm_workspace(a.device) if ((split_k or auto_split) and tile_n == 0) else None
     if ws is not None:
         d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        d.split_k_min_blocks = 4 if split_k else 128
     if head_major is not None:
         # `out` only supplies the base pointer: element (b0, m, n) goes to b0*sb0 + m*ldc + (n // 64)*chunk + n % 64
         d.ldc, d.c_sb0, d.c_sb1, d.c_chunk_stride = head_major
@@ -114,7 +128,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
         e0.record()
         check(lib().vacnic_gemm(C.byref(d), stream_ptr()), "vacnic_gemm")
         e1.record()
-        PROFILE.append((2.0 * M * N * K * nb0 * nb1, e0, e1, (M, N, K, nb0 * nb1)))
+        PROFILE.append((2.0 * M * N * K * nb0 * nb1, e0, e1, (M, N, K, nb0 * nb1), uses_pair_kernel(M, N, nb0 * nb1, tile_n)))
         return out
     check(lib().vacnic_gemm(C.byref(d), stream_ptr()), "vacnic_gemm")
     return out

@@ -33,7 +33,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float),
         ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("c_dtype", C.c_int32),
         ("act", C.c_int32), ("dact", C.c_int32), ("accumulate", C.c_int32), ("tile_n", C.c_int32),
-        ("c_chunk_stride", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("c_chunk_stride", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("split_k_min_blocks", C.c_int32),
     ]
 
 
