@@ -286,7 +286,7 @@ def main():
     ap.add_argument("--no-pipeline-opt", action="store_true", help="one fused AdamW launch after the gradient exchange instead of per-bucket updates")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="BART-base config-1 shapes (debug)")
-    ap.add_argument("--captions", type=int, default=128, help="captions per GPU (infer workload)")
+    ap.add_argument("--captions", type=int, default=256, help="captions per GPU (infer workload)")
     ap.add_argument("--max-length", type=int, default=50)
     ap.add_argument("--no-infer", action="store_true", help="train workload: skip the secondary beam-4 inference measurement")
     args = ap.parse_args()
