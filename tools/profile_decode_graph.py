@@ -12,7 +12,7 @@ from vacnic_b200 import generation, spec, synthetic  # noqa: E402
 from vacnic_b200.modeling import VacnicBart  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--captions", type=int, default=128)
+ap.add_argument("--captions", type=int, default=256)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 cfg = spec.bart_large()
