@@ -395,6 +395,8 @@ __device__ __forceinline__ ValIdx warp_argmax(ValIdx a) {
   return a;
 }
 
+constexpr int kMaxBeams = 8;
+constexpr int kMaxCand = 2 * kMaxBeams * kMaxBeams;  // nb rows x K = 2 nb candidates each
 constexpr int kTopThreads = 1024;
 
 __global__ void __launch_bounds__(kTopThreads)
@@ -402,16 +404,32 @@ decode_topk_kernel(const float* __restrict__ logits, long long ld, int V, int K,
                    int32_t* __restrict__ top_idx) {
   extern __shared__ float row[];  // [V]
   __shared__ float redf[32];
-  __shared__ int redi[32];
   __shared__ float bc_f;
-  __shared__ int bc_i;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* src = logits + static_cast<long long>(blockIdx.x) * ld;
   float mx = -INFINITY;
-  for (int i = tid; i < V; i += kTopThreads) {
-    const float x = __ldg(src + i);
-    row[i] = x;
-    mx = fmaxf(mx, x);
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // 16-byte loads, several in flight per thread: the row (200 KB) is the only HBM traffic of this kernel
+    const int v4 = V >> 2;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    float4* row4 = reinterpret_cast<float4*>(row);
+#pragma unroll 4
+    for (int i = tid; i < v4; i += kTopThreads) {
+      const float4 x = __ldg(src4 + i);
+      row4[i] = x;
+      mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+    }
+    for (int i = (v4 << 2) + tid; i < V; i += kTopThreads) {
+      const float x = __ldg(src + i);
+      row[i] = x;
+      mx = fmaxf(mx, x);
+    }
+  } else {
+    for (int i = tid; i < V; i += kTopThreads) {
+      const float x = __ldg(src + i);
+      row[i] = x;
+      mx = fmaxf(mx, x);
+    }
   }
   mx = warp_max(mx);
   if (lane == 0) redf[warp] = mx;
@@ -423,7 +441,7 @@ decode_topk_kernel(const float* __restrict__ logits, long long ld, int V, int K,
   __syncthreads();
   mx = bc_f;
   float sum = 0.f;
-  for (int i = tid; i < V; i += kTopThreads) sum += expf(row[i] - mx);
+  for (int i = tid; i < V; i += kTopThreads) sum += __expf(row[i] - mx);  // ex2.approx: |d lse| ~ 1e-7, far below score gaps
   sum = warp_sum(sum);
   __syncthreads();
   if (lane == 0) redf[warp] = sum;
@@ -434,33 +452,55 @@ decode_topk_kernel(const float* __restrict__ logits, long long ld, int V, int K,
   }
   __syncthreads();
   const float lse = bc_f;
-  // thread-local best over its strided elements
-  ValIdx best = {-INFINITY, 0x7fffffff};
-  for (int i = tid; i < V; i += kTopThreads)
-    if (better(row[i], i, best.v, best.i)) { best.v = row[i]; best.i = i; }
-  for (int k = 0; k < K; ++k) {
-    ValIdx w = warp_argmax(best);
-    __syncthreads();
-    if (lane == 0) { redf[warp] = w.v; redi[warp] = w.i; }
-    __syncthreads();
-    if (warp == 0) {
-      ValIdx a = {redf[lane], redi[lane]};
-      a = warp_argmax(a);
-      if (lane == 0) {
-        bc_f = a.v;
-        bc_i = a.i;
-        top_lp[static_cast<long long>(blockIdx.x) * K + k] = a.v - lse;
-        top_idx[static_cast<long long>(blockIdx.x) * K + k] = a.i;
+  // Stage 1: every warp extracts the K best of its own contiguous segment with warp shuffles only (no block barrier);
+  // stage 2: warp 0 merges the 32 sorted candidate lists.  Order everywhere: value descending, index ascending.
+  __shared__ float cand_v[32][2 * kMaxBeams];
+  __shared__ int cand_i[32][2 * kMaxBeams];
+  const int seg = (V + 31) / 32;
+  const int s0 = warp * seg, s1 = min(V, s0 + seg);
+  // every lane keeps the two best of its own elements, so that a full rescan (issued by the whole warp for one lane) is only
+  // needed when a lane has to supply a third candidate
+  ValIdx best = {-INFINITY, 0x7fffffff}, second = {-INFINITY, 0x7fffffff};
+  auto scan2 = [&]() {
+    best.v = second.v = -INFINITY;
+    best.i = second.i = 0x7fffffff;
+    for (int i = s0 + lane; i < s1; i += 32) {
+      const float x = row[i];
+      if (x > -INFINITY) {
+        if (better(x, i, best.v, best.i)) { second = best; best.v = x; best.i = i; }
+        else if (better(x, i, second.v, second.i)) { second.v = x; second.i = i; }
       }
     }
-    __syncthreads();
-    const int win = bc_i;
-    if (win != 0x7fffffff && (win % kTopThreads) == tid) {  // owner removes the winner and rescans
-      row[win] = -INFINITY;
-      best.v = -INFINITY;
-      best.i = 0x7fffffff;
-      for (int i = tid; i < V; i += kTopThreads)
-        if (better(row[i], i, best.v, best.i) && row[i] > -INFINITY) { best.v = row[i]; best.i = i; }
+  };
+  scan2();
+  bool second_valid = true;
+  for (int k = 0; k < K; ++k) {
+    const ValIdx w = warp_argmax(best);
+    if (lane == 0) { cand_v[warp][k] = w.v; cand_i[warp][k] = w.i; }
+    if (w.i != 0x7fffffff && ((w.i - s0) & 31) == lane) {  // owner lane: drop the winner, promote its runner-up
+      row[w.i] = -INFINITY;
+      if (second_valid) {
+        best = second;
+        second_valid = false;
+      } else {
+        scan2();
+        second_valid = true;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int head = 0;  // lane l walks the (sorted) list of warp l
+    for (int k = 0; k < K; ++k) {
+      ValIdx mine = {-INFINITY, 0x7fffffff};
+      if (head < K) { mine.v = cand_v[lane][head]; mine.i = cand_i[lane][head]; }
+      const ValIdx w = warp_argmax(mine);
+      if (w.i == mine.i && w.i != 0x7fffffff) ++head;
+      if (lane == 0) {
+        top_lp[static_cast<long long>(blockIdx.x) * K + k] = w.v - lse;
+        top_idx[static_cast<long long>(blockIdx.x) * K + k] = w.i;
+      }
     }
   }
 }
@@ -486,8 +526,6 @@ struct BeamArgs {
   float length_penalty;
 };
 
-constexpr int kMaxBeams = 8;
-constexpr int kMaxCand = 2 * kMaxBeams * kMaxBeams;  // nb rows x K = 2 nb candidates each
 
 __global__ void __launch_bounds__(128) beam_step_kernel(const BeamArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
