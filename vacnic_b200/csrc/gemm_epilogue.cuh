@@ -34,12 +34,15 @@ constexpr int kBK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 
-template <int BN>
+// BK = K extent of one pipeline stage.  The skinny problems served by BN = 64 are bound by the per-stage round trip
+// (TMA -> mbarrier -> MMA -> commit -> refill, ~0.29 us however many bytes ride on it), so they use 128-wide stages:
+// half as many round trips for the same bytes in flight.
+template <int BN, int BK = kBK>
 struct GemmCfg {
-  static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kABytes = kBM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BK == 128 ? 4 : 8));
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : 2 * BN;  // 128 / 256 / 512
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;

@@ -19,11 +19,11 @@
 
 namespace vb {
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int BK = kBK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage buffers.
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -37,7 +37,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_k = (g.K + kBK - 1) / kBK;
+  const int num_k = (g.K + BK - 1) / BK;
   const long long tiles_per_batch = static_cast<long long>(g.num_m) * g.num_n;
   const long long total_work = g.total_tiles * g.splits;
 
@@ -83,20 +83,27 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          const int k0 = kb * kBK;
-          if constexpr (!A_MN) {
-            tma_load_4d(sa, &tmA, &full_bar[stage], k0, m0, b0 * g.a_m0, b1 * g.a_m1);
-          } else {
+          const int k0 = kb * BK;
+          // K-major operand: one [rows x 64] swizzle atom per 64 k-elements; MN-major: per 64-wide M/N chunk a
+          // [BK k-rows x 128 B] block, filled 64 k-rows per TMA box
 #pragma unroll
-            for (int c = 0; c < kBM / 64; ++c)
-              tma_load_4d(sa + c * (64 * kBK * 2), &tmA, &full_bar[stage], m0 + c * 64, k0, b0 * g.a_m0, b1 * g.a_m1);
-          }
-          if constexpr (!B_MN) {
-            tma_load_4d(sb, &tmB, &full_bar[stage], k0, n0, b0 * g.b_m0, b1 * g.b_m1);
-          } else {
+          for (int kc = 0; kc < BK / 64; ++kc) {
+            if constexpr (!A_MN) {
+              tma_load_4d(sa + kc * (kBM * 128), &tmA, &full_bar[stage], k0 + kc * 64, m0, b0 * g.a_m0, b1 * g.a_m1);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_4d(sb + c * (64 * kBK * 2), &tmB, &full_bar[stage], n0 + c * 64, k0, b0 * g.b_m0, b1 * g.b_m1);
+              for (int c = 0; c < kBM / 64; ++c)
+                tma_load_4d(sa + c * (BK * 128) + kc * (64 * 128), &tmA, &full_bar[stage], m0 + c * 64, k0 + kc * 64,
+                            b0 * g.a_m0, b1 * g.a_m1);
+            }
+            if constexpr (!B_MN) {
+              tma_load_4d(sb + kc * (BN * 128), &tmB, &full_bar[stage], k0 + kc * 64, n0, b0 * g.b_m0, b1 * g.b_m1);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_4d(sb + c * (BK * 128) + kc * (64 * 128), &tmB, &full_bar[stage], n0 + c * 64, k0 + kc * 64,
+                            b0 * g.b_m0, b1 * g.b_m1);
+            }
           }
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -110,9 +117,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // K-major: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major: 64-element chunks along
-      // M/N are kBK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
-      constexpr uint32_t kLboA = A_MN ? kBK * 128 : 16, kLboB = B_MN ? kBK * 128 : 16;
-      constexpr uint32_t kStepA = A_MN ? 16 * 128 : 32, kStepB = B_MN ? 16 * 128 : 32;
+      // M/N are BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
+      constexpr uint32_t kLboA = A_MN ? BK * 128 : 16, kLboB = B_MN ? BK * 128 : 16;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
@@ -130,9 +136,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * kStepA, kLboA, 1024);
-            const uint64_t db = make_smem_desc_sw128(sb + k * kStepB, kLboB, 1024);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 k-elements = 32 B inside a 64-wide atom, atoms (rows x 128 B) follow each other;
+            // MN-major: 16 k-rows = 2048 B
+            const uint32_t offA = A_MN ? k * 2048 : (k >> 2) * (kBM * 128) + (k & 3) * 32;
+            const uint32_t offB = B_MN ? k * 2048 : (k >> 2) * (BN * 128) + (k & 3) * 32;
+            const uint64_t da = make_smem_desc_sw128(sa + offA, kLboA, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + offB, kLboB, 1024);
             umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
@@ -307,11 +317,11 @@ int make_operand_map(CUtensorMap* tm, const void* base, bool mn_major, int rows,
   return VACNIC_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int BK = kBK>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_sm100_kernel<BN, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, BK>;
+  auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, BK>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
@@ -459,5 +469,11 @@ extern "C" int vacnic_gemm(const vacnic_gemm_desc* d, void* stream_v) {
   const bool a_mn = d->a_mn_major != 0, b_mn = d->b_mn_major != 0;
   if (bn == 256) return dispatch_major<256>(tmA, tmB, g, a_mn, b_mn, stream);
   if (bn == 128) return dispatch_major<128>(tmA, tmB, g, a_mn, b_mn, stream);
+  if (g.splits == 1 && d->K > 128) {  // skinny, latency-bound: 128-wide pipeline stages
+    if (!a_mn && !b_mn) return launch_gemm<64, false, false, 128>(tmA, tmB, g, stream);
+    if (!a_mn && b_mn) return launch_gemm<64, false, true, 128>(tmA, tmB, g, stream);
+    if (a_mn && !b_mn) return launch_gemm<64, true, false, 128>(tmA, tmB, g, stream);
+    return launch_gemm<64, true, true, 128>(tmA, tmB, g, stream);
+  }
   return dispatch_major<64>(tmA, tmB, g, a_mn, b_mn, stream);
 }
