@@ -702,6 +702,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool key_oob = key >= a.Sk;
     const bool key_masked = !key_oob && a.key_mask != nullptr && a.key_mask[static_cast<long long>(b) * a.Sk + key] == 0;
     const float c2 = a.scale_log2;
+    const bool warp_plain = !a.causal && __all_sync(0xffffffffu, !(key_oob || key_masked));
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     const uint32_t pt_row = smem_u32(sPT) + r * 128, dst_row = smem_u32(sDST) + r * 128;
     const long long sbase = (static_cast<long long>(b) * a.H + h) * a.Sq;
@@ -729,24 +730,45 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(&sh->s_empty);
       uint32_t ppk[16], dsk[16];
+      if (warp_plain) {
+        // no key of this warp is masked and there is no causal mask: no per-element decisions (the common case)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float pp[8], ds[8];
+        for (int q = 0; q < 4; ++q) {
+          float pp[8], ds[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = q * 8 + e;
-          const float4 st = stq[half * 32 + c];
-          float t = __uint_as_float(xs[c]) * c2;
-          if (key_oob) t = -INFINITY;
-          else if (key_masked || (a.causal && key > qb0 + c)) t = -FLT_MAX;
-          const float p = ex2f(t - st.x) * st.y;
-          pp[e] = p;
-          ds[e] = p * (__uint_as_float(xp[c]) - st.z) * a.scale;
+          for (int e = 0; e < 8; ++e) {
+            const int c = q * 8 + e;
+            const float4 st = stq[half * 32 + c];
+            const float p = ex2f(fmaf(__uint_as_float(xs[c]), c2, -st.x)) * st.y;
+            pp[e] = p;
+            ds[e] = p * (__uint_as_float(xp[c]) - st.z) * a.scale;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            ppk[q * 4 + e] = pack_bf16x2(pp[2 * e], pp[2 * e + 1]);
+            dsk[q * 4 + e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
+          }
         }
+      } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          ppk[q * 4 + e] = pack_bf16x2(pp[2 * e], pp[2 * e + 1]);
-          dsk[q * 4 + e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
+        for (int q = 0; q < 4; ++q) {
+          float pp[8], ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = q * 8 + e;
+            const float4 st = stq[half * 32 + c];
+            float t = __uint_as_float(xs[c]) * c2;
+            if (key_oob) t = -INFINITY;
+            else if (key_masked || (a.causal && key > qb0 + c)) t = -FLT_MAX;
+            const float p = ex2f(t - st.x) * st.y;
+            pp[e] = p;
+            ds[e] = p * (__uint_as_float(xp[c]) - st.z) * a.scale;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            ppk[q * 4 + e] = pack_bf16x2(pp[2 * e], pp[2 * e + 1]);
+            dsk[q * 4 + e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
+          }
         }
       }
       if (n > 0) mbar_wait(&sh->ds_empty, (n - 1) & 1u);  // the dV / dK MMAs of step n-1 have consumed both buffers
