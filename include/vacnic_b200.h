@@ -177,6 +177,12 @@ int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int6
  * {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}; also refreshes the bf16
  * compute shadow p16 (may be null). */
 int vacnic_adamw(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const float* hyper, void* stream);
+/* clip_grad_norm_ (TRAIN:365-366) folded into the optimizer: *scale_out = base_scale * min(1, max_norm / (|base_scale| *
+ * ||g||_2 + 1e-6)); write it to hyper[7] of vacnic_adamw.  scratch: VACNIC_CLIP_SCRATCH_FLOATS device floats (per-block
+ * partial sums, reduced in a fixed order: the norm is bit-reproducible). */
+#define VACNIC_CLIP_SCRATCH_FLOATS 2368
+int vacnic_clip_grad_scale(const float* g, int64_t n, float max_norm, float base_scale, float* scratch, float* scale_out,
+                           float* norm_out, void* stream);
 int vacnic_rng_advance(uint64_t* state, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -1,0 +1,79 @@
+"""TrainStep (TRAIN:253-374 as one captured step): graph replay equals eager execution, the fused AdamW follows
+torch.optim.AdamW, and the optional clip_grad_norm_ (TRAIN:365-366) folded into the optimizer matches torch."""
+import pytest
+import torch
+
+from oracle import model as OM
+from vacnic_b200 import spec, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(dev, seed=41):
+    from vacnic_b200.modeling import VacnicBart
+    cfg = spec.VacnicConfig(d_model=768, heads=12, ffn=1024, enc_layers=2, dec_layers=2, prompt_size=4, max_pos=128)
+    gcfg = spec.VacnicConfig(**{**cfg.as_dict(), "stock": True})
+    sd, gsd = spec.test_state_dict(cfg, seed), spec.test_state_dict(gcfg, seed + 100)
+    m = VacnicBart(cfg, device=dev, p_drop=0.0)
+    m.load_reference_state_dict(sd)
+    g = VacnicBart(gcfg, device=dev, p_drop=0.0, frozen=True)
+    g.load_reference_state_dict(gsd)
+    return cfg, gcfg, sd, gsd, m, g
+
+
+def test_clip_grad_scale_kernel(cuda_device):
+    from vacnic_b200 import kernels as K
+    torch.manual_seed(0)
+    g = torch.randn(1_000_003, device=cuda_device) * 0.01
+    scratch = torch.zeros(2368, device=cuda_device)
+    out = torch.zeros(2, device=cuda_device)
+    for max_norm, base in ((0.1, 1.0), (100.0, 1.0), (0.1, 0.25)):
+        K.clip_grad_scale(g[:1_000_000], max_norm, base, scratch, out[0:1], out[1:2])
+        norm = (g[:1_000_000].double().norm() * base).item()
+        want = base * min(1.0, max_norm / (norm + 1e-6))
+        assert abs(out[1].item() - norm) <= 1e-4 * norm
+        assert abs(out[0].item() - want) <= 1e-4 * abs(want)
+
+
+@pytest.mark.parametrize("max_grad_norm", [None, 0.1])
+def test_step_matches_torch_optimizer_and_graph_equals_eager(cuda_device, max_grad_norm):
+    from vacnic_b200.trainer import TrainStep
+    batch = synthetic.make_batch(B=2, L=40, T=12, seed=9)
+    results = []
+    for use_graph in (False, True):
+        cfg, gcfg, sd, gsd, m, g = _models(cuda_device)
+        ts = TrainStep(m, g, lr=1e-3, weight_decay=0.01, use_graph=use_graph, max_grad_norm=max_grad_norm)
+        losses = [{k: float(v.detach()) for k, v in ts.step(batch).items()} for _ in range(3)]
+        torch.cuda.synchronize()
+        results.append((losses, m.store.master.clone()))
+    (le, pe), (lg, pg) = results
+    # same kernels in the same order; bias / LayerNorm / embedding gradients are accumulated with fp32 atomics, so two runs
+    # differ in the last bits and Adam (sign-like for tiny gradients) may flip isolated updates by 2*lr: losses must
+    # agree to 2e-3 relative, parameters on average to 1e-5
+    for a, b in zip(le, lg):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, le, lg)
+    assert (pe - pg).abs().mean().item() <= 1e-5
+    # fp32 oracle + torch.optim.AdamW (+ clip_grad_norm_) taking the same three steps
+    cfg, gcfg, sd, gsd, m, g = _models(cuda_device)
+    osd = {k: v.to(cuda_device).clone().requires_grad_(v.is_floating_point() and k != "final_logits_bias") for k, v in sd.items()
+           if k not in spec.TIED_TO_SHARED}
+    for k in spec.TIED_TO_SHARED:
+        osd[k] = osd["model.shared.weight"]
+    ogsd = {k: v.to(cuda_device) for k, v in gsd.items()}
+    uniq = list({id(v): v for v in osd.values() if v.requires_grad}.values())
+    opt = torch.optim.AdamW(uniq, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    db = synthetic.to_device(batch, cuda_device)
+    ol = []
+    for _ in range(3):
+        o = OM.training_losses(osd, cfg.as_dict(), ogsd, gcfg.as_dict(), db)
+        o["loss"].backward()
+        if max_grad_norm is not None:
+            torch.nn.utils.clip_grad_norm_(uniq, max_norm=max_grad_norm)
+        opt.step()
+        opt.zero_grad()
+        ol.append({k: float(o[k]) for k in ("txt", "margin", "secla")})
+    for a, b in zip(le, ol):
+        for k in b:
+            assert abs(a[k] - b[k]) <= 3e-2 * max(1.0, abs(b[k])), (k, le, ol)
+    assert le[2]["txt"] < le[0]["txt"]  # the optimizer is actually applied

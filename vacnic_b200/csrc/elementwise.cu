@@ -157,6 +157,51 @@ pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict
 }
 
 
+
+// Global-norm gradient clipping (torch.nn.utils.clip_grad_norm_, TRAIN:365-366; off in the shipped scripts) folded into the
+// fused optimizer: sum of squares of the flat gradient buffer -> grad_scale = base * min(1, max_norm / (base*||g|| + 1e-6)).
+__global__ void __launch_bounds__(256)
+sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ acc) {
+  float s = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * 256 * 4;
+  for (long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(g + i));
+      s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    } else {
+      for (long long k = i; k < n; ++k) s += g[k] * g[k];
+    }
+  }
+  s = warp_sum(s);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    acc[blockIdx.x] = t;  // per-block partial: summed in a fixed order below -> bit-reproducible norm
+  }
+}
+__global__ void __launch_bounds__(256)
+clip_scale_kernel(const float* __restrict__ partial, int nparts, float max_norm, float base, float* __restrict__ scale_out,
+                  float* __restrict__ norm_out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 256) s += static_cast<double>(partial[i]);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float norm = static_cast<float>(sqrt(red[0])) * fabsf(base);
+    const float coef = fminf(1.f, max_norm / (norm + 1e-6f));
+    *scale_out = base * coef;
+    if (norm_out) *norm_out = norm;
+  }
+}
+
 // dst[r, c] = bf16(src[r, c]) for c < n, rows re-pitched from ld_src to ld_dst (pad columns zero): gradients handed back
 // by torch ops (e.g. the script-level CrossEntropyLoss on [rows, 50267] logits) become TMA-readable GEMM operands
 __global__ void __launch_bounds__(256)
@@ -286,4 +331,17 @@ extern "C" int vacnic_cast_rows_f32_bf16(const float* src, void* dst, int64_t ro
       src, static_cast<__nv_bfloat16*>(dst), rows, n, ld_src, ld_dst);
   count_launch();
   return check_last("cast_rows");
+}
+
+extern "C" int vacnic_clip_grad_scale(const float* g, int64_t n, float max_norm, float base_scale, float* scratch,
+                                      float* scale_out, float* norm_out, void* stream) {
+  VB_REQUIRE(g && scratch && scale_out && n > 0 && max_norm > 0.f, "clip_grad_scale: bad arguments");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "clip_grad_scale: gradient buffer must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > VACNIC_CLIP_SCRATCH_FLOATS) blocks = VACNIC_CLIP_SCRATCH_FLOATS;
+  sqnorm_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(g, n, scratch);
+  clip_scale_kernel<<<1, 256, 0, s>>>(scratch, static_cast<int>(blocks), max_norm, base_scale, scale_out, norm_out);
+  count_launch(2);
+  return check_last("clip_grad_scale");
 }

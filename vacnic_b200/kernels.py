@@ -301,6 +301,12 @@ def adamw(p, g, m, v, p16, hyper):
     check(lib().vacnic_adamw(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p16), p.numel(), ptr(hyper), stream_ptr()), "vacnic_adamw")
 
 
+def clip_grad_scale(g, max_norm, base_scale, scratch, scale_out, norm_out=None):
+    """scale_out[0] = base_scale * min(1, max_norm / (|base_scale| * ||g|| + 1e-6))  (clip_grad_norm_ folded into AdamW)."""
+    check(lib().vacnic_clip_grad_scale(ptr(g), g.numel(), float(max_norm), float(base_scale), ptr(scratch), ptr(scale_out),
+                                       ptr(norm_out), stream_ptr()), "vacnic_clip_grad_scale")
+
+
 def ce_fwd(logits2d, V, targets, ignore_index=1):
     """logits fp32 [rows, ld] (ld >= V). Returns (out[2] = {mean loss, count}, lse, row_loss)."""
     _c(targets, torch.int64, "targets")

@@ -31,13 +31,16 @@ class TrainStep:
     def __init__(self, model: VacnicBart, guide: Optional[VacnicBart], lr: float = 3e-5, weight_decay: float = 0.01,
                  betas=(0.9, 0.999), eps: float = 1e-8, warmup_steps: int = 0, total_steps: int = 1_000_000,
                  margin: float = 1.0, alpha: float = 0.5, secla_weight: float = 1.0, use_graph: bool = True,
-                 process_group=None, pipeline_optimizer: Optional[bool] = None):
+                 process_group=None, pipeline_optimizer: Optional[bool] = None, max_grad_norm: Optional[float] = None):
         self.model, self.guide = model, guide
         self.cfg = model.cfg
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.warmup, self.total = warmup_steps, total_steps
         self.margin, self.alpha, self.w_secla = margin, alpha, secla_weight
         self.use_graph = use_graph
+        # torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) of TRAIN:365-366 (--no_clip_norm True in the shipped
+        # scripts): the global norm needs every gradient, so it switches the per-bucket optimizer pipelining off
+        self.max_grad_norm = max_grad_norm
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         st = model.store
@@ -45,6 +48,8 @@ class TrainStep:
         self.m = torch.zeros_like(st.master)
         self.v = torch.zeros_like(st.master)
         self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._clip_scratch = torch.zeros(2368, dtype=torch.float32, device=dev)  # VACNIC_CLIP_SCRATCH_FLOATS
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.step_no = 0
         self.graph = None
@@ -52,10 +57,13 @@ class TrainStep:
         self.losses: Dict[str, torch.Tensor] = {}
         self.launches_per_step = 0
         self.buckets: Optional[GradBuckets] = None
+        if max_grad_norm is not None:
+            pipeline_optimizer = False
         if pipeline_optimizer is None:
             # measured on B200: per-bucket updates behind the backward pass gain 0.6 % at 2 GPUs (the fused update no
             # longer waits for the last all-reduce) and lose 1 % on one GPU (HBM contention with the backward GEMMs)
             pipeline_optimizer = self.world > 1
+        self.pipeline = bool(pipeline_optimizer)
         if pipeline_optimizer or self.world > 1:
             # Address-range buckets of the flat gradient buffer, completed from markers in the backward pass
             # (vacnic_b200.dp, blocks.GradMarkFn).  On a side stream each bucket is all-reduced in place (world > 1) and
@@ -131,13 +139,19 @@ class TrainStep:
                 if not self.buckets.done[i]:
                     self.comm_stream.wait_event(ev)
                     with torch.cuda.stream(self.comm_stream):
-                        self._adamw_ranges(self.buckets.reduce_bucket(i))
+                        r = self.buckets.reduce_bucket(i)
+                        if self.pipeline:
+                            self._adamw_ranges(r)
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 # embeddings / prefix modules + any bucket whose marker did not fire
-                self._adamw_ranges(self.buckets.finish())
+                r = self.buckets.finish()
+                if self.pipeline:
+                    self._adamw_ranges(r)
             torch.cuda.current_stream().wait_stream(self.comm_stream)
-        else:
+        if self.buckets is None or not self.pipeline:
+            if self.max_grad_norm is not None:
+                K.clip_grad_scale(st.grad, self.max_grad_norm, 1.0 / self.world, self._clip_scratch, self.hyper[7:8], self.grad_norm)
             K.adamw(st.master, st.grad, self.m, self.v, st.shadow, self.hyper)
         return losses
 
