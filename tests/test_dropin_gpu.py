@@ -129,3 +129,26 @@ def test_only_visual_module_forward_signature(cuda_device):
     with pytest.raises(Exception):
         model(input_ids=src.cpu(), attention_mask=OM.src_mask(src).cpu(), decoder_input_ids=batch["caption_ids"].cpu(),
               image_features=batch["image_features"].cpu())                       # no CPU fallback
+
+
+def test_save_pretrained_roundtrip_with_reference_names(cuda_device, tmp_path):
+    """Checkpoint format: config.json + safetensors under the reference state_dict names."""
+    from safetensors.torch import load_file
+    mod = importlib.import_module(MFULL)
+    cfg = spec.VacnicConfig(d_model=768, heads=12, ffn=1024, enc_layers=2, dec_layers=2, prompt_size=4, max_pos=128)
+    model = mod.BartForMultiModalGeneration(_hf_config(cfg), **_ctor_kwargs(cfg))
+    model.load_state_dict(spec.test_state_dict(cfg, 33), strict=False)
+    model.eval()
+    out_dir = model.save_pretrained(str(tmp_path / "ckpt"))
+    saved = load_file(os.path.join(out_dir, "model.safetensors"))
+    want = set(spec.param_shapes(cfg).keys()) - set(spec.TIED_TO_SHARED)
+    assert set(saved.keys()) == want
+    clone = mod.BartForMultiModalGeneration.from_pretrained(out_dir, **_ctor_kwargs(cfg))
+    batch = synthetic.to_device(synthetic.make_batch(B=2, L=40, T=12, seed=8), cuda_device)
+    kw = _inputs(cfg, batch)
+    with torch.no_grad():
+        a = model(decoder_input_ids=batch["caption_ids"], **kw)["logits"]
+        b = clone(decoder_input_ids=batch["caption_ids"], **kw)["logits"]
+    assert torch.equal(a, b)
+    for k, v in clone.state_dict().items():
+        assert torch.equal(v.cpu(), model.state_dict()[k].cpu()), k

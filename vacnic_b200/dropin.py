@@ -97,7 +97,8 @@ class _DropInBase(VacnicBart):
         if sd is not None:
             model.load_reference_state_dict(sd, strict=False)
             enc = model.model.encoder
-            if hasattr(enc, "embed_tokens_ner"):
+            if hasattr(enc, "embed_tokens_ner") and "model.encoder.embed_tokens_ner.weight" not in sd:
+                # a plain BART checkpoint: the NER tables start as copies of the token / position tables
                 n = min(50265, enc.embed_tokens.weight.shape[0])
                 with torch.no_grad():
                     enc.embed_tokens_ner.weight[:n] = enc.embed_tokens.weight[:n]
@@ -108,6 +109,34 @@ class _DropInBase(VacnicBart):
     def state_dict(self, *a, **k):
         sd = super().state_dict(*a, **k)
         return sd
+
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = True):
+        """Write `config.json` + `model.safetensors` (or `pytorch_model.bin`) with the REFERENCE parameter names, so the
+        checkpoint loads into the reference classes (`load_state_dict`) and back through `from_pretrained` (SURVEY §8f,
+        replaces the whole-module pickles of TRAIN:467 / INFER:1087).  Entries that alias `model.shared.weight` are
+        written once."""
+        os.makedirs(save_directory, exist_ok=True)
+        sd = {}
+        seen = {}
+        for k, v in self.state_dict().items():
+            key = (v.data_ptr(), tuple(v.shape))
+            if key in seen:
+                continue  # tied alias (model.encoder/decoder.embed_tokens.weight)
+            seen[key] = k
+            sd[k] = v.detach().to("cpu").contiguous().clone()
+        cfg = self.config
+        if hasattr(cfg, "save_pretrained"):
+            cfg.save_pretrained(save_directory)
+        else:  # pragma: no cover
+            import json
+            with open(os.path.join(save_directory, "config.json"), "w") as f:
+                json.dump(dict(cfg), f)
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, "model.safetensors"), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(save_directory, "pytorch_model.bin"))
+        return save_directory
 
     # whole-module pickling (torch.save(model) at TRAIN:467): rebuild the flat store on load
     def __reduce__(self):
@@ -201,6 +230,8 @@ def _read_checkpoint(path: str) -> Optional[dict]:
             sd.update(torch.load(f, map_location="cpu", weights_only=True))
     if "model.shared.weight" in sd:  # tied entries that some checkpoints omit
         sd.setdefault("lm_head.weight", sd["model.shared.weight"])
+        sd.setdefault("model.encoder.embed_tokens.weight", sd["model.shared.weight"])
+        sd.setdefault("model.decoder.embed_tokens.weight", sd["model.shared.weight"])
     return sd
 
 
