@@ -54,7 +54,7 @@ def train_flops_per_sample(cfg, L, T, with_guide=True):
     prefix = 2 * 768 * 384 * P + 2 * 384 * P * 768 * P + (2 * P * 768 * d if d == 1024 else 0) + (2 * F * 512 * d if full else 0)
     fwd = cfg.enc_layers * enc + cfg.dec_layers * dec + head + prefix
     stock_enc = 8 * L * d * d + 4 * L * L * d + 4 * L * d * f
-    guide = cfg.enc_layers * stock_enc + cfg.dec_layers * dec
+    guide = cfg.enc_layers * stock_enc + cfg.dec_layers * dec + head  # HF forward of the frozen guide computes its logits too
     return 3 * fwd + (guide if with_guide else 0), fwd, guide
 
 

@@ -1,0 +1,47 @@
+"""CPU checks of the measurement plumbing: the algorithmic FLOP / byte model bench.py divides by reproduces the
+figures of SURVEY.md §8(d), and the reference arm prints a well-formed line without touching a GPU."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec_ = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mod)
+    return mod
+
+
+def test_flop_model_matches_survey_8d():
+    from vacnic_b200 import spec
+    b = _bench()
+    total, fwd, guide = b.train_flops_per_sample(spec.bart_large(), 1024, 64)
+    assert abs(fwd / 1e9 - 514.1) < 0.6          # forward per sample, config 2
+    assert abs(guide / 1e9 - 444.9) < 0.6        # frozen stock-BART guide forward
+    assert abs(total / 1e9 - 1987.0) < 2.0       # 3 x forward + guide
+    vis_total, vis_fwd, _ = b.train_flops_per_sample(spec.bart_large(only_image=True), 512, 64, with_guide=False)
+    assert abs(vis_fwd / 1e9 - 255.8) < 0.6 and abs(vis_total / 1e9 - 767.0) < 2.0   # config 5
+    base_fwd = b.train_flops_per_sample(spec.bart_base(), 512, 40)[1]
+    assert abs(base_fwd / 1e9 - 74.4) < 0.5      # config 1
+
+
+def test_decode_byte_model_matches_survey_8d():
+    from vacnic_b200 import spec
+    b = _bench()
+    cfg = spec.bart_large()
+    enc_flops, dec_bytes, cross_per_layer = b.infer_flops_bytes(cfg, C=64, L=1024, nb=4, steps=1, key_lens=[1024] * 64)
+    w_bytes = 2 * (cfg.dec_layers * (8 * cfg.d_model ** 2 + 2 * cfg.d_model * cfg.ffn) + cfg.d_model * cfg.vocab)
+    assert abs(w_bytes / 1e6 - 505.6) < 1.0                                  # decoder + LM-head weights read per step
+    assert abs(cross_per_layer * cfg.dec_layers / 64 / 1e6 - 50.3) < 0.1     # cross K/V per caption per step
+    assert abs(dec_bytes / 1e9 - 3.73) < 0.02                                # per-step traffic at 64 captions
+
+
+def test_reference_arm_is_rank0_only_and_cpu_only():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1", CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""   # ranks != 0 exit 0 without work
