@@ -206,3 +206,56 @@ def test_decode_self_attention_with_ancestry_matches_torch(cuda_device):
         anc[ob] = new_anc
         logical = [list(logical[int(src[r])]) for r in range(R)]
         K.advance_len(cur)
+
+
+@pytest.mark.parametrize("nb,lp", [(4, 2.0), (1, 1.0)])
+def test_device_search_follows_oracle_search_on_its_own_logits_full_length(cuda_device, nb, lp):
+    """Size-independent exactness property at BASELINE's inference sizes (L = 1024 article tokens, V = 50267, max_length
+    50): the oracle's `_beam_search` / greedy loop is driven with the fp32 logits our cached decoder produces step by step;
+    the device-side search, seeing the same numbers, must make the same decisions, so the final ids are identical — however
+    small the margins are (no bf16-vs-fp32 noise enters this comparison)."""
+    from vacnic_b200 import generation
+    from vacnic_b200.modeling import VacnicBart
+    dev = cuda_device
+    cfg = spec.VacnicConfig(d_model=1024, heads=16, ffn=2048, enc_layers=2, dec_layers=2, prompt_size=20, max_pos=1024)
+    sd = spec.test_state_dict(cfg, 77, lm_scale=4.0)
+    sd["final_logits_bias"][0, cfg.eos_token_id] = 9.0          # some beams finish early
+    m = VacnicBart(cfg, device=dev, p_drop=0.0)
+    m.load_reference_state_dict(sd)
+    m.eval()
+    C, L, max_len = 6, 1024, 50
+    batch = synthetic.to_device(synthetic.make_batch(B=C, L=L, T=8, seed=21), dev)
+    kw = _gen_kwargs(cfg, batch)
+    eng = generation.Generator(m, C, nb, L, max_len, length_penalty=lp, use_graph=False)
+    eng.encode(generation._enc_inputs(m, kw["input_ids"], kw["attention_mask"], kw["image_features"], kw.get("face_features"),
+                                      kw.get("face_mask"), kw.get("name_ids"), kw.get("name_mask")))
+    eng._reset_state()
+    V = cfg.vocab
+
+    def step_fn(flat_ids, reorder):
+        eng._step()                       # advances the DEVICE search by one position, leaves this step's logits in eng.logits
+        return eng.logits[:, :V].clone()
+
+    if nb > 1:
+        want, _ = OG.beam_search_core(step_fn, C, V, dev, nb, max_len, lp, cfg.eos_token_id, cfg.pad_token_id,
+                                      cfg.decoder_start_token_id)
+        steps = int(eng.st["cur_len"].item()) - 1
+        ob = (steps + 1) & 1
+        gen_len = int(eng.st["fin_len"][ob, :, 0].max().item())
+        got = eng.st["fin_seq"][ob, :, 0, :1 + gen_len].long()
+    else:
+        ids = torch.full((C, 1), cfg.decoder_start_token_id, dtype=torch.long, device=dev)
+        unfinished = torch.ones(C, dtype=torch.long, device=dev)
+        while True:
+            logits = step_fn(ids, None)
+            if ids.shape[1] == max_len - 1:
+                logits = torch.full_like(logits, -float("inf"))
+                logits[:, cfg.eos_token_id] = 0
+            nxt = logits.argmax(-1) * unfinished + cfg.pad_token_id * (1 - unfinished)
+            ids = torch.cat([ids, nxt[:, None]], dim=-1)
+            unfinished = unfinished & (nxt != cfg.eos_token_id).long() & int(ids.shape[1] < max_len)
+            if unfinished.max() == 0:
+                break
+        want = ids
+        got = eng.st["seq"][:, :want.shape[1]].long()
+    assert got.shape == want.shape and bool((got == want).all()), (got, want)
