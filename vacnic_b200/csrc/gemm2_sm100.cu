@@ -25,7 +25,9 @@ struct Gemm2Cfg {
   static constexpr int kStages = (BN == 256) ? 6 : 8;
   static constexpr int kTmemCols = 2 * BN;               // double-buffered accumulator: 512 / 256
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr int kBiasBytes = kEpiWarps * (BN / 2) * 4;  // each epilogue warp's bias slice of the current tile
+  static constexpr int kStoreBytes = kEpiWarps * 32 * 64;      // each epilogue warp's 32 x 32 bf16 transpose buffer
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + kStoreBytes + 1024;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -77,13 +79,16 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       "h"(static_cast<uint16_t>(3))
       : "memory");
 }
-// arrive on the barrier at this offset in the LEADER CTA
+// Arrive on the barrier at this offset in the LEADER CTA.  Relaxed: the only thing the MMA thread may not overtake
+// is this warp's TMEM reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync have already retired; a
+// release at cluster scope would also drain the warp's global stores (MEMBAR.ALL.GPU + ERRBAR, ~10 % of the
+// kernel's stall samples in profiles/r1_ncu_gemm2_fc1_gelu.md) for no reason.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar))
       : "memory");
 }
@@ -209,8 +214,17 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------ epilogue warps 2..9 (own 128 rows)
+    // Per tile: each warp stages the bias of its BN/2 columns in its own shared-memory slice while the accumulator
+    // is still being produced (no CTA-level barrier), then drains its 32 rows x BN/2 columns in 32-column chunks with the
+    // tcgen05.ld of chunk i+1 in flight behind the arithmetic and stores of chunk i, and hands the accumulator
+    // back to the MMA thread as soon as its last chunk is in registers (before that chunk is computed / stored).
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
+    float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes) +
+                   (warp - 2) * (BN / 2);
+    uint8_t* sstore = smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + Cfg::kBiasBytes + (warp - 2) * (32 * 64);
+    constexpr int kChunks = BN / 64;  // 32-column chunks per warp
+    const bool has_bias = g.bias != nullptr;
     uint32_t it = 0;
     for (long long t = first_tile; t < g.total_tiles; t += tile_stride, ++it) {
       const int batch = static_cast<int>(t / tiles_per_batch);
@@ -221,28 +235,71 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int b1 = batch / g.batch0;
       const uint32_t as = it & 1u;
       const uint32_t aphase = (it >> 1) & 1u;
+      if (has_bias) {
+        __syncwarp();  // every lane is done reading the previous tile's slice
+#pragma unroll
+        for (int j = lane; j < BN / 2; j += 32) {
+          const int n = n0 + half * (BN / 2) + j;
+          sbias[j] = n < g.N ? __ldg(g.bias + n) : 0.0f;
+        }
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const long long row_off = static_cast<long long>(b0) * g.c_sb0 + static_cast<long long>(b1) * g.c_sb1 +
                                 static_cast<long long>(row) * g.ldc;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
-        if (n0 + c * 32 >= g.N) break;
-        uint32_t r32[32];
-        tmem_ld_32x32(taddr + c * 32, r32);
-        tmem_ld_wait();
-        if (row < g.M) {
-          float v[32];
+      const int c0 = half * kChunks;
+      const long long warp_off = static_cast<long long>(b0) * g.c_sb0 + static_cast<long long>(b1) * g.c_sb1 +
+                                 static_cast<long long>(m0 + quad * 32) * g.ldc;
+      const int rows_valid = g.M - (m0 + quad * 32);
+      const bool row_ok = lane < rows_valid;
+      // bf16 results without read-modify-write leave through the warp-cooperative coalesced store
+      const bool coalesced = g.c_dtype == VACNIC_DT_BF16 && !g.accumulate;
+      auto process = [&](const uint32_t (&buf)[32], int i) {
+        const int n = n0 + (c0 + i) * 32;
+        if (n >= g.N) return;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r32[j]);
-          epilogue_row_chunk(g, v, row_off, n0 + c * 32);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(buf[j]);
+        const float* sb = has_bias ? sbias + i * 32 : nullptr;
+        const long long coff = epilogue_col_off(g, n);
+        if (epilogue_chunk_is_vec(g, n, sb)) {
+          epilogue_bias_alpha(g, v, n, sb);
+          if (g.aux_out != nullptr) {
+            __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(g.aux_out);
+            if (coalesced) store_chunk_bf16_coalesced(sstore, lane, v, aux + warp_off + coff, g.ldc, rows_valid);
+            else if (row_ok) store_row_bf16_vec(aux + row_off + coff, v);
+          }
+          epilogue_act(g, v);
+          if (g.dact != VACNIC_ACT_NONE && row_ok) epilogue_dact_vec(g, v, row_off + coff);
+          if (coalesced)
+            store_chunk_bf16_coalesced(sstore, lane, v, reinterpret_cast<__nv_bfloat16*>(g.c) + warp_off + coff, g.ldc,
+                                       rows_valid);
+          else if (row_ok)
+            epilogue_store_vec(g, v, row_off + coff);
+        } else if (row_ok) {
+          epilogue_chunk_ragged_call(g, v, row_off + coff, n, sb);
         }
+      };
+      uint32_t buf_a[32], buf_b[32];
+      tmem_ld_32x32(taddr + c0 * 32, buf_a);
+#pragma unroll 1
+      for (int i = 0; i < kChunks; i += 2) {  // kChunks is 2 or 4: the body handles one chunk pair
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + (c0 + i + 1) * 32, buf_b);
+        process(buf_a, i);
+        tmem_ld_wait();
+        if (i + 2 < kChunks) {
+          tmem_ld_32x32(taddr + (c0 + i + 2) * 32, buf_a);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+        }
+        process(buf_b, i + 1);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
     }
   }
 

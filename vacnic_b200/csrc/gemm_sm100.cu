@@ -355,16 +355,30 @@ int launch_gemm_pair(int bn, bool a_mn, bool b_mn, const CUtensorMap& tmA, const
 // CTA-pair (256 x BN tiles) kernel: worth it once every SM pair gets at least one tile.  Returns 0 for "use the
 // single-CTA kernel".
 static int choose_pair_tile_n(const vacnic_gemm_desc* d, int sms) {
+  // The CTA-pair kernel is used when some tile width fills every SM pair at least once; among the widths the
+  // cheaper one by (waves x tile width) wins, with the 128-wide tile charged 15 % for its lower MMA efficiency
+  // (measured: 5.9 us vs 2 x 3.7 us per 1024-deep tile).  E.g. the fc1 weight gradient (4096 x 1024 outputs):
+  // 64 tiles of 256 in ONE wave beat 128 tiles of 128 in two.
   if (d->M < 256) return 0;
   const long long batch = static_cast<long long>(d->batch0) * d->batch1;
   const long long num_m = (d->M + 255) / 256;
+  const long long pairs = sms / 2;
   const int cands[2] = {256, 128};
+  int best = 0;
+  double best_cost = 0.0;
+  bool fills = false;
   for (int i = 0; i < 2; ++i) {
     const int bn = cands[i];
     if (d->N < bn) continue;
-    if (batch * num_m * ((d->N + bn - 1) / bn) >= sms / 2) return bn;
+    const long long tiles = batch * num_m * ((d->N + bn - 1) / bn);
+    if (tiles >= pairs) fills = true;
+    const double cost = static_cast<double>((tiles + pairs - 1) / pairs) * bn * (bn == 128 ? 1.15 : 1.0);
+    if (best == 0 || cost < best_cost) {
+      best = bn;
+      best_cost = cost;
+    }
   }
-  return 0;
+  return fills ? best : 0;
 }
 
 static int choose_tile_n(const vacnic_gemm_desc* d, int sms) {
