@@ -45,3 +45,17 @@ def test_reference_arm_is_rank0_only_and_cpu_only():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""   # ranks != 0 exit 0 without work
+
+
+def test_wgrad_k_slices_policy():
+    """Only long reductions with few 256 x 256 output tiles are sliced, and the slices tile the token dimension."""
+    from vacnic_b200.blocks import wgrad_k_slices
+    assert wgrad_k_slices(16384, 1024, 1024) == 4      # 16 tiles -> 4 slices fill 64 of 74 SM pairs
+    assert wgrad_k_slices(16384, 4096, 1024) == 1      # 64 tiles: one wave already
+    assert wgrad_k_slices(16384, 3072, 1024) == 1
+    assert wgrad_k_slices(1024, 1024, 1024) == 1       # decoder rows: short reduction
+    assert wgrad_k_slices(16384, 512, 512) == 8
+    assert wgrad_k_slices(16384, 64, 1024) == 1
+    for rows in (8192, 16384, 16704, 32768):
+        s = wgrad_k_slices(rows, 1024, 1024)
+        assert rows % s == 0 and (rows // s) % 8 == 0 and rows // s >= 2048

@@ -185,3 +185,78 @@ def test_gemm_split_k_is_deterministic_and_matches(cuda_device, M, N, K, a_mn, b
     y = k.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias, act=k.ACT_GELU, split_k=True)
     yref = torch.nn.functional.gelu(ref)
     assert (y.float() - yref).abs().max().item() <= 2e-2 * max(1.0, yref.abs().max().item())
+
+
+@pytest.mark.parametrize("tile_n", [1128, 1256])
+@pytest.mark.parametrize("M,N,K", [(1000, 392, 136), (264, 416, 72), (776, 1024, 256)])
+def test_gemm_cta_pair_bf16_epilogues(cuda_device, M, N, K, tile_n):
+    """bf16 results of the CTA-pair kernel leave through the warp-cooperative coalesced store: ragged M (partial warps),
+    ragged N (scalar tail chunk), pre-activation side output, activation gradient, accumulate (thread-owns-row path)."""
+    from vacnic_b200 import kernels as k
+    a = _mk((M, K), cuda_device, 0.3, seed=31)
+    b = _mk((N, K), cuda_device, 0.3, seed=32)
+    bias = torch.randn(N, device=cuda_device)
+    pre = (a.float() @ b.float().t() + bias) * 0.5   # bias is added before alpha
+    # canary-framed outputs: nothing outside [M, N] may be written
+    big = torch.full((M + 8, N + 8), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    zbig = torch.full((M + 8, N + 8), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    y, z = big[:M, :N], zbig[:M, :N]
+    k.gemm(a, b, out=y, bias=bias, alpha=0.5, act=k.ACT_GELU, aux_out=z, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert (z.float() - pre).abs().max().item() <= 1e-2 * max(1.0, pre.abs().max().item())
+    assert (y.float() - torch.nn.functional.gelu(pre)).abs().max().item() <= 1e-2 * max(1.0, pre.abs().max().item())
+    assert (big[M:] == 7).all() and (big[:, N:] == 7).all() and (zbig[M:] == 7).all() and (zbig[:, N:] == 7).all()
+    # same numbers as the single-CTA kernel (shared arithmetic, different store path)
+    y1 = k.gemm(a, b, bias=bias, alpha=0.5, act=k.ACT_GELU, tile_n=128)
+    assert torch.equal(y, y1)
+    # activation gradient + tanh
+    dz = k.gemm(a, b, aux_in=z.contiguous(), dact=k.ACT_GELU, tile_n=tile_n)
+    zf = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).sum().backward()
+    ref = (a.float() @ b.float().t()) * zf.grad
+    assert (dz.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+    t = k.gemm(a, b, bias=bias, act=k.ACT_TANH, tile_n=tile_n)
+    tref = torch.tanh(a.float() @ b.float().t() + bias)
+    assert (t.float() - tref).abs().max().item() <= 1e-2
+    # accumulate into bf16
+    acc = torch.ones(M, N, device=cuda_device, dtype=torch.bfloat16)
+    k.gemm(a, b, out=acc, accumulate=True, tile_n=tile_n)
+    ref = a.float() @ b.float().t() + 1.0
+    assert (acc.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_cta_pair_head_major(cuda_device):
+    """Head-major scattered output (decode cross-K/V layout) through the CTA-pair kernel's coalesced store."""
+    from vacnic_b200 import kernels as K
+    torch.manual_seed(2)
+    C, L, d, H = 2, 520, 256, 8
+    h = torch.randn(C, L, d, device=cuda_device).bfloat16()
+    w = (torch.randn(2 * H * 64, d, device=cuda_device) * 0.1).bfloat16()
+    bias = torch.randn(2 * H * 64, device=cuda_device)
+    ref = (h.float() @ w.float().t() + bias).view(C, L, 2, H, 64).permute(0, 2, 3, 1, 4)
+    for tn in (1256, 1128):
+        out = torch.zeros(C, 2, H, L, 64, device=cuda_device, dtype=torch.bfloat16)
+        K.gemm(h, w.unsqueeze(0).expand(C, -1, -1), out=out, bias=bias, head_major=(64, 2 * H * 64 * L, 0, L * 64), tile_n=tn)
+        assert (out.float() - ref).abs().max().item() <= 3e-2, tn
+
+
+def test_wgrad_k_slices_batched_matches(cuda_device):
+    """Weight gradient of a 1024 x 1024 projection over 16384 tokens: K-sliced batched CTA-pair GEMM + ordered partial
+    sum (blocks._wgrad) against fp32 torch; bit-reproducible; accumulates into an existing gradient."""
+    from vacnic_b200 import blocks, kernels as k
+    rows, n_out, k_in = 16384, 1024, 1024
+    s = blocks.wgrad_k_slices(rows, n_out, k_in, k.sm_count(cuda_device))
+    assert s == 4
+    dy = _mk((rows, 3 * n_out), cuda_device, 0.1, seed=41)[:, n_out:2 * n_out]   # a column slice: row pitch 3072
+    x = _mk((rows, k_in), cuda_device, 0.1, seed=42)
+    ref = dy.float().t() @ x.float()
+    outs = []
+    for _ in range(2):
+        part = torch.empty(s, n_out, k_in, dtype=torch.float32, device=cuda_device)
+        k.gemm(dy.view(s, rows // s, n_out), x.view(s, rows // s, k_in), out=part, a_mn=True, b_mn=True)
+        gw = torch.ones(n_out, k_in, device=cuda_device)
+        k.sum_partials(part.view(s, -1), gw, accumulate=True)
+        outs.append(gw)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0] - 1.0 - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()

@@ -53,9 +53,33 @@ def _ceil8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def wgrad_k_slices(rows: int, n_out: int, k_in: int, sms: int = 148) -> int:
+    """How many slices of the token dimension a weight gradient gw[n_out, k_in] = dy[rows, n_out]^T x[rows, k_in] is
+    cut into.  A long reduction (rows = B*L) with few 256 x 256 output tiles (the 1024 x 1024 projections: 16 tiles for
+    74 SM pairs) leaves most of the GPU idle; the slices run as the batch dimension of ONE CTA-pair GEMM into fp32
+    partials that `vacnic_sum_partials` adds in slice order (deterministic).  1 = no slicing."""
+    if rows < 8192 or n_out < 256 or k_in < 256:
+        return 1
+    tiles = ((n_out + 255) // 256) * ((k_in + 255) // 256)
+    pairs = sms // 2
+    if 2 * tiles > pairs:
+        return 1
+    s = min(pairs // tiles, 8)
+    while s > 1 and (rows % s != 0 or rows // s < 2048 or (rows // s) % 8 != 0):
+        s -= 1
+    return s
+
+
 def _wgrad(rt: Runtime, lin: Lin, dy2d: torch.Tensor, x2d: torch.Tensor, bias_from: Optional[torch.Tensor] = None):
     """gw (+)= dy^T x ; gb += colsum(dy)."""
-    K.gemm(dy2d, x2d, out=lin.gw, a_mn=True, b_mn=True, accumulate=rt.store.touch(lin.key))
+    rows, n_out, k_in = dy2d.shape[0], dy2d.shape[1], x2d.shape[1]
+    s = wgrad_k_slices(rows, n_out, k_in, K.sm_count(dy2d.device))
+    if s > 1:
+        part = torch.empty(s, n_out, k_in, dtype=torch.float32, device=dy2d.device)
+        K.gemm(dy2d.view(s, rows // s, n_out), x2d.view(s, rows // s, k_in), out=part, a_mn=True, b_mn=True)
+        K.sum_partials(part.view(s, n_out * k_in), lin.gw, accumulate=rt.store.touch(lin.key))
+    else:
+        K.gemm(dy2d, x2d, out=lin.gw, a_mn=True, b_mn=True, accumulate=rt.store.touch(lin.key))
     if lin.gb is not None and bias_from is not None:
         K.colsum_into(bias_from, lin.gb)
 

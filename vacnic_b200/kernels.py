@@ -27,6 +27,16 @@ def _gemm_workspace(device):
     return ws
 
 
+_SM_COUNT: dict = {}
+
+
+def sm_count(device) -> int:
+    n = _SM_COUNT.get(device.index)
+    if n is None:
+        n = _SM_COUNT[device.index] = torch.cuda.get_device_properties(device).multi_processor_count
+    return n
+
+
 def uses_pair_kernel(M: int, N: int, batch: int, tile_n: int = 0, sms: int = 148) -> bool:
     """Mirror of choose_pair_tile_n (csrc/gemm_sm100.cu): does vacnic_gemm route this problem to the CTA-pair kernel?"""
     if tile_n in (1128, 1256):
