@@ -458,9 +458,9 @@ def main():
         peak = pk["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "gemm2_sm100_kernel (CTA-pair tcgen05.mma.cta_group::2 / TMEM / TMA batched bf16 GEMM)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                # DRAM bytes of ONE representative launch (FFN fc1, 16384x4096x1024: 137 MB moved for 176 MB of algorithmic
-                # operand+result bytes, the rest stays in L2), profiles/r1_ncu_gemm_fwd_fc1.md
-                "traffic": 136.8e6 if not args.small else None, "peak_source": pk["_source"] + " sustained",
+                # DRAM bytes of ONE representative launch (FFN fc1 + GELU, 16384x4096x1024: 55.1 MB read + 105.3 MB written
+                # for 176 MB of algorithmic operand+result bytes, the rest stays in L2), profiles/r1_ncu_gemm2_fc1_gelu.md
+                "traffic": 160.4e6 if not args.small else None, "peak_source": pk["_source"] + " sustained",
                 "launches_per_step": len(big), "kernel_ms_per_step": gms, "kernel_tflop_per_step": gf / 1e12,
                 "kernel_share_of_step": gms / (ms_dev / args.steps),
                 # every vacnic_gemm launch of the step (skinny side-branch / decoder GEMMs included; eager pass, so the

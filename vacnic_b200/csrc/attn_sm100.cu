@@ -52,9 +52,6 @@ struct AttnSmem {
   float xch[2][2][128];      // [block parity][column half][row]: block maxima / final row sums exchanged between halves
 };
 
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -356,11 +353,6 @@ struct BwdSmem {
   uint8_t blk_flag[2 * kMaxKB];  // dq kernel: per 64-key block, 1 = per-key mask checks needed
 };
 
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 u;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
-  return u;
-}
 __device__ __forceinline__ void store_row64(__nv_bfloat16* op, const uint32_t (&o0)[32], const uint32_t (&o1)[32], float f) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {

@@ -222,7 +222,8 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int half = (warp - 2) >> 2;
     float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes) +
                    (warp - 2) * (BN / 2);
-    uint8_t* sstore = smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + Cfg::kBiasBytes + (warp - 2) * (32 * 64);
+    const uint32_t sstore =
+        smem_u32(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + Cfg::kBiasBytes + (warp - 2) * (32 * 64));
     constexpr int kChunks = BN / 64;  // 32-column chunks per warp
     const bool has_bias = g.bias != nullptr;
     uint32_t it = 0;

@@ -241,20 +241,21 @@ __device__ __forceinline__ void epilogue_row_chunk(const GemmArgs& g, float (&v)
 // STG.128 covers 8 rows x 64 contiguous bytes (8 fully written sector pairs) instead of 32 rows x 16 bytes (32
 // half-written sectors) -- 4x fewer LSU / L2 requests for the same bytes.  `p0` = address of (row of lane 0,
 // first column of the chunk); rows >= rows_valid are not written.  All 32 lanes must call.
-__device__ __forceinline__ void store_chunk_bf16_coalesced(uint8_t* stage, int lane, const float (&v)[32],
+__device__ __forceinline__ void store_chunk_bf16_coalesced(uint32_t stage, int lane, const float (&v)[32],
                                                            __nv_bfloat16* p0, long long ld, int rows_valid) {
   uint4 u[4];
   pack_chunk_bf16(v, u);
-  const int sw = (lane >> 1) & 3;
+  const uint32_t sw = static_cast<uint32_t>(lane >> 1) & 3u;
+  const uint32_t wr = stage + static_cast<uint32_t>(lane) * 64u;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ sw) << 4)) = u[q];
+  for (uint32_t q = 0; q < 4; ++q) st_shared_v4(wr + ((q ^ sw) << 4), u[q].x, u[q].y, u[q].z, u[q].w);
   __syncwarp();
-  const int q = lane & 3;
+  const uint32_t q = static_cast<uint32_t>(lane) & 3u;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int r = 8 * j + (lane >> 2);
-    const uint4 w = *reinterpret_cast<const uint4*>(stage + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
-    if (r < rows_valid) *reinterpret_cast<uint4*>(p0 + static_cast<long long>(r) * ld + q * 8) = w;
+    const uint4 w = ld_shared_v4(stage + static_cast<uint32_t>(r) * 64u + ((q ^ (static_cast<uint32_t>(r >> 1) & 3u)) << 4));
+    if (r < rows_valid) st_global_v4(p0 + static_cast<long long>(r) * ld + q * 8, w);
   }
   __syncwarp();
 }

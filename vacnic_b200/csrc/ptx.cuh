@@ -174,6 +174,20 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
          | (static_cast<uint32_t>(m >> 4) << 24);    // m_dim
 }
 
+// ---------------------------------------------------------------- shared-space vector access (32-bit addresses)
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+  return u;
+}
+
+__device__ __forceinline__ void st_global_v4(void* p, const uint4& u) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
 // ---------------------------------------------------------------- math
 // erf for the GELU epilogues of the FFN GEMMs, which run once per output element on two warps per scheduler and
 // must hide behind the tile's main loop: Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution)
