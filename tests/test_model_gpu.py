@@ -144,3 +144,22 @@ def test_losses_and_gradients_match_oracle(cuda_device, path):
             denom = gs.norm().item() * got.norm().item() + 1e-30
             assert (gs @ got).item() / denom >= 0.99, k
         assert abs(full.norm().item() - fx["grad_norms"][k]) <= 5e-2 * fx["grad_norms"][k] + 1e-6, k
+
+
+def test_accuracy_next_to_reference_bf16_modes(cuda_device):
+    """The GPU-side comparator of SURVEY.md §8d: logit error against the fp32 oracle of (a) this implementation,
+    (b) the reference arithmetic under torch.autocast(bfloat16) and (c) the reference arithmetic entirely in bf16
+    (model.bfloat16()), on the same device, weights and config-1 inputs (BART-base, B=2, L=512, T=40).
+    Measured on B200: ours 0.024 max / 0.0034 mean, autocast 0.0145 / 0.0022, full bf16 0.039 / 0.0057 (BART-large, L=1024:
+    0.030 / 0.0046, 0.028 / 0.0039, 0.051 / 0.0081).  Asserted: strictly more accurate than the reference's own full-bf16
+    mode, and within 2x of its autocast mode (which keeps the residual stream and LayerNorm inputs in fp32)."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "accuracy_report.py")
+    s = importlib.util.spec_from_file_location("accuracy_report", path)
+    mod = importlib.util.module_from_spec(s)
+    s.loader.exec_module(mod)
+    r = mod.report(spec.bart_base(), cuda_device, B=2, L=512, T=40)
+    ours, ac, b16 = r["ours"], r["ref_autocast"], r["ref_bf16"]
+    assert ours["max_abs"] <= 0.85 * b16["max_abs"] and ours["mean_abs"] <= 0.85 * b16["mean_abs"], r
+    assert ours["max_abs"] <= 2.0 * ac["max_abs"] and ours["mean_abs"] <= 2.0 * ac["mean_abs"], r
+    assert ours["max_abs"] <= 3e-2, r
