@@ -52,6 +52,15 @@ struct AttnSmem {
   float xch[2][2][128];      // [block parity][column half][row]: block maxima / final row sums exchanged between halves
 };
 
+// named barrier 2 + quad over the two softmax warps (column halves) that own the same 32 query rows
+__device__ __forceinline__ void pair_bar_sync(int quad) {  // immediate ids: ptxas reserves only the barriers named
+  switch (quad) {
+    case 0: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+  }
+}
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -103,15 +112,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_relinquish();
   }
   if (warp >= 2) {
-    // classify the key blocks once: does any key of the block need a mask decision?
-    for (int j = threadIdx.x - 64; j < nkb; j += kCompThreads) {
+    // classify the key blocks once: does any key of the block need a mask decision?  Geometry first, then the mask
+    // bytes in 16-key segments spread over all 256 threads (one thread scanning a block's 128 bytes kept the whole
+    // CTA at the barrier below for ~10 % of its life, profiles/r1_ncu_attention_encoder_shape.md)
+    const int tid = static_cast<int>(threadIdx.x) - 64;
+    for (int j = tid; j < nkb; j += kCompThreads) {
       const int k0 = j * kAK;
-      bool need = (k0 + kAK > a.Sk) || (a.causal && k0 + kAK - 1 > q0);
-      if (!need && a.key_mask != nullptr) {
-        const uint8_t* mk = a.key_mask + static_cast<long long>(b) * a.Sk + k0;
-        for (int c = 0; c < kAK; ++c) need |= (mk[c] == 0);
+      sh->blk_flag[j] = ((k0 + kAK > a.Sk) || (a.causal && k0 + kAK - 1 > q0)) ? 1 : 0;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (a.key_mask != nullptr) {
+      const uint8_t* mk = a.key_mask + static_cast<long long>(b) * a.Sk;
+      const int kend = min(nkb * kAK, a.Sk);
+      for (int k = tid * 16; k < kend; k += kCompThreads * 16) {
+        bool z = false;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) z |= (k + c < kend) && (mk[k + c] == 0);
+        if (z) sh->blk_flag[k / kAK] = 1;  // racing writers all store 1
       }
-      sh->blk_flag[j] = need ? 1 : 0;
     }
   }
   tc_fence_before();
@@ -230,7 +248,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         bm = fmaxf(bm, fmaxf(t0, t1));
       }
       sh->xch[j & 1][half][r] = bm;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      pair_bar_sync(quad);  // only the two warps that share these 32 rows exchange maxima
       bm = fmaxf(bm, sh->xch[j & 1][half ^ 1][r]);
       // reference maximum: fixed by block 0, raised later only where a row's block maximum exceeds it by more than 2^8
       // (both halves of a row see the same maxima, so they agree)
@@ -285,9 +303,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor pipe (async proxy)
       mbar_arrive(&sh->p_full);
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    pair_bar_sync(quad);
     sh->xch[0][half][r] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    pair_bar_sync(quad);
     l += sh->xch[0][half ^ 1][r];
     // ---- epilogue: O / l -> bf16 (each half stores 32 of the 64 head-dim columns)
     mbar_wait(&sh->o_full, 0);
@@ -498,13 +516,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint8_t* mk = a.key_mask ? a.key_mask + static_cast<long long>(b) * a.Sk : nullptr;
     const float c2 = a.scale_log2;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    // classify the 64-key blocks: does any key need a mask decision?
-    for (int j = threadIdx.x - 64; j < nkb; j += kCompThreads) {
-      const int kb0 = j * 64;
-      bool need = (kb0 + 64 > a.Sk) || (a.causal && kb0 + 63 > q0);
-      if (!need && mk != nullptr)
-        for (int c = 0; c < 64; ++c) need |= (mk[kb0 + c] == 0);
-      sh->blk_flag[j] = need ? 1 : 0;
+    // classify the 64-key blocks: does any key need a mask decision?  (geometry, then the mask bytes in 16-key
+    // segments over all 256 threads)
+    {
+      const int tid = static_cast<int>(threadIdx.x) - 64;
+      for (int j = tid; j < nkb; j += kCompThreads) {
+        const int kb0 = j * 64;
+        sh->blk_flag[j] = ((kb0 + 64 > a.Sk) || (a.causal && kb0 + 63 > q0)) ? 1 : 0;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (mk != nullptr) {
+        const int kend = min(nkb * 64, a.Sk);
+        for (int k = tid * 16; k < kend; k += kCompThreads * 16) {
+          bool z = false;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) z |= (k + c < kend) && (mk[k + c] == 0);
+          if (z) sh->blk_flag[k / 64] = 1;
+        }
+      }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     // ---- delta = rowsum(dO * O) (both column halves compute it; half 0 stores it)
@@ -698,18 +727,26 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     const uint32_t pt_row = smem_u32(sPT) + r * 128, dst_row = smem_u32(sDST) + r * 128;
     const long long sbase = (static_cast<long long>(b) * a.H + h) * a.Sq;
+    // row statistics of a 64-query block (threads 0..63): {reference max, 1/row sum, delta, scale/row sum}
+    auto load_stat = [&](int i) -> float4 {
+      const int qrow = i * 64 + tid;
+      float4 st = make_float4(0.f, 0.f, 0.f, 0.f);  // query rows beyond Sq: 1/sum = 0 -> p = 0
+      if (qrow < a.Sq) {
+        const float2 s2 = reinterpret_cast<const float2*>(a.stats)[sbase + qrow];
+        st = make_float4(s2.x, s2.y, a.delta[sbase + qrow], s2.y * a.scale);
+      }
+      return st;
+    };
+    float4 st_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 64 && i0 < nqb) st_next = load_stat(i0);
     for (int i = i0, n = 0; i < nqb; ++i, ++n) {
       // stage the row statistics of the 64 queries of this block (double buffered: buffer n&1 was last read in
-      // step n-2, which every thread finished before passing the named barrier of step n-1)
+      // step n-2, which every thread finished before passing the named barrier of step n-1).  The global loads
+      // were issued one block ahead, so the barrier below no longer waits for a DRAM / L2 round trip.
       float4* stq = sh->stat[n & 1];
       if (tid < 64) {
-        const int qrow = i * 64 + tid;
-        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);  // query rows beyond Sq: 1/sum = 0 -> p = 0
-        if (qrow < a.Sq) {
-          const float2 s2 = reinterpret_cast<const float2*>(a.stats)[sbase + qrow];
-          st = make_float4(s2.x, s2.y, a.delta[sbase + qrow], s2.y * a.scale);
-        }
-        stq[tid] = st;
+        stq[tid] = st_next;
+        if (i + 1 < nqb) st_next = load_stat(i + 1);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&sh->sdp_full, n & 1u);
