@@ -81,6 +81,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * kAQ;
+  pdl_sync();  // key_len / key_mask below are global reads
 
   // number of key blocks that can contribute
   int kmax = a.Sk;
@@ -442,6 +443,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  pdl_sync();  // key_len / key_mask / stats below are global reads
   const int q0 = qb * kAQ;
   int kmax = a.Sk;
   if (a.key_len != nullptr) {
@@ -635,6 +637,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  pdl_sync();  // key_len / key_mask / stats below are global reads
   const int k0 = kb * kAK;
   const int kl = a.key_len != nullptr ? a.key_len[b] : 0;
   if (kl > 0 && k0 >= kl) {
@@ -864,7 +867,7 @@ extern "C" int vacnic_attn_fwd(const vacnic_attn_desc* d, void* stream) {
     configured = true;
   }
   const dim3 grid((d->Sq + kAQ - 1) / kAQ, d->H, d->B);
-  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+  launch_pdl(attn_fwd_kernel, grid, dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, a);
   count_launch();
   return check_last("attn_fwd launch");
 }
@@ -910,11 +913,13 @@ extern "C" int vacnic_attn_bwd(const vacnic_attn_desc* d, void* stream) {
     configured = true;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  attn_bwd_dq_kernel<<<dim3((d->Sq + kAQ - 1) / kAQ, d->H, d->B), kAttnThreads, kBwdDqSmemBytes, s>>>(q128, k64, v64, do128, o128, a);
+  launch_pdl(attn_bwd_dq_kernel, dim3((d->Sq + kAQ - 1) / kAQ, d->H, d->B), dim3(kAttnThreads), kBwdDqSmemBytes, s, q128, k64,
+             v64, do128, o128, a);
   count_launch();
   rc = check_last("attn_bwd dq launch");
   if (rc != VACNIC_OK) return rc;
-  attn_bwd_dkv_kernel<<<dim3((d->Sk + kAK - 1) / kAK, d->H, d->B), kAttnThreads, kBwdDkvSmemBytes, s>>>(q64, k128, v128, do64, a);
+  launch_pdl(attn_bwd_dkv_kernel, dim3((d->Sk + kAK - 1) / kAK, d->H, d->B), dim3(kAttnThreads), kBwdDkvSmemBytes, s, q64, k128,
+             v128, do64, a);
   count_launch();
   return check_last("attn_bwd dkv launch");
 }

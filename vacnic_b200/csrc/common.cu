@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace vb {
@@ -36,6 +37,14 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VACNIC_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 int check_last(const char* what) {

@@ -37,6 +37,7 @@ decode_embed_ln_kernel(const int32_t* __restrict__ seq, const int32_t* __restric
                        const __nv_bfloat16* __restrict__ tok, const __nv_bfloat16* __restrict__ pos,
                        const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                        int R, int maxT, int d, int pos_offset, int pingpong, float eps) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -94,6 +95,7 @@ decode_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
                         __nv_bfloat16* __restrict__ vcache, const int32_t* __restrict__ anc,
                         const int32_t* __restrict__ cur_len_p, __nv_bfloat16* __restrict__ out, int R, int maxT, int d,
                         float scale) {
+  pdl_sync();
   const int h = blockIdx.x, r = blockIdx.y, j = threadIdx.x;
   const int t = *cur_len_p;
   const int pos = t - 1;
@@ -196,6 +198,7 @@ decode_cross_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
                              const __nv_bfloat16* __restrict__ vp, long long ldkv, long long kv_hs, long long kv_cs,
                              const uint8_t* __restrict__ key_mask, const int32_t* __restrict__ key_len,
                              __nv_bfloat16* __restrict__ out, long long ldo, int nq, int L, float scale) {
+  pdl_sync();
   extern __shared__ __align__(128) uint8_t xsm[];
   float* sc = reinterpret_cast<float*>(xsm + 4 * kXWarpRing);  // [nq][Lp]
   float* red = reinterpret_cast<float*>(xsm);                  // [4][64][8] partial O^T, aliases the rings after pass 2
@@ -402,6 +405,7 @@ constexpr int kTopThreads = 1024;
 __global__ void __launch_bounds__(kTopThreads)
 decode_topk_kernel(const float* __restrict__ logits, long long ld, int V, int K, float* __restrict__ top_lp,
                    int32_t* __restrict__ top_idx) {
+  pdl_sync();
   extern __shared__ float row[];  // [V]
   __shared__ float redf[32];
   __shared__ float bc_f;
@@ -528,6 +532,7 @@ struct BeamArgs {
 
 
 __global__ void __launch_bounds__(128) beam_step_kernel(const BeamArgs a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int c = blockIdx.x * 4 + wib;
   __shared__ float s_lp[4][kMaxCand];
@@ -688,6 +693,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const BeamArgs a) {
 __global__ void greedy_step_kernel(const int32_t* __restrict__ top_idx, int32_t* __restrict__ seq,
                                    uint8_t* __restrict__ unfinished, int32_t* __restrict__ flags,
                                    const int32_t* __restrict__ cur_len_p, int R, int maxT, int max_len, int eos, int pad) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   const int t = *cur_len_p;
@@ -701,7 +707,10 @@ __global__ void greedy_step_kernel(const int32_t* __restrict__ top_idx, int32_t*
   atomicOr(flags + 2 * t + 1, 1);
 }
 
-__global__ void advance_len_kernel(int32_t* cur_len_p) { *cur_len_p += 1; }
+__global__ void advance_len_kernel(int32_t* cur_len_p) {
+  pdl_sync();
+  *cur_len_p += 1;
+}
 
 }  // namespace vb
 
@@ -718,10 +727,10 @@ extern "C" int vacnic_decode_embed_ln(const int32_t* seq, const int32_t* cur_len
   const __nv_bfloat16* ps = static_cast<const __nv_bfloat16*>(pos);
   __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
   switch (d / 256) {
-    case 1: decode_embed_ln_kernel<1><<<grid, 256, 0, s>>>(seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
-    case 2: decode_embed_ln_kernel<2><<<grid, 256, 0, s>>>(seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
-    case 3: decode_embed_ln_kernel<3><<<grid, 256, 0, s>>>(seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
-    default: decode_embed_ln_kernel<4><<<grid, 256, 0, s>>>(seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
+    case 1: launch_pdl(decode_embed_ln_kernel<1>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
+    case 2: launch_pdl(decode_embed_ln_kernel<2>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
+    case 3: launch_pdl(decode_embed_ln_kernel<3>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
+    default: launch_pdl(decode_embed_ln_kernel<4>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
   }
   count_launch();
   return check_last("decode_embed_ln");
@@ -734,9 +743,7 @@ extern "C" int vacnic_decode_self_attn(const void* qkv, void* kcache, void* vcac
   VB_REQUIRE(head_dim == 64, "decode_self_attn: head_dim must be 64 (BART-base / BART-large)");
   VB_REQUIRE(R > 0 && H > 0 && maxT > 0 && maxT <= kMaxT, "decode_self_attn: maxT must be in 1..%d", kMaxT);
   const int d = H * head_dim;
-  decode_self_attn_kernel<<<dim3(H, R), 64, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(kcache), static_cast<__nv_bfloat16*>(vcache),
-      anc, cur_len, static_cast<__nv_bfloat16*>(out), R, maxT, d, 1.0f / sqrtf(static_cast<float>(head_dim)));
+  launch_pdl(decode_self_attn_kernel, dim3(H, R), dim3(64), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(kcache), static_cast<__nv_bfloat16*>(vcache), anc, cur_len, static_cast<__nv_bfloat16*>(out), R, maxT, d, 1.0f / sqrtf(static_cast<float>(head_dim)));
   count_launch();
   return check_last("decode_self_attn");
 }
@@ -764,9 +771,7 @@ extern "C" int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* 
       configured = smem;
     }
     VB_REQUIRE(smem <= 200 * 1024, "decode_cross_attn: nq * L too large for the shared-memory score buffer");
-    decode_cross_attn_mma_kernel<<<dim3(H, captions), 128, smem, s>>>(
-        static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), ldkv,
-        kv_hs, kv_cs, key_mask, key_len, static_cast<__nv_bfloat16*>(out), ldo, nq, L, scale);
+    launch_pdl(decode_cross_attn_mma_kernel, dim3(H, captions), dim3(128), smem, s, static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), ldkv, kv_hs, kv_cs, key_mask, key_len, static_cast<__nv_bfloat16*>(out), ldo, nq, L, scale);
     count_launch();
     return check_last("decode_cross_attn");
   }
@@ -791,7 +796,7 @@ extern "C" int vacnic_decode_topk(const float* logits, int64_t ld, int32_t rows,
     if (e != cudaSuccess) return fail(VACNIC_ECUDA, "decode_topk: smem %zu: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  decode_topk_kernel<<<rows, kTopThreads, smem, static_cast<cudaStream_t>(stream)>>>(logits, ld, V, K, top_lp, top_idx);
+  launch_pdl(decode_topk_kernel, dim3(rows), dim3(kTopThreads), smem, static_cast<cudaStream_t>(stream), logits, ld, V, K, top_lp, top_idx);
   count_launch();
   return check_last("decode_topk");
 }
@@ -811,7 +816,7 @@ extern "C" int vacnic_beam_step(const float* top_lp, const int32_t* top_idx, int
   a.flags = flags; a.cur_len_p = cur_len;
   a.C = captions; a.nb = beams; a.K = 2 * beams; a.maxT = maxT; a.max_len = max_len; a.eos = eos; a.V = V;
   a.length_penalty = length_penalty;
-  beam_step_kernel<<<(captions + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(beam_step_kernel, dim3((captions + 3) / 4), dim3(128), 0, static_cast<cudaStream_t>(stream), a);
   count_launch();
   return check_last("beam_step");
 }
@@ -821,15 +826,14 @@ extern "C" int vacnic_greedy_step(const int32_t* top_idx, int32_t* seq, uint8_t*
                                   int32_t pad, void* stream) {
   VB_REQUIRE(top_idx && seq && unfinished && flags && cur_len, "greedy_step: null pointer");
   VB_REQUIRE(rows > 0 && max_len >= 2 && max_len <= maxT, "greedy_step: bad shape");
-  greedy_step_kernel<<<(rows + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(top_idx, seq, unfinished, flags,
-                                                                                       cur_len, rows, maxT, max_len, eos, pad);
+  launch_pdl(greedy_step_kernel, dim3((rows + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), top_idx, seq, unfinished, flags, cur_len, rows, maxT, max_len, eos, pad);
   count_launch();
   return check_last("greedy_step");
 }
 
 extern "C" int vacnic_advance_len(int32_t* cur_len, void* stream) {
   VB_REQUIRE(cur_len, "advance_len: null pointer");
-  advance_len_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(cur_len);
+  launch_pdl(advance_len_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), cur_len);
   count_launch();
   return check_last("advance_len");
 }

@@ -10,6 +10,7 @@ namespace vb {
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int n, long long ld,
               int rows_per_block) {
+  pdl_sync();
   const int c0 = blockIdx.x * 256 + (threadIdx.x & 31) * 8;
   const int wr = threadIdx.x >> 5;  // 8 warps walk rows
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
@@ -107,6 +108,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 __global__ void __launch_bounds__(256)
 add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                 const __nv_bfloat16* __restrict__ c, __nv_bfloat16* __restrict__ out, long long n) {
+  pdl_sync();
   const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const uint4 ua = *reinterpret_cast<const uint4*>(a + i);
@@ -134,6 +136,7 @@ add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256)
 concat_rows_kernel(const uint4* __restrict__ a, const uint4* __restrict__ c, uint4* __restrict__ out, int B,
                    long long va, long long vc) {
+  pdl_sync();
   const long long per = va + vc;
   const long long n = per * B;
   for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
@@ -149,6 +152,7 @@ __global__ void rng_advance_kernel(unsigned long long* state) { *state += 0x9E37
 // read them (the NER-map gradient dz2 has 20-element = 40-byte rows)
 __global__ void __launch_bounds__(256)
 pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int n, int ld_dst) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= rows * ld_dst) return;
   const long long r = i / ld_dst;
@@ -217,6 +221,7 @@ cast_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
 // dst[j] (+)= sum_p src[p, j]: reduction of split-K partial weight gradients (fp32)
 __global__ void __launch_bounds__(256)
 sum_partials_kernel(const float* __restrict__ src, float* __restrict__ dst, int parts, long long len, int accumulate) {
+  pdl_sync();
   const long long j = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (j >= len) return;
   float s = accumulate ? dst[j] : 0.f;
@@ -239,8 +244,7 @@ extern "C" int vacnic_colsum(const void* x, float* out, int64_t rows, int32_t n,
   if (slabs < 1) slabs = 1;
   const int rpb = static_cast<int>((rows + slabs - 1) / slabs);
   dim3 grid(col_tiles, static_cast<unsigned>((rows + rpb - 1) / rpb));
-  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), out, rows,
-                                                                    n, ld, rpb);
+  launch_pdl(colsum_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), out, rows, n, ld, rpb);
   count_launch();
   return check_last("colsum");
 }
@@ -277,9 +281,7 @@ extern "C" int vacnic_add_bf16(const void* a, const void* b, const void* c, void
                reinterpret_cast<uintptr_t>(out)) & 15) == 0, "add_bf16: buffers must be 16-byte aligned");
   if (n <= 0) return VACNIC_OK;
   const long long blocks = (n + 2047) / 2048;
-  add_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b),
-      static_cast<const __nv_bfloat16*>(c), static_cast<__nv_bfloat16*>(out), n);
+  launch_pdl(add_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<const __nv_bfloat16*>(c), static_cast<__nv_bfloat16*>(out), n);
   count_launch();
   return check_last("add_bf16");
 }
@@ -293,8 +295,7 @@ extern "C" int vacnic_concat_rows(const void* a, const void* b, void* out, int32
   if (n == 0) return VACNIC_OK;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  concat_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), B, va, vc);
+  launch_pdl(concat_rows_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), B, va, vc);
   count_launch();
   return check_last("concat_rows");
 }
@@ -309,16 +310,14 @@ extern "C" int vacnic_rng_advance(uint64_t* state, void* stream) {
 extern "C" int vacnic_pad_rows(const void* src, void* dst, int64_t rows, int32_t n, int32_t ld_dst, void* stream) {
   VB_REQUIRE(src && dst && rows > 0 && n > 0 && ld_dst >= n, "pad_rows: bad arguments");
   const long long total = rows * ld_dst;
-  pad_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, n, ld_dst);
+  launch_pdl(pad_rows_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, n, ld_dst);
   count_launch();
   return check_last("pad_rows");
 }
 
 extern "C" int vacnic_sum_partials(const float* src, float* dst, int32_t parts, int64_t len, int32_t accumulate, void* stream) {
   VB_REQUIRE(src && dst && parts > 0 && len > 0, "sum_partials: bad arguments");
-  sum_partials_kernel<<<static_cast<unsigned>((len + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, parts, len,
-                                                                                                          accumulate);
+  launch_pdl(sum_partials_kernel, dim3(static_cast<unsigned>((len + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, dst, parts, len, accumulate);
   count_launch();
   return check_last("sum_partials");
 }

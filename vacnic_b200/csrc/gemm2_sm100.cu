@@ -137,6 +137,7 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // everything above is on-chip setup; operands, bias, aux and C are touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -327,7 +328,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   if (sms <= 0) return fail(VACNIC_EDEVICE, "gemm2: no CUDA device");
   const long long pairs = sms / 2;
   const int grid = 2 * static_cast<int>(g.total_tiles < pairs ? g.total_tiles : pairs);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, g);
+  launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, g);
   count_launch();
   return check_last("gemm2 launch");
 }

@@ -62,6 +62,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // on-chip setup above; global memory (operands, split-K workspace, bias, aux, C) only below
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -335,7 +336,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   if (sms <= 0) return fail(VACNIC_EDEVICE, "gemm: no CUDA device");
   const long long work = g.total_tiles * g.splits;
   const int grid = static_cast<int>(work < sms ? work : sms);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, g);
+  launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, g);
   count_launch();
   return check_last("gemm launch");
 }

@@ -80,6 +80,7 @@ __device__ __forceinline__ void ln_row_stats(float (&v)[VPL][8], int d, float ep
 
 template <int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(const LnArgs a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= a.rows) return;
@@ -152,6 +153,7 @@ struct LnBwdArgs {
 
 template <int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_bwd_kernel(const LnBwdArgs a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const bool drop = a.p_drop > 0.f;
@@ -501,7 +503,7 @@ extern "C" int vacnic_add_layernorm_fwd(const void* x, const void* res, const fl
   a.eps = eps; a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
   const int grid = static_cast<int>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  VB_DISPATCH_VPL(d, (add_layernorm_fwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(a)));
+  VB_DISPATCH_VPL(d, (launch_pdl(add_layernorm_fwd_kernel<VPL>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, a)));
   count_launch();
   return check_last("add_layernorm_fwd");
 }
@@ -528,7 +530,7 @@ extern "C" int vacnic_add_layernorm_bwd(const void* dy, const void* x, const voi
   a.accumulate_dsum = accumulate_dsum;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = bwd_grid(rows);
-  VB_DISPATCH_VPL(d, (add_layernorm_bwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(a)));
+  VB_DISPATCH_VPL(d, (launch_pdl(add_layernorm_bwd_kernel<VPL>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, a)));
   count_launch();
   return check_last("add_layernorm_bwd");
 }
