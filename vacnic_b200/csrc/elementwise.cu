@@ -17,16 +17,28 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
   const long long r1 = min(rows, r0 + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool vec = (c0 + 8 <= n) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  for (long long r = r0 + wr; r < r1; r += 8) {
-    const __nv_bfloat16* p = x + r * ld + c0;
-    if (vec) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-      float2 f;
-      f = unpack_bf16x2(u.x); acc[0] += f.x; acc[1] += f.y;
-      f = unpack_bf16x2(u.y); acc[2] += f.x; acc[3] += f.y;
-      f = unpack_bf16x2(u.z); acc[4] += f.x; acc[5] += f.y;
-      f = unpack_bf16x2(u.w); acc[6] += f.x; acc[7] += f.y;
-    } else {
+  auto add8 = [&](const uint4& u) {
+    float2 f;
+    f = unpack_bf16x2(u.x); acc[0] += f.x; acc[1] += f.y;
+    f = unpack_bf16x2(u.y); acc[2] += f.x; acc[3] += f.y;
+    f = unpack_bf16x2(u.z); acc[4] += f.x; acc[5] += f.y;
+    f = unpack_bf16x2(u.w); acc[6] += f.x; acc[7] += f.y;
+  };
+  long long r = r0 + wr;
+  if (vec) {
+    // four independent 16-byte loads in flight per thread (the one-load loop left HBM latency exposed)
+    for (; r + 24 < r1; r += 32) {
+      const __nv_bfloat16* p = x + r * ld + c0;
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(p));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(p + 8 * ld));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(p + 16 * ld));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(p + 24 * ld));
+      add8(u0); add8(u1); add8(u2); add8(u3);
+    }
+    for (; r < r1; r += 8) add8(__ldg(reinterpret_cast<const uint4*>(x + r * ld + c0)));
+  } else {
+    for (; r < r1; r += 8) {
+      const __nv_bfloat16* p = x + r * ld + c0;
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         if (c0 + e < n) acc[e] += __bfloat162float(p[e]);
@@ -239,7 +251,7 @@ extern "C" int vacnic_colsum(const void* x, float* out, int64_t rows, int32_t n,
   if (rows == 0) return VACNIC_OK;
   const int col_tiles = (n + 255) / 256;
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  long long slabs = (2LL * sms + col_tiles - 1) / col_tiles;
+  long long slabs = (4LL * sms + col_tiles - 1) / col_tiles;
   if (slabs > (rows + 63) / 64) slabs = (rows + 63) / 64;
   if (slabs < 1) slabs = 1;
   const int rpb = static_cast<int>((rows + slabs - 1) / slabs);
