@@ -237,16 +237,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&sh->s_empty);  // all of S_j is in registers: the tensor pipe may overwrite it
-      // scores in the log2 domain (masked), block maximum of this half
+      // block maximum of this half in the log2 domain.  Blocks that need mask decisions are scaled and masked in place
+      // (kk = 1 below); the others stay raw -- their scale rides on the FFMA in front of the exponential (kk = c2 > 0,
+      // so max(raw) * c2 == max(raw * c2)), as in the backward kernels
       float bm = -INFINITY;
+      const float kk = need ? 1.0f : c2;
+      if (need) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float t0 = __uint_as_float(x0[c]), t1 = __uint_as_float(x1[c]);
-        if (need) { t0 = masked(t0, kb + c); t1 = masked(t1, kb + 32 + c); }
-        else { t0 *= c2; t1 *= c2; }
-        x0[c] = __float_as_uint(t0);
-        x1[c] = __float_as_uint(t1);
-        bm = fmaxf(bm, fmaxf(t0, t1));
+        for (int c = 0; c < 32; ++c) {
+          const float t0 = masked(__uint_as_float(x0[c]), kb + c), t1 = masked(__uint_as_float(x1[c]), kb + 32 + c);
+          x0[c] = __float_as_uint(t0);
+          x1[c] = __float_as_uint(t1);
+          bm = fmaxf(bm, fmaxf(t0, t1));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) bm = fmaxf(bm, fmaxf(__uint_as_float(x0[c]), __uint_as_float(x1[c])));
+        bm *= c2;
       }
       sh->xch[j & 1][half][r] = bm;
       pair_bar_sync(quad);  // only the two warps that share these 32 rows exchange maxima
@@ -266,7 +273,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // exponentials in place (registers), before waiting for PV_{j-1}
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const float p0 = ex2f(__uint_as_float(x0[c]) - m), p1 = ex2f(__uint_as_float(x1[c]) - m);
+        const float p0 = ex2f(fmaf(__uint_as_float(x0[c]), kk, -m)), p1 = ex2f(fmaf(__uint_as_float(x1[c]), kk, -m));
         l += p0 + p1;
         x0[c] = __float_as_uint(p0);
         x1[c] = __float_as_uint(p1);
