@@ -3,7 +3,8 @@
 // B tile; the leader CTA issues one MMA (M = 256) that reads A and the B halves from both CTAs' shared memory
 // and writes 128 x BN fp32 accumulators into each CTA's TMEM.  Per SM this halves the B-operand shared-memory
 // traffic and footprint (more pipeline stages), which is what lifts the large K >= 1024 GEMMs of the VACNIC
-// step over the single-CTA kernel in gemm_sm100.cu (same epilogue, same descriptor semantics).
+// step over the single-CTA kernel in gemm_sm100.cu (same epilogue arithmetic and descriptor semantics; bf16 results
+// leave through a warp-cooperative coalesced store instead of thread-owns-row stores).
 //
 // Warp roles per CTA (320 threads): warp 0 TMA producer (own A rows + own B half, completing on the LEADER's
 // "full" barrier), warp 1 MMA issuer (leader only) + TMEM allocator, warps 2..9 epilogue (own 128 rows).
