@@ -12,6 +12,10 @@ KEYS = [
     ("dram__bytes_write.sum", "DRAM write"),
     ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput % of peak"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "TENSOR PIPE active % of peak (while SM active)"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % of peak (elapsed)"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak (gpu__dram_throughput)"),
+    ("sm__cycles_elapsed.avg.per_second", "SM clock during the capture"),
     ("sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe (hmma) active % of peak"),
     ("sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active", "tensor pipe inst % of peak"),
     ("sm__pipe_tensor_subpipe_umma_cycles_active.avg.pct_of_peak_sustained_active", "UMMA sub-pipe active % of peak"),
