@@ -59,3 +59,29 @@ def test_wgrad_k_slices_policy():
     for rows in (8192, 16384, 16704, 32768):
         s = wgrad_k_slices(rows, 1024, 1024)
         assert rows % s == 0 and (rows // s) % 8 == 0 and rows // s >= 2048
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The bench line committed under profiles/ (produced by `python bench.py` on a B200) carries every key of the
+    measurement contract: base keys, clocks, e2e with byte counts, gpu_launches, roofline and cpu_baseline objects."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "profiles", "r1_bench_default_n1.json")
+    d = json.loads(open(path).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"]))
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert d["gpu_launches"] > 0
+    # the secondary headline (beam-4 captions/s) rides on the same line
+    assert d["infer"]["metric"] == "beam4_captions_per_sec" and d["infer"]["roofline"]["bound"] == "hbm"
