@@ -84,3 +84,36 @@ def test_no_cpu_fallback():
     d.lda = d.ldb = d.ldc = 64
     assert L.vacnic_gemm(C.byref(d), None) == -2
     assert spec.bart_large().d_model == 1024
+
+
+def test_every_pdl_launched_kernel_waits_before_touching_memory():
+    """Static guard for programmatic dependent launch (csrc/common.h): a kernel launched through launch_pdl may start
+    while its predecessor is still running, so its body must execute pdl_sync() (griddepcontrol.wait + trigger); a
+    kernel that is launched with the attribute but never waits would race silently."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vacnic_b200", "csrc")
+    src = {p: open(p).read() for p in glob.glob(os.path.join(root, "*.cu"))}
+    launched = set()
+    for text in src.values():
+        for m in re.finditer(r"launch_pdl\(\s*([A-Za-z_0-9]+)", text):
+            launched.add(m.group(1))
+    launched.discard("kernel")  # the helper's own parameter name
+    launched.discard("kern")    # GEMM launchers pass a function pointer variable: checked by name below
+    launched |= {"gemm_sm100_kernel", "gemm2_sm100_kernel"}
+    assert len(launched) >= 15, launched
+    for name in sorted(launched):
+        body = None
+        for text in src.values():
+            m = re.search(r"__global__[^;{]*?\b" + re.escape(name) + r"\s*\([^;{]*?\)\s*\{", text, re.S)
+            if m:
+                # body = up to the next kernel definition (or end of file)
+                nxt = text.find("__global__", m.end())
+                body = text[m.end(): nxt if nxt != -1 else len(text)]
+                break
+        assert body is not None, f"definition of {name} not found"
+        assert "pdl_sync()" in body, f"{name} is launched with the PDL attribute but never calls pdl_sync()"
+        # nothing that dereferences global memory may precede the wait: the first statement region up to pdl_sync()
+        head = body[: body.index("pdl_sync()")]
+        assert "__ldg" not in head and "tma_load" not in head and "atomicAdd" not in head, name
