@@ -177,6 +177,12 @@ int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int6
  * {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}; also refreshes the bf16
  * compute shadow p16 (may be null). */
 int vacnic_adamw(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const float* hyper, void* stream);
+/* Device-side optimizer step counter + schedule (get_linear_schedule_with_warmup TRAIN:102, scheduler.step() after
+ * optimizer.step() TRAIN:371-374; Adam bias corrections of torch.optim.AdamW TRAIN:95-101): *step += 1 (t), then hyper =
+ * {base_lr * multiplier(t-1), beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}.  Runs inside the captured
+ * step graph, so no host buffer is read asynchronously. */
+int vacnic_optim_schedule(int64_t* step, float* hyper, double base_lr, double beta1, double beta2, float eps, float weight_decay,
+                          int64_t warmup_steps, int64_t total_steps, float grad_scale, void* stream);
 /* clip_grad_norm_ (TRAIN:365-366) folded into the optimizer: *scale_out = base_scale * min(1, max_norm / (|base_scale| *
  * ||g||_2 + 1e-6)); write it to hyper[7] of vacnic_adamw.  scratch: VACNIC_CLIP_SCRATCH_FLOATS device floats (per-block
  * partial sums, reduced in a fixed order: the norm is bit-reproducible). */

@@ -352,3 +352,37 @@ def test_attn_bwd_matches_torch_autograd(cuda_device, B, H, Sq, Sk, causal, mask
         assert err <= 3e-2 * scale + 2e-3, (name, err, scale)
         cos = torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0).item()
         assert cos >= 0.999, (name, cos)
+
+
+def test_ner_map_block_applies_the_reference_dropout(cuda_device):
+    """MFULL:685-687: dropout sits between ner_map_down and the reshape + ner_map_layer_norm.  With res = None the
+    LayerNorm kernel is y = LN(dropout(z)): the mask the backward pass rebuilds is the one the forward pass applied,
+    the drop rate is p, and NerMapFn uses it in training mode only."""
+    from vacnic_b200 import blocks as Bk, kernels as k, spec
+    from vacnic_b200.modeling import VacnicBart
+    d, rows, p = 1024, 2048, 0.25
+    gamma = torch.ones(d, device=cuda_device); beta = torch.zeros(d, device=cuda_device)
+    rng = k.Rng(cuda_device, seed=5)
+    z = torch.ones(rows, d, dtype=torch.bfloat16, device=cuda_device)        # dropout(1) in {0, 1/(1-p)}: LN output sign = mask
+    y, mean, rstd = k.add_layernorm_fwd(z, None, gamma, beta, p_drop=p, rng=rng, salt=3)
+    kept_fwd = y.float() > 0
+    assert abs((~kept_fwd).float().mean().item() - p) < 0.01
+    dg = torch.zeros(d, device=cuda_device); db = torch.zeros(d, device=cuda_device)
+    dy = rnd((rows, d), cuda_device, 1.0, 9)
+    _, dx = k.add_layernorm_bwd(dy, z, None, gamma, mean, rstd, dg, db, want_dx=True, p_drop=p, rng=rng, salt=3)
+    assert torch.equal(dx != 0, kept_fwd) or ((dx != 0) ^ kept_fwd).float().mean().item() < 1e-4   # (a kept gradient may round to 0)
+    # block level: training mode drops, eval mode does not
+    cfg = spec.VacnicConfig(d_model=768, heads=12, ffn=1024, enc_layers=1, dec_layers=1, prompt_size=4, max_pos=128)
+    m = VacnicBart(cfg, device=cuda_device, p_drop=0.5, seed=1)
+    layer = m.model.encoder.layers[0]
+    ner = rnd((2, 80, 768), cuda_device, 1.0, 4)
+    outs = {}
+    for mode in (False, True):
+        m.rt.training = mode
+        with torch.no_grad():
+            outs[mode] = Bk.NerMapFn.apply(ner, m.rt, layer.lin_nup, layer.lin_ndown, layer.ln_nmap).float()
+    m.rt.training = False
+    with torch.no_grad():
+        again = Bk.NerMapFn.apply(ner, m.rt, layer.lin_nup, layer.lin_ndown, layer.ln_nmap).float()
+    assert torch.equal(outs[False], again)
+    assert (outs[True] - outs[False]).abs().mean().item() > 0.1

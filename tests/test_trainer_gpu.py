@@ -77,3 +77,55 @@ def test_step_matches_torch_optimizer_and_graph_equals_eager(cuda_device, max_gr
         for k in b:
             assert abs(a[k] - b[k]) <= 3e-2 * max(1.0, abs(b[k])), (k, le, ol)
     assert le[2]["txt"] < le[0]["txt"]  # the optimizer is actually applied
+
+
+def test_steps_enqueued_without_sync_equal_steps_synced_every_time(cuda_device):
+    """The host may run any number of graph replays ahead: step counter, warm-up learning rate and Adam bias corrections
+    live on the device (vacnic_optim_schedule), so N unsynchronised steps give bit-for-bit the schedule of N synchronised
+    ones (round-1 advisor finding: a re-used pinned host buffer was overwritten before the async copy ran)."""
+    from vacnic_b200.trainer import TrainStep, linear_schedule
+    batch = synthetic.make_batch(B=2, L=40, T=12, seed=9)
+    outs = []
+    for sync in (True, False):
+        cfg, gcfg, sd, gsd, m, g = _models(cuda_device)
+        ts = TrainStep(m, g, lr=1e-3, weight_decay=0.01, warmup_steps=6, total_steps=20, use_graph=True)
+        devb = {k: v.to(cuda_device) for k, v in TrainStep.prepare(batch, cfg).items()}
+        hyper_seen = []
+        for i in range(8):
+            ts.step(devb, prepared=True)
+            if sync:
+                torch.cuda.synchronize()
+                hyper_seen.append(ts.hyper.cpu().clone())
+        torch.cuda.synchronize()
+        outs.append((ts.hyper.cpu().clone(), int(ts.step_dev.item()), m.store.master.clone(), hyper_seen))
+    (h_sync, t_sync, p_sync, seen), (h_async, t_async, p_async, _) = outs
+    assert t_sync == t_async == 8
+    assert torch.equal(h_sync, h_async)
+    for t, h in enumerate(seen, start=1):   # the device schedule is the reference's (TRAIN:102, 371-374)
+        assert abs(h[0].item() - 1e-3 * linear_schedule(t - 1, 6, 20)) <= 1e-9
+        assert abs(h[5].item() - (1 - 0.9 ** t)) <= 1e-6 and abs(h[6].item() - (1 - 0.999 ** t)) <= 1e-7
+    # same kernels, same order, same hyper-parameters: only the fp32 atomics of bias / LayerNorm gradients may differ
+    assert (p_sync - p_async).abs().mean().item() <= 1e-5
+
+
+def test_plain_loop_still_works_after_a_trainstep_used_the_model(cuda_device):
+    """`store.external_step` is reset when TrainStep.step returns: a later forward / backward / optimizer.step loop on the
+    same model starts a fresh gradient step (bias / LayerNorm / embedding gradients must not accumulate across steps)."""
+    from vacnic_b200.trainer import TrainStep
+    cfg, gcfg, sd, gsd, m, g = _models(cuda_device)
+    batch = synthetic.make_batch(B=2, L=40, T=12, seed=9)
+    ts = TrainStep(m, g, lr=0.0, weight_decay=0.0, use_graph=False)
+    ts.step(batch)
+    assert m.store.external_step is False
+    db = {k: v.to(cuda_device) for k, v in TrainStep.prepare(batch, cfg).items()}
+    kw = dict(input_ids=db["article_ids"], attention_mask=db["src_mask"], decoder_input_ids=db["decoder_input_ids"],
+              image_features=db["image_features"], face_features=db["face_emb"], face_mask=db["face_mask"],
+              name_ids=db["names_art_ids"], name_mask=db["name_mask"], ce_targets=db["caption_ids"])
+    grads = []
+    for _ in range(2):
+        m(**kw)["loss"].backward()
+        torch.cuda.synchronize()
+        grads.append(m.store.grad.clone())
+    z = m.store.z_begin
+    denom = grads[0][z:].abs().max().item()
+    assert denom > 0 and (grads[0][z:] - grads[1][z:]).abs().max().item() <= 1e-3 * denom   # not doubled

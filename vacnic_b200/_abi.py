@@ -6,6 +6,7 @@ I32 = C.c_int32
 U32 = C.c_uint32
 I64 = C.c_int64
 F32 = C.c_float
+F64 = C.c_double
 
 # name -> argtypes (restype is int for all of these)
 SIGNATURES = {
@@ -27,6 +28,7 @@ SIGNATURES = {
     "vacnic_cast_rows_f32_bf16": [P, P, I64, I32, I64, I32, P],
     "vacnic_sum_partials": [P, P, I32, I64, I32, P],
     "vacnic_adamw": [P, P, P, P, P, I64, P, P],
+    "vacnic_optim_schedule": [P, P, F64, F64, F64, F32, F32, I64, I64, F32, P],
     "vacnic_rng_advance": [P, P],
     "vacnic_clip_grad_scale": [P, I64, F32, F32, P, P, P, P],
     "vacnic_ce_fwd": [P, P, P, P, P, I64, I32, I64, I64, P],

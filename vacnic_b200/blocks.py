@@ -28,6 +28,9 @@ class Runtime:
         self.training = False
         self.rng = K.Rng(store.device, seed)
         self._salt = 0
+        self.grad_hook = None
+        # requires-grad root every block of a forward pass hangs off (store.anchor, or its ParamTouchFn image under DDP)
+        self.fwd_anchor = store.anchor
 
     def new_salt(self) -> int:
         self._salt += 1
@@ -325,8 +328,11 @@ class NerMapFn(torch.autograd.Function):
         y1 = K.gemm(x_rows, up.w16, bias=up.b32, act=K.ACT_GELU, aux_out=z1)
         z2 = K.gemm(y1, down.w16, bias=down.b32)
         z2r = z2.view(B * G, d)
-        y, mean, rstd = K.add_layernorm_fwd(z2r, None, ln.g, ln.b)
-        ctx.rt, ctx.up, ctx.down, ctx.ln = rt, up, down, ln
+        # nn.functional.dropout(hidden_states_ner_prefix, p=self.dropout, training=self.training) sits between
+        # ner_map_down and the reshape + ner_map_layer_norm (MFULL:685-687); elementwise, so it commutes with the reshape
+        p = rt.drop
+        y, mean, rstd = K.add_layernorm_fwd(z2r, None, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt)
+        ctx.rt, ctx.up, ctx.down, ctx.ln, ctx.p = rt, up, down, ln, p
         ctx.saved = (x_rows, z1, y1, z2r, mean, rstd)
         ctx.dims = (B, E, d, G)
         return y.view(B, G, d)
@@ -337,7 +343,8 @@ class NerMapFn(torch.autograd.Function):
         x_rows, z1, y1, z2r, mean, rstd = ctx.saved
         B, E, d, G = ctx.dims
         R, U = B * d, up.out_f
-        dz2, _ = K.add_layernorm_bwd(dy.contiguous().view(B * G, d), z2r, None, ln.g, mean, rstd, ln.gg, ln.gb)
+        _, dz2 = K.add_layernorm_bwd(dy.contiguous().view(B * G, d), z2r, None, ln.g, mean, rstd, ln.gg, ln.gb,
+                                     want_dx=True, p_drop=ctx.p, rng=rt.rng, salt=ln.salt)  # dz2 = dropout-masked branch gradient
         Gp = (G + 7) // 8 * 8
         dz2p = K.pad_rows(dz2.view(R, G), Gp)[:, :G]  # 16-byte row pitch for TMA
         # dz1 = (dz2 W_down) * gelu'(z1) ; dx = dz1 W_up
@@ -395,6 +402,28 @@ class FanoutFn(torch.autograd.Function):
                 acc = K.add_bf16(acc, gs[i])
                 i += 1
         return acc, None
+
+
+class ParamTouchFn(torch.autograd.Function):
+    """Identity on the anchor that makes every parameter an autograd ancestor of the forward outputs.
+
+    Parameter gradients are written by kernels straight into the flat gradient buffer (`p.grad` are views of it), so
+    autograd itself never delivers a gradient to a parameter and the hooks `DistributedDataParallel` (TRAIN:86-87,
+    TRAINVIS:84) hangs on each parameter's AccumulateGrad node would never fire.  Every block takes the anchor as an
+    input, hence this node is the LAST one of the backward pass: when it runs all kernels that write gradients have been
+    enqueued.  It returns no gradient for the parameters (nothing is added to `p.grad`), but their AccumulateGrad nodes
+    still execute, DDP's hooks run, find the finished local gradient in `p.grad`, bucket it, all-reduce it and copy the
+    average back IN PLACE (the views survive).  `find_unused_parameters=True` also works: all parameters are reachable."""
+
+    @staticmethod
+    def forward(ctx, anchor, store, *params):
+        ctx.n, ctx.store = len(params), store
+        return anchor.view_as(anchor)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.store.finish_backward()  # end of the backward pass of the plain loop: unused GEMM weights read as zero
+        return (None,) * (2 + ctx.n)
 
 
 class GradMarkFn(torch.autograd.Function):

@@ -116,6 +116,31 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+
+// Step counter and schedule ON THE DEVICE (TRAIN:102 get_linear_schedule_with_warmup + torch.optim.AdamW bias corrections):
+// *step += 1, then hyper = {lr_t, beta1, beta2, eps, wd, 1-beta1^t, 1-beta2^t, grad_scale}.  One thread; it is part of the
+// captured step graph, so a host that runs several replays ahead can never overwrite a value an earlier replay still needs.
+__global__ void optim_schedule_kernel(long long* __restrict__ step, float* __restrict__ hyper, double base_lr, double beta1,
+                                      double beta2, float eps, float wd, long long warmup, long long total, float grad_scale) {
+  pdl_sync();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long t = *step + 1;
+  *step = t;
+  const long long s = t - 1;  // scheduler.step() follows optimizer.step(): update t uses multiplier(t - 1)
+  double mult;
+  if (s < warmup) mult = static_cast<double>(s) / static_cast<double>(warmup > 1 ? warmup : 1);
+  else {
+    const long long den = total - warmup > 1 ? total - warmup : 1;
+    mult = static_cast<double>(total - s) / static_cast<double>(den);
+    if (mult < 0.0) mult = 0.0;
+  }
+  hyper[0] = static_cast<float>(base_lr * mult);
+  hyper[1] = static_cast<float>(beta1); hyper[2] = static_cast<float>(beta2); hyper[3] = eps; hyper[4] = wd;
+  hyper[5] = static_cast<float>(1.0 - pow(beta1, static_cast<double>(t)));  // double like torch.optim.AdamW's Python floats
+  hyper[6] = static_cast<float>(1.0 - pow(beta2, static_cast<double>(t)));
+  hyper[7] = grad_scale;
+}
+
 // out = a + b (+ c) on bf16, fp32 math; gradient fan-in of the residual / state streams
 __global__ void __launch_bounds__(256)
 add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
@@ -285,6 +310,19 @@ extern "C" int vacnic_adamw(float* p, const float* g, float* m, float* v, void* 
       p, g, m, v, static_cast<__nv_bfloat16*>(p16), n, hyper);
   count_launch();
   return check_last("adamw");
+}
+
+
+extern "C" int vacnic_optim_schedule(int64_t* step, float* hyper, double base_lr, double beta1, double beta2, float eps,
+                                     float weight_decay, int64_t warmup_steps, int64_t total_steps, float grad_scale,
+                                     void* stream) {
+  VB_REQUIRE(step && hyper, "optim_schedule: null pointer");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(step) & 7) == 0, "optim_schedule: step must be 8-byte aligned");
+  launch_pdl(optim_schedule_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<long long*>(step),
+             hyper, base_lr, beta1, beta2, eps, weight_decay, static_cast<long long>(warmup_steps),
+             static_cast<long long>(total_steps), grad_scale);
+  count_launch();
+  return check_last("optim_schedule");
 }
 
 extern "C" int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream) {

@@ -42,6 +42,52 @@ def to_vacnic_config(config, prompt_size, max_ner_type_len, max_ner_type_len_gt,
         decoder_start_token_id=_cfg_get(config, "decoder_start_token_id", 2), eos_token_id=_cfg_get(config, "eos_token_id", 2))
 
 
+# what the device-side search implements (transformers `_beam_search` / greedy with a default BartConfig, see
+# vacnic_b200.generation); any other value -- passed as a kwarg or inherited from the checkpoint's config /
+# generation_config the way HF `generate()` (INFER:798) inherits it -- would change the captions, so it RAISES
+_GEN_TOKEN_KEYS = ("eos_token_id", "forced_eos_token_id", "pad_token_id", "bos_token_id", "decoder_start_token_id")
+GEN_IMPLEMENTED = {
+    "do_sample": (False,), "early_stopping": (False,), "num_return_sequences": (1,), "num_beam_groups": (1,),
+    "no_repeat_ngram_size": (0, None), "encoder_no_repeat_ngram_size": (0, None), "repetition_penalty": (1.0, None),
+    "encoder_repetition_penalty": (1.0, None), "diversity_penalty": (0.0, None), "min_length": (0, None),
+    "min_new_tokens": (None,), "max_new_tokens": (None,), "temperature": (1.0, None), "top_k": (50, None), "top_p": (1.0, None),
+    "bad_words_ids": (None,), "force_words_ids": (None,), "forced_bos_token_id": (None,), "suppress_tokens": (None,),
+    "begin_suppress_tokens": (None,), "exponential_decay_length_penalty": (None,), "renormalize_logits": (False,),
+    "remove_invalid_values": (False, None), "constraints": (None,), "prefix_allowed_tokens_fn": (None,),
+    "logits_processor": (None,), "stopping_criteria": (None,), "penalty_alpha": (None,), "output_scores": (False,),
+    "output_attentions": (False, True), "output_hidden_states": (False, True),  # no effect on the returned ids (TRAIN:743)
+    "output_logits": (False, None),
+    "return_dict_in_generate": (False,), "use_cache": (True, False), "assistant_model": (None,), "streamer": (None,),
+    "synced_gpus": (False, None), "sequence_bias": (None,), "guidance_scale": (None, 1.0), "decoder_input_ids": (None,),
+}
+
+def check_generation_request(cfg: VacnicConfig, config, generation_config, kwargs: dict):
+    """Raise NotImplementedError for every generate() argument or inherited checkpoint setting the device-side search does
+    not implement (host-only logic, CPU-testable)."""
+    sources = [("generate() argument", kwargs)]
+    for name, obj in (("generation_config", generation_config), ("config", config)):
+        if obj is not None:
+            d = obj.to_dict() if hasattr(obj, "to_dict") else dict(obj)
+            sources.append((name, {k: v for k, v in d.items() if k not in kwargs}))  # explicit arguments win, as in HF
+    for where, d in sources:
+        for k, v in d.items():
+            if k in GEN_IMPLEMENTED:
+                ok = GEN_IMPLEMENTED[k]
+                if v is not None and not any(o is not None and v == o for o in ok):
+                    raise NotImplementedError(
+                        f"generate(): {k}={v!r} (from {where}) is not implemented by the vacnic_b200 search "
+                        f"(implemented: {ok[0]!r}); pass {k}={ok[0]!r} explicitly to override a checkpoint setting")
+            elif where == "generate() argument" and k not in _GEN_TOKEN_KEYS:
+                raise NotImplementedError(f"generate(): unknown / unimplemented argument {k!r}")
+    eos = kwargs.get("eos_token_id", cfg.eos_token_id)
+    forced_eos = kwargs.get("forced_eos_token_id", _cfg_get(config, "forced_eos_token_id", cfg.eos_token_id))
+    if eos != cfg.eos_token_id or forced_eos != cfg.eos_token_id:
+        raise NotImplementedError("generate(): eos_token_id / forced_eos_token_id other than the model's EOS are not implemented")
+    for k, want in (("pad_token_id", cfg.pad_token_id), ("bos_token_id", None), ("decoder_start_token_id", cfg.decoder_start_token_id)):
+        if k in kwargs and want is not None and kwargs[k] != want:
+            raise NotImplementedError(f"generate(): {k}={kwargs[k]!r} differs from the model configuration ({want})")
+
+
 class _DropInBase(VacnicBart):
     ONLY_IMAGE_FILE = False  # the MVIS module has no face/name branch at all
 
@@ -93,6 +139,7 @@ class _DropInBase(VacnicBart):
             with open(os.path.join(pretrained_model_name_or_path, "config.json")) as f:
                 config = json.load(f)
         model = cls(config, **ctor)
+        object.__setattr__(model, "generation_config", _read_generation_settings(pretrained_model_name_or_path))
         sd = _read_checkpoint(pretrained_model_name_or_path)
         if sd is not None:
             model.load_reference_state_dict(sd, strict=False)
@@ -142,7 +189,7 @@ class _DropInBase(VacnicBart):
     def __reduce__(self):
         sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
         cfg = self.config.to_dict() if hasattr(self.config, "to_dict") else dict(self.config)
-        return (_rebuild, (type(self), cfg, self._ctor, sd))
+        return (_rebuild, (type(self), cfg, self._ctor, sd, getattr(self, "generation_config", None)))
 
     # ------------------------------------------------------------------ embeddings
     def resize_token_embeddings(self, new_num_tokens: int):
@@ -169,6 +216,7 @@ class _DropInBase(VacnicBart):
                 else:  # [vocab, d] tables: shared / lm_head
                     tgt[:n].copy_(v[:n])
         fresh.store.refresh_shadow()
+        self.__dict__.pop("_generators", None)  # captured decode graphs point at the old store / vocabulary
         self.__dict__.update(fresh.__dict__)
         return self.model.shared
 
@@ -180,8 +228,15 @@ class _DropInBase(VacnicBart):
     def generate(self, input_ids=None, attention_mask=None, num_beams: int = 1, max_length: int = 20,
                  length_penalty: float = 1.0, image_features=None, face_features=None, face_mask=None, name_ids=None,
                  name_mask=None, add_ner_ffn=True, **kwargs):
-        """Greedy (num_beams=1) or beam search, transformers-5.5 semantics (see vacnic_b200.generation)."""
+        """Greedy (num_beams=1) or beam search, transformers-5.5 semantics (see vacnic_b200.generation).  Arguments and
+        checkpoint generation settings that would alter the search (no_repeat_ngram_size, early_stopping,
+        forced_bos_token_id, sampling, ...) raise NotImplementedError instead of being ignored."""
         from . import generation
+        if not add_ner_ffn:
+            raise ValueError("add_ner_ffn=False is broken in the reference (MFULL:666 vs :1296) and is not provided")
+        passthrough = {k: kwargs.pop(k) for k in ("eos_token_id", "forced_eos_token_id", "pad_token_id", "bos_token_id",
+                                                  "decoder_start_token_id") if k in kwargs}
+        check_generation_request(self.cfg, self.config, getattr(self, "generation_config", None), {**kwargs, **passthrough})
         return generation.generate(self, input_ids=input_ids, attention_mask=attention_mask, num_beams=num_beams,
                                    max_length=max_length, length_penalty=length_penalty, image_features=image_features,
                                    face_features=face_features, face_mask=face_mask, name_ids=name_ids, name_mask=name_mask)
@@ -201,7 +256,22 @@ class _DropInBase(VacnicBart):
         return tuple(tuple(t.index_select(0, beam_idx) for t in layer[:2]) + tuple(layer[2:]) for layer in past)
 
 
-def _rebuild(cls, cfg, ctor, sd):
+def _read_generation_settings(path: str) -> dict:
+    """Generation settings a checkpoint directory carries (`generation_config.json`, and the legacy generation keys of
+    `config.json` that transformers 4.18 -- the reference's pin, vacnic.yml:187 -- applies inside generate()), as a raw
+    dict: `generate()` refuses the ones the device-side search does not implement instead of silently dropping them."""
+    import json
+    out = {}
+    for fn in ("config.json", "generation_config.json"):
+        f = os.path.join(path, fn)
+        if os.path.isfile(f):
+            with open(f) as fh:
+                raw = json.load(fh)
+            out.update({k: raw[k] for k in GEN_IMPLEMENTED if k in raw})
+    return out
+
+
+def _rebuild(cls, cfg, ctor, sd, gen_cfg=None):
     try:
         from transformers import BartConfig
         config = BartConfig(**cfg)
@@ -209,6 +279,8 @@ def _rebuild(cls, cfg, ctor, sd):
         config = cfg
     m = cls(config, **ctor)
     m.load_reference_state_dict(sd, strict=False)
+    if gen_cfg is not None:
+        object.__setattr__(m, "generation_config", gen_cfg)
     return m
 
 

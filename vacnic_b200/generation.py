@@ -95,15 +95,19 @@ class Generator:
             st["seq"][:, 0] = cfg.decoder_start_token_id
             st["unfinished"].fill_(1)
 
+    @torch.no_grad()
     def encode(self, enc_inputs: dict):
         """Encoder forward (a7a) + the one-off cross-attention K/V projection of every decoder layer."""
         model, cfg = self.model, self.cfg
         if model.store.dirty_shadow:
             model.store.refresh_shadow()
-        was_training = model.training
-        model.eval()
-        enc = model.model.encoder(output_hidden_states=False, **enc_inputs)
-        model.train(was_training)
+        encoder = model.model.encoder
+        was_training = encoder.training
+        encoder.training = False  # dropout off for this call only; no train()/eval() round trip (that would re-cast the shadow)
+        try:
+            enc = encoder(output_hidden_states=False, **enc_inputs)
+        finally:
+            encoder.training = was_training
         h = enc["last_hidden_state"]
         C, L, d = h.shape
         if (C, L) != (self.C, self.L):

@@ -311,6 +311,15 @@ def adamw(p, g, m, v, p16, hyper):
     check(lib().vacnic_adamw(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p16), p.numel(), ptr(hyper), stream_ptr()), "vacnic_adamw")
 
 
+def optim_schedule(step_dev, hyper, base_lr, beta1, beta2, eps, weight_decay, warmup_steps, total_steps, grad_scale):
+    """Advance the device-side step counter (int64[1]) and write this update's {lr, betas, eps, wd, bias corrections,
+    grad_scale} into `hyper` (fp32[8]) -- TRAIN:102, 371-374."""
+    _c(step_dev, torch.int64, "step counter"); _c(hyper, torch.float32, "hyper")
+    check(lib().vacnic_optim_schedule(ptr(step_dev), ptr(hyper), float(base_lr), float(beta1), float(beta2), float(eps),
+                                      float(weight_decay), int(warmup_steps), int(total_steps), float(grad_scale), stream_ptr()),
+          "vacnic_optim_schedule")
+
+
 def clip_grad_scale(g, max_norm, base_scale, scratch, scale_out, norm_out=None):
     """scale_out[0] = base_scale * min(1, max_norm / (|base_scale| * ||g|| + 1e-6))  (clip_grad_norm_ folded into AdamW)."""
     check(lib().vacnic_clip_grad_scale(ptr(g), g.numel(), float(max_norm), float(base_scale), ptr(scratch), ptr(scale_out),

@@ -138,10 +138,10 @@ class BartEncoderLayer(nn.Module):
         rt, cfg, H = self.rt, self.cfg, self.cfg.heads
         kv = None
         if not cfg.stock:
-            img = Bk.MlpBlockFn.apply(img, rt.store.anchor, rt, self.lin_iup, self.lin_idown, K.ACT_GELU, self.ln_img)
+            img = Bk.MlpBlockFn.apply(img, rt.fwd_anchor, rt, self.lin_iup, self.lin_idown, K.ACT_GELU, self.ln_img)
             img_kv, img = Bk.fanout(img, 2)
             if not cfg.only_image:
-                face = Bk.MlpBlockFn.apply(face, rt.store.anchor, rt, self.lin_fup, self.lin_fdown, K.ACT_GELU, self.ln_face)
+                face = Bk.MlpBlockFn.apply(face, rt.fwd_anchor, rt, self.lin_fup, self.lin_fdown, K.ACT_GELU, self.ln_face)
                 face_kv, face = Bk.fanout(face, 2)
                 ner_q, ner_kv = Bk.fanout(ner, 2)
                 a = self.self_attn_img_name
@@ -159,7 +159,7 @@ class BartEncoderLayer(nn.Module):
             a = self.cross_attn_img_ner
             h = Bk.AttnBlockFn.apply(h, kv, None, rt, None, a.lin_q, a.lin_kv, a.lin_o, a.ln, H, None, False, True, 0,
                                      None, False)
-        h = Bk.MlpBlockFn.apply(h, rt.store.anchor, rt, self.lin_fc1, self.lin_fc2, K.ACT_GELU, self.ln_final)
+        h = Bk.MlpBlockFn.apply(h, rt.fwd_anchor, rt, self.lin_fc1, self.lin_fc2, K.ACT_GELU, self.ln_final)
         return h, face, ner, img
 
 
@@ -252,20 +252,20 @@ class BartEncoder(nn.Module):
         if attention_mask is None:
             attention_mask = torch.ones_like(input_ids)
         key_mask = Bk.KeyMask(attention_mask)
-        h = Bk.EmbedFn.apply(st.anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
+        h = Bk.EmbedFn.apply(rt.fwd_anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
                              self.ln_emb, 2, cfg.pad_token_id)
         img = face = ner = fn_mask = None
         if not cfg.stock:
             if not cfg.only_image:
-                ner = Bk.EmbedFn.apply(st.anchor, name_ids.contiguous(), rt, self.embed_tokens_ner.weight,
+                ner = Bk.EmbedFn.apply(rt.fwd_anchor, name_ids.contiguous(), rt, self.embed_tokens_ner.weight,
                                        self.embed_positions_ner.weight, self.ln_emb_ner, 2, cfg.pad_token_id)
                 fn_mask = Bk.KeyMask(torch.cat((face_mask, name_mask), dim=1))  # MFULL:1262
-                face = Bk.LinearFn.apply(face_features.to(torch.bfloat16), st.anchor, rt, self.lin_face, torch.bfloat16, False, None,
+                face = Bk.LinearFn.apply(face_features.to(torch.bfloat16), rt.fwd_anchor, rt, self.lin_face, torch.bfloat16, False, None,
                                          None)
-            z = Bk.MlpBlockFn.apply(image_features.to(torch.bfloat16), st.anchor, rt, self.lin_p0, self.lin_p2, K.ACT_TANH, None)
+            z = Bk.MlpBlockFn.apply(image_features.to(torch.bfloat16), rt.fwd_anchor, rt, self.lin_p0, self.lin_p2, K.ACT_TANH, None)
             img = z.view(B, cfg.prompt_size, CLIP_DIM)  # MFULL:1276
             if cfg.d_model == 1024:
-                img = Bk.LinearFn.apply(img, st.anchor, rt, self.lin_vmap, torch.bfloat16, True, None, None)
+                img = Bk.LinearFn.apply(img, rt.fwd_anchor, rt, self.lin_vmap, torch.bfloat16, True, None, None)
         states = []
         for i, layer in enumerate(self.layers):
             if output_hidden_states:
@@ -314,13 +314,13 @@ class BartDecoder(nn.Module):
         st = rt.store
         B, T = input_ids.shape
         d, H = cfg.d_model, cfg.heads
-        x = Bk.EmbedFn.apply(st.anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
+        x = Bk.EmbedFn.apply(rt.fwd_anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
                              self.ln_emb, 2, cfg.pad_token_id)
         enc_mask = None if encoder_attention_mask is None else Bk.KeyMask(encoder_attention_mask)
         dec_mask = None if attention_mask is None else Bk.KeyMask(attention_mask)
         # backward: once this marker fires, the decoder (incl. the hoisted cross K/V projection) and the LM head are done
         encoder_hidden_states = Bk.grad_mark(encoder_hidden_states, rt, ("dec", 0))
-        kv_all = Bk.LinearFn.apply(encoder_hidden_states, st.anchor, rt, self.lin_cross_kv, torch.bfloat16, True, None, None)
+        kv_all = Bk.LinearFn.apply(encoder_hidden_states, rt.fwd_anchor, rt, self.lin_cross_kv, torch.bfloat16, True, None, None)
         dkv_all = torch.empty_like(kv_all) if (torch.is_grad_enabled() and kv_all.requires_grad) else None
         states = []
         for i, l in enumerate(self.layers):
@@ -332,7 +332,7 @@ class BartDecoder(nn.Module):
             a = l.encoder_attn
             x = Bk.AttnBlockFn.apply(x, None, kv_all, rt, None, a.lin_q, None, a.lin_o, a.ln, H, enc_mask, False, True,
                                      i * 2 * d, dkv_all, i == 0)
-            x = Bk.MlpBlockFn.apply(x, rt.store.anchor, rt, l.lin_fc1, l.lin_fc2, K.ACT_GELU, l.ln_final)
+            x = Bk.MlpBlockFn.apply(x, rt.fwd_anchor, rt, l.lin_fc1, l.lin_fc2, K.ACT_GELU, l.ln_final)
         if output_hidden_states:
             states.append(x)
         return VacnicOutput(last_hidden_state=x, past_key_values=None,
@@ -410,7 +410,10 @@ class VacnicBart(nn.Module):
     def train(self, mode: bool = True):
         super().train(mode)
         self.rt.training = mode
-        self.store._shadow_version = -1  # `.data` edits (TRAIN:758) do not bump version counters: re-cast on the next forward
+        # `.data` edits (TRAIN:758) do not bump version counters: every train() / eval() call (once per epoch in the scripts,
+        # TRAIN train_epoch) re-casts the bf16 shadow on the next forward.  Per-step callers (trainer.TrainStep,
+        # generation.Generator) do not go through here unless the mode really changes.
+        self.store._shadow_version = -1
         return self
 
     def get_encoder(self):
@@ -444,6 +447,14 @@ class VacnicBart(nn.Module):
             # training forward starts a fresh gradient step in the flat buffer (p.grad views are re-attached after
             # zero_grad(set_to_none=True)); gradient accumulation over several forwards needs vacnic_b200.trainer
             self.store.begin_step()
+            # end-of-backward node of the plain loop; under torch.distributed (the script wraps the model in
+            # DistributedDataParallel, TRAIN:86-87 / TRAINVIS:84) it also makes DDP's reducer hooks fire -- see ParamTouchFn
+            dist = torch.distributed
+            multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            self.rt.fwd_anchor = Bk.ParamTouchFn.apply(self.store.anchor, self.store,
+                                                       *(tuple(self.store.params.values()) if multi else ()))
+        else:
+            self.rt.fwd_anchor = self.store.anchor
         if labels is not None and decoder_input_ids is None:
             decoder_input_ids = shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
         if decoder_input_ids is None:
@@ -469,7 +480,7 @@ class VacnicBart(nn.Module):
             B, T, d = x.shape
             ldp = (cfg.vocab + 7) // 8 * 8
             buf = torch.empty(B * T, ldp, dtype=torch.float32, device=x.device)
-            logits = Bk.LinearFn.apply(x_lm, self.store.anchor, self.rt, flb_lin, torch.float32, True, buf[:, :cfg.vocab], None)
+            logits = Bk.LinearFn.apply(x_lm, self.rt.fwd_anchor, self.rt, flb_lin, torch.float32, True, buf[:, :cfg.vocab], None)
         dec_states = dec["hidden_states"]
         if dec_states is not None:
             dec_states = dec_states[:-1] + (x_out,)

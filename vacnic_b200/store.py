@@ -82,6 +82,8 @@ class ParamStore:
                 if p is not None and id(p) in remap:
                     m._parameters[k] = remap[id(p)]
         self._touched = set()
+        self._untouched: list = []          # (offset, numel) of GEMM weights not written in the previous step
+        self._untouched_key = None
         self._lin_span: Dict[str, tuple] = {}
         self._shadow_version = -1  # version counter of `master` when the bf16 shadow was last refreshed
         self.external_step = False  # True while a TrainStep drives begin_step / finish_backward itself
@@ -133,6 +135,11 @@ class ParamStore:
         if self.frozen:
             return
         self.grad[self.z_begin:].zero_()
+        # GEMM weights no kernel wrote in the previous step (parameters the configuration never uses): the set is a
+        # property of the model, so zero them HERE, on the compute stream and before the forward pass -- not after the
+        # backward pass, where a data-parallel bucket holding them may already be in flight on the communication stream
+        for o, k in self._untouched:
+            self.grad[o:o + k].zero_()
         self._touched.clear()
         for p in self.params.values():  # optimizer.zero_grad(set_to_none=True) drops the views
             if p.grad is None:
@@ -143,11 +150,19 @@ class ParamStore:
         """GEMM-weight gradients never touched in this step (unused parameters) must read as zero."""
         if self.frozen:
             return
+        key = frozenset(self._touched)
+        if key == self._untouched_key:
+            return  # same set as last step: begin_step already zeroed them
         spans = sorted(self._lin_span[k] for k in self._touched)
+        untouched = []
         for n, p in self.params.items():
             o = self.offsets[n]
             if o < self.z_begin and not any(a <= o < a + k for a, k in spans):
-                self.grad[o:o + p.numel()].zero_()
+                untouched.append((o, p.numel()))
+        for o, k in untouched:  # first step (or the used set changed): zero now; from the next step on begin_step does it
+            if (o, k) not in self._untouched:
+                self.grad[o:o + k].zero_()
+        self._untouched, self._untouched_key = untouched, key
 
     def touch(self, key: str) -> bool:
         """True if `key`'s weight gradient already holds this step's partial sum (-> accumulate)."""

@@ -3,8 +3,9 @@ loss against the frozen stock-BART guide, SECLA face-name loss, backward, (data-
 all-reduce), fused AdamW with the linear warm-up/decay schedule — optionally captured once as a CUDA
 graph and replayed, so that the ~2.5k kernel launches of a step cost no host time.
 
-Host-side work per step is: copy the batch into static device buffers, write the step's scalar
-hyper-parameters (lr and Adam bias corrections), replay.
+Host-side work per step is: copy the batch into static device buffers and replay.  The step counter, the
+learning-rate schedule and the Adam bias corrections live ON THE DEVICE (`vacnic_optim_schedule`, first node of
+the step): the host may run any number of replays ahead without a synchronisation.
 """
 from __future__ import annotations
 
@@ -50,8 +51,8 @@ class TrainStep:
         self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
         self._clip_scratch = torch.zeros(2368, dtype=torch.float32, device=dev)  # VACNIC_CLIP_SCRATCH_FLOATS
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
-        self.step_no = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)  # optimizer updates applied so far (device truth)
+        self.step_no = 0                                               # host mirror (bookkeeping only)
         self.graph = None
         self.static: Dict[str, torch.Tensor] = {}
         self.losses: Dict[str, torch.Tensor] = {}
@@ -100,7 +101,9 @@ class TrainStep:
     def _body(self, b: Dict[str, torch.Tensor]):
         model, guide, cfg = self.model, self.guide, self.cfg
         st = model.store
-        st.external_step = True
+        # t += 1; hyper = {lr_t, betas, eps, wd, bias corrections, 1/world} -- computed by a device kernel inside the step
+        K.optim_schedule(self.step_dev, self.hyper, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.warmup,
+                         self.total, 1.0 / self.world)
         st.begin_step()
         # the backward-pass markers call into THIS step object (another TrainStep may share the model)
         model.rt.grad_hook = self._on_grad_ready if self.buckets is not None else None
@@ -172,14 +175,14 @@ class TrainStep:
             b["name_mask"] = (batch["names_art_ids"] != 1).to(torch.int64)
         return b
 
-    def _write_hyper(self):
-        self.step_no += 1
-        t = self.step_no
-        lr = self.lr * linear_schedule(t - 1, self.warmup, self.total)  # scheduler.step() follows optimizer.step()
-        h = self.hyper_host
-        h[0], h[1], h[2], h[3], h[4] = lr, self.betas[0], self.betas[1], self.eps, self.wd
-        h[5], h[6], h[7] = 1 - self.betas[0] ** t, 1 - self.betas[1] ** t, 1.0 / self.world
-        self.hyper.copy_(h, non_blocking=True)
+    def current_lr(self) -> float:
+        """Learning rate the NEXT update will use (host-side restatement of the device schedule, for logging)."""
+        return self.lr * linear_schedule(self.step_no, self.warmup, self.total)
+
+    def set_step(self, t: int):
+        """Resume at optimizer update count `t` (checkpoint restore)."""
+        self.step_no = int(t)
+        self.step_dev.fill_(int(t))
 
     def _load_static(self, b: Dict[str, torch.Tensor]):
         for k, v in b.items():
@@ -193,39 +196,58 @@ class TrainStep:
     def step(self, batch: Dict[str, torch.Tensor], prepared: bool = False) -> Dict[str, torch.Tensor]:
         """Run one optimisation step on a (host or device) batch; returns device scalars {txt, margin, secla}."""
         b = batch if prepared else self.prepare(batch, self.cfg)
-        self.model.train()
-        if self.guide is not None:
-            self.guide.eval()
-        self._write_hyper()
-        if not self.use_graph:
-            dev = self.model.store.device
-            b = {k: v.to(dev, non_blocking=True) for k, v in b.items()}
-            c0 = K._l.launch_count()
-            self.losses = self._body(b)
-            self.launches_per_step = K._l.launch_count() - c0
+        model, guide = self.model, self.guide
+        if not model.training:
+            model.train()
+        if guide is not None and guide.training:
+            guide.eval()
+        # bring the bf16 compute shadows up to date HERE (outside any capture): the fused AdamW keeps the model's shadow
+        # current from then on and the guide never changes, so the captured step holds no fp32 -> bf16 re-cast
+        for mm in (model, guide):
+            if mm is not None and mm.store.dirty_shadow:
+                mm.store.refresh_shadow()
+        st = model.store
+        st.external_step = True  # this object drives begin_step / finish_backward (reset below: the plain
+        try:                     # forward / backward / optimizer.step loop must keep working on the same model)
+            self.step_no += 1
+            if not self.use_graph:
+                dev = st.device
+                b = {k: v.to(dev, non_blocking=True) for k, v in b.items()}
+                c0 = K._l.launch_count()
+                self.losses = self._body(b)
+                self.launches_per_step = K._l.launch_count() - c0
+                return self.losses
+            self._load_static(b)
+            if self.graph is None:
+                # warm-up on a side stream (allocator, lazy kernel attribute setup), then capture
+                saved = (st.master.clone(), self.m.clone(), self.v.clone(), model.rt.rng.state.clone(), self.step_dev.clone())
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    for _ in range(2):
+                        self._body(self.static)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                # the warm-up steps must not count as optimisation steps
+                st.master.copy_(saved[0]); self.m.copy_(saved[1]); self.v.copy_(saved[2])
+                model.rt.rng.state.copy_(saved[3]); self.step_dev.copy_(saved[4])
+                st.refresh_shadow()
+                del saved
+                self.graph = torch.cuda.CUDAGraph()
+                c0 = K._l.launch_count()
+                with torch.cuda.graph(self.graph):
+                    self.losses = self._body(self.static)
+                self.launches_per_step = K._l.launch_count() - c0
+            self.graph.replay()
             return self.losses
-        self._load_static(b)
-        if self.graph is None:
-            # warm-up on a side stream (allocator, lazy kernel attribute setup), then capture
-            self.step_no -= 1
-            saved = (self.model.store.master.clone(), self.m.clone(), self.v.clone(), self.model.rt.rng.state.clone())
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    self._body(self.static)
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
-            # the warm-up steps must not count as optimisation steps
-            self.model.store.master.copy_(saved[0]); self.m.copy_(saved[1]); self.v.copy_(saved[2])
-            self.model.rt.rng.state.copy_(saved[3])
-            self.model.store.refresh_shadow()
-            del saved
-            self.graph = torch.cuda.CUDAGraph()
-            c0 = K._l.launch_count()
-            with torch.cuda.graph(self.graph):
-                self.losses = self._body(self.static)
-            self.launches_per_step = K._l.launch_count() - c0
-            self._write_hyper()
-        self.graph.replay()
-        return self.losses
+        finally:
+            st.external_step = False
+
+    def close(self):
+        """Drop the captured graph and break the model <-> step reference cycle (the backward-pass markers hold a bound
+        method of this object), so the step's device memory is returned as soon as the caller drops its reference."""
+        self.graph = None
+        self.static.clear()
+        self.losses = {}
+        if getattr(self.model.rt, "grad_hook", None) is not None:
+            self.model.rt.grad_hook = None
