@@ -305,6 +305,11 @@ def main():
     ap.add_argument("--caption-len", type=int, default=64)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pipeline-opt", action="store_true", help="one fused AdamW launch after the gradient exchange instead of per-bucket updates")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-mc", "nccl", "none"],
+                    help="multi-GPU gradient exchange (auto = peer-memory sharded optimizer when available); none = debugging: "
+                         "independent replicas, NOT data-parallel training")
+    ap.add_argument("--seed-offset", type=int, default=0, help="debug: shift the synthetic batch seeds")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the rank-0 eager roofline pass (quick A/B runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager comparator of the reference arithmetic on the GPU")
     ap.add_argument("--small", action="store_true", help="BART-base config-1 shapes (debug)")
@@ -416,10 +421,13 @@ def main():
     model = VacnicBart(cfg, device=dev, p_drop=0.1, seed=684331)          # seed of run_full_train.sh:2
     guide = None if vis else VacnicBart(gcfg, device=dev, p_drop=0.0, seed=7, frozen=True)
     ts = TrainStep(model, guide, lr=3e-5, weight_decay=0.01, warmup_steps=100, total_steps=100000, margin=1.0, alpha=0.5,
-                   use_graph=not args.no_graph, process_group=pg, pipeline_optimizer=False if args.no_pipeline_opt else None)
+                   use_graph=not args.no_graph, process_group=None if args.exchange == "none" else pg,
+                   pipeline_optimizer=False if args.no_pipeline_opt else None,
+                   exchange=None if args.exchange in ("auto", "none") else args.exchange)
+    config["exchange"] = ts.exchange if (world > 1 and args.exchange != "none") else ("none" if world > 1 else "single GPU")
 
     n_batches = 4
-    host = [TrainStep.prepare(synthetic.make_batch(B=B, L=L, T=T, seed=1000 * rank + i), cfg) for i in range(n_batches)]
+    host = [TrainStep.prepare(synthetic.make_batch(B=B, L=L, T=T, seed=1000 * rank + i + args.seed_offset), cfg) for i in range(n_batches)]
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
@@ -483,7 +491,7 @@ def main():
 
     try:
         # ---- roofline of the dominant kernel (gemm2_sm100_kernel): one eager, event-instrumented step on rank 0
-        if rank == 0:
+        if rank == 0 and not args.no_roofline:
             line["roofline"] = guarded("roofline", lambda: train_roofline(model, guide, ts, devb, pk, step_tflops, ms_dev / args.steps,
                                                                          args.small))
         if world > 1:

@@ -183,6 +183,18 @@ int vacnic_adamw(float* p, const float* g, float* m, float* v, void* p16, int64_
  * step graph, so no host buffer is read asynchronously. */
 int vacnic_optim_schedule(int64_t* step, float* hyper, double base_lr, double beta1, double beta2, float eps, float weight_decay,
                           int64_t warmup_steps, int64_t total_steps, float grad_scale, void* stream);
+/* Data-parallel optimizer step over NVLink peer memory: reduce-scatter + AdamW + all-gather as ONE kernel (replaces the DDP
+ * gradient all-reduce TRAIN:86-87 followed by optimizer.step() TRAIN:371).  grad_ptrs[r] / shadow_ptrs[r] (host arrays of
+ * `world` device addresses) are rank r's flat fp32 gradient buffer and bf16 compute shadow, mapped into this process
+ * (symmetric memory).  This rank owns elements [begin, begin+count) (multiples of 8): it sums that shard of every rank's
+ * gradient in rank order (fp32), applies vacnic_adamw's arithmetic to its local master / m / v, and stores the new bf16
+ * weights into every rank's shadow.  grad_mc / shadow_mc: NVSwitch multicast addresses of the same buffers (0 = plain peer
+ * loads / stores; non-zero = multimem.ld_reduce / multimem.st).  Cross-rank ordering (all ranks finished writing the
+ * bucket; all ranks finished the step) is the caller's: a symmetric-memory barrier on the same stream.  max_blocks caps
+ * the grid (0 = 4 x SM count) so the kernel can run beside the backward pass. */
+int vacnic_dp_adamw_shard(const uint64_t* grad_ptrs, const uint64_t* shadow_ptrs, uint64_t grad_mc, uint64_t shadow_mc,
+                          int32_t world, int32_t rank, float* master, float* m, float* v, const float* hyper, int64_t begin,
+                          int64_t count, int32_t max_blocks, void* stream);
 /* clip_grad_norm_ (TRAIN:365-366) folded into the optimizer: *scale_out = base_scale * min(1, max_norm / (|base_scale| *
  * ||g||_2 + 1e-6)); write it to hyper[7] of vacnic_adamw.  scratch: VACNIC_CLIP_SCRATCH_FLOATS device floats (per-block
  * partial sums, reduced in a fixed order: the norm is bit-reproducible). */

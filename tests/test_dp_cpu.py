@@ -109,3 +109,24 @@ def test_linear_schedule_matches_transformers():
         assert abs(opt.param_groups[0]["lr"] - linear_schedule(step, 5, 40)) < 1e-7, step
         opt.step()
         sch.step()
+
+
+def test_shard_of_range_partitions_every_range_exactly_once():
+    """Rank-sharded optimizer (csrc/dp.cu): for any world size the per-rank shards of an address range are disjoint,
+    cover it exactly, start on 64-element boundaries relative to the range and have lengths that are multiples of 8
+    whenever the range length is (the kernel processes 8 elements per thread)."""
+    from vacnic_b200.dp import shard_of_range
+    for world in (1, 2, 4, 8):
+        for a, b in ((0, 64), (128, 128 + 1024), (64, 64 + 7 * 64), (0, 1048576 + 192), (4096, 4096 + 80 * 320), (0, 0)):
+            covered = []
+            for r in range(world):
+                begin, count = shard_of_range(a, b, r, world)
+                assert count >= 0 and (begin - a) % 64 == 0 and (count % 8 == 0 or (b - a) % 8 != 0)
+                if count:
+                    covered.append((begin, begin + count))
+            covered.sort()
+            pos = a
+            for lo, hi in covered:
+                assert lo == pos, (world, a, b, covered)
+                pos = hi
+            assert pos == b, (world, a, b, covered)

@@ -5,6 +5,7 @@ P = C.c_void_p
 I32 = C.c_int32
 U32 = C.c_uint32
 I64 = C.c_int64
+U64 = C.c_uint64
 F32 = C.c_float
 F64 = C.c_double
 
@@ -29,6 +30,7 @@ SIGNATURES = {
     "vacnic_sum_partials": [P, P, I32, I64, I32, P],
     "vacnic_adamw": [P, P, P, P, P, I64, P, P],
     "vacnic_optim_schedule": [P, P, F64, F64, F64, F32, F32, I64, I64, F32, P],
+    "vacnic_dp_adamw_shard": [P, P, U64, U64, I32, I32, P, P, P, P, I64, I64, I32, P],
     "vacnic_rng_advance": [P, P],
     "vacnic_clip_grad_scale": [P, I64, F32, F32, P, P, P, P],
     "vacnic_ce_fwd": [P, P, P, P, P, I64, I32, I64, I64, P],

@@ -74,10 +74,7 @@ cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ p16, long long n, const float* __restrict__ hyper) {
-  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5],
-              bc2 = hyper[6], gs = hyper[7];
-  const float step_size = lr / bc1;
-  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const AdamwCoef c = adamw_coef(hyper);
   const long long i0 = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4;
   if (i0 >= n) return;
   if (i0 + 4 <= n) {
@@ -87,14 +84,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     float4 vv = *reinterpret_cast<float4*>(v + i0);
     float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gr = ga[k] * gs;
-      pa[k] *= 1.f - lr * wd;  // decoupled weight decay (torch.optim.AdamW)
-      ma[k] = b1 * ma[k] + (1.f - b1) * gr;
-      va[k] = b2 * va[k] + (1.f - b2) * gr * gr;
-      const float denom = sqrtf(va[k]) * inv_sqrt_bc2 + eps;
-      pa[k] -= step_size * ma[k] / denom;
-    }
+    for (int k = 0; k < 4; ++k) adamw_elem(c, ga[k], pa[k], ma[k], va[k]);
     *reinterpret_cast<float4*>(p + i0) = pp;
     *reinterpret_cast<float4*>(m + i0) = mm;
     *reinterpret_cast<float4*>(v + i0) = vv;
@@ -105,17 +95,13 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     }
   } else {
     for (long long i = i0; i < n; ++i) {
-      const float gr = g[i] * gs;
-      float pv = p[i] * (1.f - lr * wd);
-      const float mv = b1 * m[i] + (1.f - b1) * gr;
-      const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
-      pv -= step_size * mv / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+      float pv = p[i], mv = m[i], vv = v[i];
+      adamw_elem(c, g[i], pv, mv, vv);
       p[i] = pv; m[i] = mv; v[i] = vv;
       if (p16) p16[i] = __float2bfloat16_rn(pv);
     }
   }
 }
-
 
 // Step counter and schedule ON THE DEVICE (TRAIN:102 get_linear_schedule_with_warmup + torch.optim.AdamW bias corrections):
 // *step += 1, then hyper = {lr_t, beta1, beta2, eps, wd, 1-beta1^t, 1-beta2^t, grad_scale}.  One thread; it is part of the

@@ -258,4 +258,31 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(t);
 }
 
+
+// One AdamW element update (torch.optim.AdamW, TRAIN:95-101) with every rounding pinned by intrinsics, so that the flat
+// kernel (elementwise.cu) and the rank-sharded peer-memory kernel (dp.cu) produce bit-identical weights from identical
+// gradients whatever the compiler's FMA contraction does (a last-bit difference is enough to flip the sign-like Adam
+// update of parameters whose true gradient is zero, e.g. every k_proj.bias).
+struct AdamwCoef {
+  float b1, b2, one_m_b1, one_m_b2, eps, decay, step_size, inv_sqrt_bc2, gs;
+};
+__device__ __forceinline__ AdamwCoef adamw_coef(const float* __restrict__ hyper) {
+  AdamwCoef c;
+  const float lr = hyper[0], wd = hyper[4], bc1 = hyper[5], bc2 = hyper[6];
+  c.b1 = hyper[1]; c.b2 = hyper[2]; c.eps = hyper[3]; c.gs = hyper[7];
+  c.one_m_b1 = __fsub_rn(1.f, c.b1); c.one_m_b2 = __fsub_rn(1.f, c.b2);
+  c.decay = __fsub_rn(1.f, __fmul_rn(lr, wd));
+  c.step_size = __fdiv_rn(lr, bc1);
+  c.inv_sqrt_bc2 = __fdiv_rn(1.f, __fsqrt_rn(bc2));
+  return c;
+}
+__device__ __forceinline__ void adamw_elem(const AdamwCoef& c, float g, float& p, float& m, float& v) {
+  const float gr = __fmul_rn(g, c.gs);
+  p = __fmul_rn(p, c.decay);  // decoupled weight decay
+  m = __fmaf_rn(c.b1, m, __fmul_rn(c.one_m_b1, gr));
+  v = __fmaf_rn(c.b2, v, __fmul_rn(__fmul_rn(c.one_m_b2, gr), gr));
+  const float denom = __fadd_rn(__fmul_rn(__fsqrt_rn(v), c.inv_sqrt_bc2), c.eps);
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(c.step_size, m), denom));
+}
+
 }  // namespace vb

@@ -120,6 +120,53 @@ def vacnic_bucket_prefixes(enc_layers: int, dec_layers: int, group_size: int = 3
     return buckets
 
 
+def shard_of_range(a: int, b: int, rank: int, world: int, align: int = 64) -> Tuple[int, int]:
+    """Sub-range of [a, b) owned by `rank` when the range is cut into `world` contiguous chunks whose length is a multiple
+    of `align` elements (the last chunks may be short or empty).  Returns (begin, count)."""
+    n = b - a
+    chunk = (n + world - 1) // world
+    chunk = (chunk + align - 1) // align * align
+    lo = min(n, rank * chunk)
+    hi = min(n, lo + chunk)
+    return a + lo, hi - lo
+
+
+class PeerShards:
+    """Symmetric-memory view of the flat gradient buffer and bf16 shadow of every rank + the shard arithmetic of the
+    fused reduce-scatter / AdamW / all-gather kernel (csrc/dp.cu).  Needs CUDA + NCCL-backed process group; the pure
+    range logic (`shard_of_range`) is covered on CPU."""
+
+    def __init__(self, store, group, use_multicast: bool = False):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+        if not getattr(store, "symmetric", False):
+            raise ValueError("PeerShards needs a ParamStore allocated with symmetric=True")
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world not in (2, 4, 8):
+            raise ValueError(f"peer-memory optimizer supports 2, 4 or 8 ranks, got {self.world}")
+        self.h_grad = symm_mem.rendezvous(store.grad, group)
+        self.h_shadow = symm_mem.rendezvous(store.shadow, group)
+        self.grad_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in self.h_grad.buffer_ptrs])
+        self.shadow_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in self.h_shadow.buffer_ptrs])
+        if int(self.grad_ptrs[self.rank]) != store.grad.data_ptr() or int(self.shadow_ptrs[self.rank]) != store.shadow.data_ptr():
+            raise RuntimeError("symmetric-memory rendezvous returned a different local address than the store's buffers")
+        self.grad_mc = self.shadow_mc = 0
+        if use_multicast:
+            gm, sm = int(self.h_grad.multicast_ptr or 0), int(self.h_shadow.multicast_ptr or 0)
+            if gm and sm:
+                self.grad_mc, self.shadow_mc = gm, sm
+        self.bytes_read_remote = 0
+        self.bytes_written_remote = 0
+
+    def barrier(self, channel: int):
+        """All ranks reach this point of their communication stream (device-side, capturable in a CUDA graph)."""
+        self.h_grad.barrier(channel=channel)
+
+    def shard(self, a: int, b: int) -> Tuple[int, int]:
+        return shard_of_range(a, b, self.rank, self.world)
+
+
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous shard of `n_items` independent items (captions at inference) owned by `rank`."""
     base, extra = divmod(n_items, world)

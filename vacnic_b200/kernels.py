@@ -320,6 +320,14 @@ def optim_schedule(step_dev, hyper, base_lr, beta1, beta2, eps, weight_decay, wa
           "vacnic_optim_schedule")
 
 
+def dp_adamw_shard(grad_ptrs, shadow_ptrs, grad_mc, shadow_mc, world, rank, master, m, v, hyper, begin, count, max_blocks=0):
+    """Fused reduce-scatter + AdamW + all-gather over peer memory for this rank's shard [begin, begin+count) of the flat
+    buffers.  grad_ptrs / shadow_ptrs: ctypes arrays (c_uint64 * world) of every rank's buffer address."""
+    check(lib().vacnic_dp_adamw_shard(grad_ptrs, shadow_ptrs, int(grad_mc), int(shadow_mc), world, rank, ptr(master), ptr(m),
+                                      ptr(v), ptr(hyper), int(begin), int(count), int(max_blocks), stream_ptr()),
+          "vacnic_dp_adamw_shard")
+
+
 def clip_grad_scale(g, max_norm, base_scale, scratch, scale_out, norm_out=None):
     """scale_out[0] = base_scale * min(1, max_norm / (|base_scale| * ||g|| + 1e-6))  (clip_grad_norm_ folded into AdamW)."""
     check(lib().vacnic_clip_grad_scale(ptr(g), g.numel(), float(max_norm), float(base_scale), ptr(scratch), ptr(scale_out),

@@ -360,7 +360,7 @@ class VacnicBart(nn.Module):
     classes in src/models/ add `from_pretrained` / `generate` on top of it."""
 
     def __init__(self, cfg: VacnicConfig, device="cuda", p_drop: float = 0.1, seed: int = 0, tie_lm_head: bool = False,
-                 frozen: bool = False):
+                 frozen: bool = False, symmetric: Optional[bool] = None):
         super().__init__()
         self.cfg = cfg
         self.model = BartModel(cfg)
@@ -373,7 +373,15 @@ class VacnicBart(nn.Module):
             first += [f"model.decoder.layers.{i}.encoder_attn.k_proj.weight", f"model.decoder.layers.{i}.encoder_attn.v_proj.weight"]
         for i in range(cfg.dec_layers):
             first += [f"model.decoder.layers.{i}.encoder_attn.k_proj.bias", f"model.decoder.layers.{i}.encoder_attn.v_proj.bias"]
-        self.store = ParamStore(self, device, first=first, frozen=frozen)
+        if symmetric is None:
+            # one process per GPU under torch.distributed: gradient buffer and bf16 shadow live in symmetric memory so the
+            # rank-sharded optimizer step can run over NVLink peer loads / stores (VACNIC_DP_P2P=0 keeps plain allocations
+            # and the NCCL all-reduce path)
+            import os
+            dist = torch.distributed
+            symmetric = (not frozen and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                         and dist.get_backend() == "nccl" and os.environ.get("VACNIC_DP_P2P", "1") != "0")
+        self.store = ParamStore(self, device, first=first, frozen=frozen, symmetric=symmetric)
         self.rt = Runtime(self.store, p_drop=p_drop, seed=seed)
         self.model.encoder.bind(self.rt)
         self.model.decoder.bind(self.rt)
@@ -421,6 +429,10 @@ class VacnicBart(nn.Module):
 
     def get_decoder(self):
         return self.model.decoder
+
+    def state_dict(self, *args, **kwargs):
+        self.store.sync_master()  # rank-sharded optimizer: COLLECTIVE (call on every rank, like FSDP's state_dict)
+        return super().state_dict(*args, **kwargs)
 
     # ------------------------------------------------------------------ forward
     def forward(self, input_ids=None, attention_mask=None, decoder_input_ids=None, decoder_attention_mask=None,

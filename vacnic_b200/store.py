@@ -30,9 +30,11 @@ class Lin:
 
 
 class ParamStore:
-    def __init__(self, module: nn.Module, device, first: Sequence[str] = (), frozen: bool = False):
+    def __init__(self, module: nn.Module, device, first: Sequence[str] = (), frozen: bool = False, symmetric: bool = False):
         """`first`: parameter names to lay out first in their region, in the given order (used to make
-        fused groups adjacent).  `frozen`: no gradient / optimizer buffers (the CoLaM guide)."""
+        fused groups adjacent).  `frozen`: no gradient / optimizer buffers (the CoLaM guide).  `symmetric`: allocate
+        the gradient buffer and the bf16 shadow as torch symmetric memory (cuMem allocations every rank of the job can
+        map), so the data-parallel optimizer kernel reads / writes them across NVLink (vacnic_dp_adamw_shard)."""
         named = []
         seen = set()
         for n, p in module.named_parameters():
@@ -61,8 +63,18 @@ class ParamStore:
         self.device = torch.device(device)
         self.frozen = frozen
         self.master = torch.zeros(self.total, dtype=torch.float32, device=self.device)
-        self.shadow = torch.zeros(self.total, dtype=torch.bfloat16, device=self.device)
-        self.grad = None if frozen else torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.symmetric = bool(symmetric) and not frozen
+        if self.symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.shadow = symm_mem.empty(self.total, dtype=torch.bfloat16, device=self.device).zero_()
+            self.grad = symm_mem.empty(self.total, dtype=torch.float32, device=self.device).zero_()
+        else:
+            self.shadow = torch.zeros(self.total, dtype=torch.bfloat16, device=self.device)
+            self.grad = None if frozen else torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        # rank-sharded optimizer (trainer.TrainStep over peer memory): each rank keeps only ITS shard of the fp32 master
+        # current; `gather_master` (a collective every rank must reach) brings the rest up to date before anything reads it
+        self.master_sharded = False
+        self.gather_master = None
         self.params: Dict[str, nn.Parameter] = {}
         self._by_id: Dict[int, str] = {}
         remap: Dict[int, nn.Parameter] = {}
@@ -177,7 +189,13 @@ class ParamStore:
         AdamW kernel writes both copies itself and does not count."""
         return self.master._version != self._shadow_version
 
+    def sync_master(self):
+        """Make the fp32 master complete on this rank (no-op unless a rank-sharded optimizer owns it).  COLLECTIVE."""
+        if self.master_sharded and self.gather_master is not None:
+            self.gather_master()
+
     def refresh_shadow(self):
+        self.sync_master()
         K.cast_bf16(self.master, self.shadow)
         self._shadow_version = self.master._version
 

@@ -17,7 +17,7 @@ import torch
 
 from . import blocks as Bk
 from . import kernels as K
-from .dp import GradBuckets, vacnic_bucket_prefixes
+from .dp import GradBuckets, PeerShards, vacnic_bucket_prefixes
 from .modeling import VacnicBart, shift_tokens_right
 
 
@@ -32,7 +32,12 @@ class TrainStep:
     def __init__(self, model: VacnicBart, guide: Optional[VacnicBart], lr: float = 3e-5, weight_decay: float = 0.01,
                  betas=(0.9, 0.999), eps: float = 1e-8, warmup_steps: int = 0, total_steps: int = 1_000_000,
                  margin: float = 1.0, alpha: float = 0.5, secla_weight: float = 1.0, use_graph: bool = True,
-                 process_group=None, pipeline_optimizer: Optional[bool] = None, max_grad_norm: Optional[float] = None):
+                 process_group=None, pipeline_optimizer: Optional[bool] = None, max_grad_norm: Optional[float] = None,
+                 exchange: Optional[str] = None):
+        """`exchange` (world > 1): "p2p" = rank-sharded optimizer over NVLink peer memory (one fused reduce-scatter + AdamW +
+        all-gather kernel per bucket, csrc/dp.cu; needs the model's store in symmetric memory), "p2p-mc" = the same through
+        the NVSwitch multicast object (multimem.ld_reduce / multimem.st), "nccl" = in-place NCCL all-reduce of the fp32
+        gradient buckets followed by the replicated fused AdamW.  None = "p2p" when available, else "nccl"."""
         self.model, self.guide = model, guide
         self.cfg = model.cfg
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
@@ -58,6 +63,24 @@ class TrainStep:
         self.losses: Dict[str, torch.Tensor] = {}
         self.launches_per_step = 0
         self.buckets: Optional[GradBuckets] = None
+        self.p2p: Optional[PeerShards] = None
+        if exchange is None:
+            exchange = os.environ.get("VACNIC_DP_EXCHANGE") or ("p2p" if (self.world > 1 and st.symmetric and max_grad_norm is None)
+                                                                else "nccl")
+        if exchange not in ("p2p", "p2p-mc", "nccl"):
+            raise ValueError(f"exchange must be 'p2p', 'p2p-mc' or 'nccl', got {exchange!r}")
+        if exchange != "nccl":
+            if self.world == 1:
+                exchange = "nccl"
+            elif max_grad_norm is not None:
+                raise ValueError("clip_grad_norm_ needs the full reduced gradient: use exchange='nccl' with max_grad_norm")
+            else:
+                self.p2p = PeerShards(st, process_group, use_multicast=(exchange == "p2p-mc"))
+                if exchange == "p2p-mc" and not self.p2p.grad_mc:
+                    raise RuntimeError("exchange='p2p-mc': this system exposes no multicast (NVLS) mapping")
+                pipeline_optimizer = True
+                st.gather_master = self.gather_master
+        self.exchange = exchange
         if max_grad_norm is not None:
             pipeline_optimizer = False
         if pipeline_optimizer is None:
@@ -72,8 +95,8 @@ class TrainStep:
             # running: a finished layer's weights are not read again in this step.
             spans = {n: (st.offsets[n], p.numel()) for n, p in st.params.items()}
             prefixes = vacnic_bucket_prefixes(self.cfg.enc_layers, self.cfg.dec_layers, group_size=3)
-            self.buckets = GradBuckets(st.grad, spans, prefixes, group=process_group if self.world > 1 or
-                                       os.environ.get("VACNIC_DP_FORCE") else None)
+            self.buckets = GradBuckets(st.grad, spans, prefixes, group=process_group if (self.p2p is None and (
+                self.world > 1 or os.environ.get("VACNIC_DP_FORCE"))) else None)
             self.comm_stream = torch.cuda.Stream(device=dev)
             self._tag_to_bucket = {("dec", 0): 0}
             hi, k = self.cfg.enc_layers, 1
@@ -81,6 +104,17 @@ class TrainStep:
                 lo = max(0, hi - 3)
                 self._tag_to_bucket[("enc", lo)] = k
                 hi, k = lo, k + 1
+        # grid cap of the shard kernels that run BESIDE the backward pass (they only need enough loads in flight to fill
+        # NVLink, not the whole GPU); the exposed tail bucket uses the full grid
+        self.overlap_blocks = int(os.environ.get("VACNIC_DP_OVERLAP_BLOCKS", "64"))
+        # Overlap of the exchange with the backward pass.  NCCL path: on (the fp32 all-reduce is ~10 ms of wire time).  Peer-
+        # memory path: OFF by default -- measured on 2 x B200 (profiles/r2_dp_exchange_n2.md): the sharded update run entirely
+        # after the backward pass costs no more than the single-GPU AdamW it replaces (533 samples/s = two independent
+        # replicas), while shard kernels running beside the backward GEMMs slow those down by 5 ms / step (488 samples/s).
+        # VACNIC_DP_SERIAL=1 / VACNIC_DP_OVERLAP=1 force either behaviour.
+        env_serial, env_overlap = os.environ.get("VACNIC_DP_SERIAL"), os.environ.get("VACNIC_DP_OVERLAP")
+        self.overlap = (self.p2p is None) if (env_serial is None and env_overlap is None) else (
+            env_overlap == "1" if env_overlap is not None else env_serial != "1")
         self._g_txt = torch.ones(1, device=dev)
         self._g_margin = torch.full((1,), alpha, device=dev)
         self._g_secla = torch.full((1,), secla_weight, device=dev)
@@ -91,7 +125,7 @@ class TrainStep:
         communication stream by `_body` right after the (asynchronous) backward pass has been enqueued, so on the GPU
         timeline it still overlaps the remaining backward kernels — and no NCCL call is made from an engine thread."""
         i = self._tag_to_bucket.get(tag)
-        if i is None:
+        if i is None or not self.overlap:
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
@@ -137,7 +171,27 @@ class TrainStep:
             losses["secla"] = secla
         torch.autograd.backward(heads, grads)
         st.finish_backward()
-        if self.buckets is not None:  # sum over ranks; the 1/world mean is folded into hyper[7]
+        if self.p2p is not None:
+            # rank-sharded optimizer over NVLink peer memory.  Per bucket, on the communication stream: wait for the
+            # backward-pass marker, barrier (every rank's gradients of the bucket are final and nobody reads its weights
+            # again in this step), then ONE kernel per address range sums this rank's shard of all ranks' gradients,
+            # updates its master / moments and stores the new bf16 weights into every rank's shadow.
+            nb = len(self.buckets.buckets)
+            for i, ev in self._ready:
+                if not self.buckets.done[i]:
+                    self.buckets.done[i] = True
+                    self.comm_stream.wait_event(ev)
+                    with torch.cuda.stream(self.comm_stream):
+                        self._p2p_update(self.buckets.buckets[i], channel=i, max_blocks=self.overlap_blocks)
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                rest = [r for i, d in enumerate(self.buckets.done) if not d for r in self.buckets.buckets[i]] + list(self.buckets.rest)
+                self.buckets.done = [True] * nb
+                self._p2p_update(rest, channel=nb, max_blocks=0)       # exposed tail: the whole GPU
+                self.p2p.barrier(nb + 1)   # all ranks finished reading my gradients and writing my shadow: the step is over
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            st.master_sharded = True
+        elif self.buckets is not None:  # sum over ranks; the 1/world mean is folded into hyper[7]
             for i, ev in self._ready:  # bucket i only depends on the point of the backward pass where it became final
                 if not self.buckets.done[i]:
                     self.comm_stream.wait_event(ev)
@@ -157,6 +211,34 @@ class TrainStep:
                 K.clip_grad_scale(st.grad, self.max_grad_norm, 1.0 / self.world, self._clip_scratch, self.hyper[7:8], self.grad_norm)
             K.adamw(st.master, st.grad, self.m, self.v, st.shadow, self.hyper)
         return losses
+
+    def _p2p_update(self, ranges, channel: int, max_blocks: int):
+        st, pz = self.model.store, self.p2p
+        pz.barrier(channel)
+        for a, b in ranges:
+            begin, count = pz.shard(a, b)
+            if count > 0:
+                K.dp_adamw_shard(pz.grad_ptrs, pz.shadow_ptrs, pz.grad_mc, pz.shadow_mc, pz.world, pz.rank, st.master, self.m,
+                                 self.v, self.hyper, begin, count, max_blocks)
+
+    @torch.no_grad()
+    def gather_master(self):
+        """Rank-sharded optimizer: bring the fp32 master up to date on every rank (each shard is broadcast by its owner).
+        COLLECTIVE; used before checkpoints / state_dict() / any re-cast of the bf16 shadow, never inside the step."""
+        st = self.model.store
+        if self.p2p is None or not st.master_sharded:
+            return
+        torch.cuda.synchronize()
+        ranges = [r for bk in self.buckets.buckets for r in bk] + list(self.buckets.rest)
+        from .dp import shard_of_range
+        for a, b in ranges:
+            for r in range(self.world):
+                begin, count = shard_of_range(a, b, r, self.world)
+                if count > 0:
+                    torch.distributed.broadcast(st.master[begin:begin + count], src=torch.distributed.get_global_rank(
+                        self.pg, r) if self.pg is not None else r, group=self.pg)
+        st.master_sharded = False
+        st._shadow_version = st.master._version  # the shadow is already the bf16 image of these weights
 
     def _adamw_ranges(self, ranges):
         st = self.model.store
@@ -231,6 +313,7 @@ class TrainStep:
                 # the warm-up steps must not count as optimisation steps
                 st.master.copy_(saved[0]); self.m.copy_(saved[1]); self.v.copy_(saved[2])
                 model.rt.rng.state.copy_(saved[3]); self.step_dev.copy_(saved[4])
+                st.master_sharded = False  # the complete master was just restored on every rank
                 st.refresh_shadow()
                 del saved
                 self.graph = torch.cuda.CUDAGraph()
@@ -242,10 +325,15 @@ class TrainStep:
             return self.losses
         finally:
             st.external_step = False
+            if self.p2p is not None:
+                st.master_sharded = True  # from here on only this rank's shard of the fp32 master is current
 
     def close(self):
         """Drop the captured graph and break the model <-> step reference cycle (the backward-pass markers hold a bound
         method of this object), so the step's device memory is returned as soon as the caller drops its reference."""
+        if self.p2p is not None:
+            self.gather_master()  # COLLECTIVE: leave every rank with the complete fp32 master
+            self.model.store.gather_master = None
         self.graph = None
         self.static.clear()
         self.losses = {}
