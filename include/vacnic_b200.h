@@ -107,11 +107,14 @@ int vacnic_gemm(const vacnic_gemm_desc* d, void* stream);
  * ------------------------------------------------------------------------------------------ */
 /* y = LN(res + dropout(x)).  Output row r lands at y + (r / rows_per_group) * y_group_stride +
  * (r % rows_per_group) * d, so a result can be written straight into a slice of the prefix/NER
- * concat buffer (torch.cat at MFULL:691).  rows_per_group = 0 means contiguous output. */
+ * concat buffer (torch.cat at MFULL:691).  rows_per_group = 0 means contiguous output.
+ * res32 (optional, fp32 [rows, d]): the residual in fp32 (used instead of `res`); y32 (optional, fp32 [rows, d]): fp32 copy
+ * of the output.  Together they carry the residual stream in fp32 from block to block, like the reference under
+ * torch.autocast (LayerNorm runs and returns fp32 there) -- the GEMMs still consume the bf16 `y`. */
 int vacnic_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
                              float* mean, float* rstd, int64_t rows, int32_t d, int64_t rows_per_group,
                              int64_t y_group_stride, float eps, float p_drop, const uint64_t* rng_state,
-                             uint32_t salt, void* stream);
+                             uint32_t salt, const float* res32, float* y32, void* stream);
 /* Gradients of the above: dsum = d(res + dropout(x)) (written or accumulated), dx = dropout-masked
  * dsum (skipped when dx == dsum or null), dgamma/dbeta/dbias are accumulated atomically (fp32);
  * dbias is the bias gradient of the linear layer that produced x (column sums of dx). */
@@ -120,16 +123,20 @@ int vacnic_add_layernorm_bwd(const void* dy, const void* x, const void* res, con
                              int64_t rows, int32_t d, int64_t rows_per_group, int64_t dy_group_stride, float p_drop,
                              const uint64_t* rng_state, uint32_t salt, int32_t accumulate_dsum, void* stream);
 /* y = dropout(LN(tok[ids] + pos[(r % seq_len) + pos_offset])): MFULL:1243-1249 (article),
- * 1254-1260 (names, embed_tokens_ner), 1555-1563 (decoder, pos_offset = 2 + cached length). */
+ * 1254-1260 (names, embed_tokens_ner), 1555-1563 (decoder, pos_offset = 2 + cached length).
+ * y32 (optional): fp32 copy of the output (start of the fp32 residual stream).  pos_ids (optional, int32 [rows]): the
+ * position of every row given explicitly instead of r % seq_len -- rows of several articles packed back to back
+ * (varlen batches: the collate's padding, DNYT:957-972, never reaches the device). */
 int vacnic_embed_ln_fwd(const int64_t* ids, const void* tok, const void* pos, const float* gamma, const float* beta,
                         void* y, float* mean, float* rstd, int64_t rows, int32_t seq_len, int32_t pos_offset,
-                        int32_t d, float eps, float p_drop, const uint64_t* rng_state, uint32_t salt, void* stream);
+                        int32_t d, float eps, float p_drop, const uint64_t* rng_state, uint32_t salt, float* y32,
+                        const int32_t* pos_ids, void* stream);
 /* Scatter-add gradients into the fp32 embedding tables; rows with ids == pad_id get no token
  * gradient (nn.Embedding padding_idx, MFULL:1115,1150). */
 int vacnic_embed_ln_bwd(const void* dy, const int64_t* ids, const void* tok, const void* pos, const float* gamma,
                         const float* mean, const float* rstd, float* dtok, float* dpos, float* dgamma, float* dbeta,
                         int64_t rows, int32_t seq_len, int32_t pos_offset, int32_t d, int32_t pad_id, float p_drop,
-                        const uint64_t* rng_state, uint32_t salt, void* stream);
+                        const uint64_t* rng_state, uint32_t salt, const int32_t* pos_ids, void* stream);
 /* get_embedding_ner (TRAIN:112-133): out[span] = mean_t LN(tok[ids[span,t]] + pos[t + 2]), fp32. */
 int vacnic_names_embed(const int64_t* ids, const void* tok, const void* pos, const float* gamma, const float* beta,
                        float* out, int64_t spans, int32_t len, int32_t d, float eps, void* stream);
@@ -238,10 +245,10 @@ int vacnic_secla_bwd(const float* workspace, const float* names, const float* gs
  * Ping-pong state buffers hold two copies; step t reads copy (t & 1) and writes copy ((t+1) & 1).
  * ------------------------------------------------------------------------------------------ */
 /* y[r] = LN(tok[seq[r][cur_len-1]] + pos[cur_len-1 + pos_offset])  (MFULL:1552-1563, cached).
- * seq: int32 [R][maxT] (pingpong = 0) or [2][R][maxT] (pingpong = 1). */
+ * seq: int32 [R][maxT] (pingpong = 0) or [2][R][maxT] (pingpong = 1).  y32 (optional): fp32 copy of y. */
 int vacnic_decode_embed_ln(const int32_t* seq, const int32_t* cur_len, const void* tok, const void* pos,
                            const float* gamma, const float* beta, void* y, int32_t R, int32_t maxT, int32_t d,
-                           int32_t pos_offset, int32_t pingpong, float eps, void* stream);
+                           int32_t pos_offset, int32_t pingpong, float eps, float* y32, void* stream);
 /* Self-attention of the newest token over the cache (MFULL:490-495,509-563).  qkv bf16 [R][3d] in
  * [k|v|q] order; the new k/v are appended to kcache/vcache [R][maxT][d] at position cur_len-1; position
  * s < cur_len-1 is read from row anc[(cur_len&1)][r][s] (null anc = own row: greedy).  out bf16 [R][d]. */

@@ -12,10 +12,10 @@ F64 = C.c_double
 # name -> argtypes (restype is int for all of these)
 SIGNATURES = {
     "vacnic_gemm": [P, P],
-    "vacnic_add_layernorm_fwd": [P, P, P, P, P, P, P, I64, I32, I64, I64, F32, F32, P, U32, P],
+    "vacnic_add_layernorm_fwd": [P, P, P, P, P, P, P, I64, I32, I64, I64, F32, F32, P, U32, P, P, P],
     "vacnic_add_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, I64, I64, F32, P, U32, I32, P],
-    "vacnic_embed_ln_fwd": [P, P, P, P, P, P, P, P, I64, I32, I32, I32, F32, F32, P, U32, P],
-    "vacnic_embed_ln_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, I32, I32, I32, F32, P, U32, P],
+    "vacnic_embed_ln_fwd": [P, P, P, P, P, P, P, P, I64, I32, I32, I32, F32, F32, P, U32, P, P, P],
+    "vacnic_embed_ln_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, I32, I32, I32, F32, P, U32, P, P],
     "vacnic_names_embed": [P, P, P, P, P, P, I64, I32, I32, F32, P],
     "vacnic_softmax_fwd": [P, P, P, I32, I32, I32, I32, I32, I32, I32, P],
     "vacnic_softmax_bwd": [P, P, P, I64, I32, I32, P],
@@ -39,7 +39,7 @@ SIGNATURES = {
     "vacnic_colam_bwd": [P, P, P, P, P, F32, P, I32, I32, I32, I64, I32, P],
     "vacnic_secla_fwd": [P, P, P, P, I32, I32, I32, I32, P],
     "vacnic_secla_bwd": [P, P, P, F32, P, I32, I32, I32, I32, I32, P],
-    "vacnic_decode_embed_ln": [P, P, P, P, P, P, P, I32, I32, I32, I32, I32, F32, P],
+    "vacnic_decode_embed_ln": [P, P, P, P, P, P, P, I32, I32, I32, I32, I32, F32, P, P],
     "vacnic_decode_self_attn": [P, P, P, P, P, P, I32, I32, I32, I32, P],
     "vacnic_decode_cross_attn": [P, I64, P, P, I64, I64, I64, P, P, P, I64, I32, I32, I32, I32, I32, P],
     "vacnic_mask_key_len": [P, P, I32, I32, P],

@@ -29,6 +29,10 @@ class Runtime:
         self.rng = K.Rng(store.device, seed)
         self._salt = 0
         self.grad_hook = None
+        # residual stream in fp32: every LayerNorm also emits its output in fp32 and the next block adds its branch to THAT
+        # (what the reference does under torch.autocast, where LayerNorm runs and returns fp32); the GEMMs consume the
+        # bf16 copy.  Forward only -- the backward pass keeps using the bf16 copy to rebuild x_hat.
+        self.res_fp32 = True
         # requires-grad root every block of a forward pass hangs off (store.anchor, or its ParamTouchFn image under DDP)
         self.fwd_anchor = store.anchor
 
@@ -127,8 +131,9 @@ class AttnBlockFn(torch.autograd.Function):
     the hoisted decoder cross-K/V GEMM) with gradients written to `dkv_pre`."""
 
     @staticmethod
-    def forward(ctx, x, kv_src, kv_pre, rt: Runtime, lin_qkv: Lin, lin_q: Lin, lin_kv: Lin, lin_o: Lin, ln: LN,
+    def forward(ctx, x, x32, kv_src, kv_pre, rt: Runtime, lin_qkv: Lin, lin_q: Lin, lin_kv: Lin, lin_o: Lin, ln: LN,
                 H: int, key_mask, causal: bool, use_dropout: bool, kv_col0: int, dkv_all, return_dkv_all: bool):
+        """x: bf16 [B, Sq, d]; x32: the same state in fp32 (or None).  Returns (y bf16, y32 fp32 or None)."""
         B, Sq, d = x.shape
         hd = d // H
         x2 = x.view(B * Sq, d)
@@ -150,7 +155,14 @@ class AttnBlockFn(torch.autograd.Function):
         O, stats = sdpa_fwd(q4, k4, v4, key_mask, causal, want_stats=not rt.store.frozen)
         a = K.gemm(O.view(B * Sq, d), lin_o.w16, bias=lin_o.b32)
         p = rt.drop if use_dropout else 0.0
-        y, mean, rstd = K.add_layernorm_fwd(a, x2, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt)
+        y32 = None
+        if rt.res_fp32:
+            y, mean, rstd, y32 = K.add_layernorm_fwd(a, x2, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt, want_y32=True,
+                                                     res32=None if x32 is None else x32.view(B * Sq, d))
+            y32 = y32.view(B, Sq, d)
+            ctx.mark_non_differentiable(y32)
+        else:
+            y, mean, rstd = K.add_layernorm_fwd(a, x2, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt)
         ctx.rt, ctx.lins, ctx.ln, ctx.H, ctx.p = rt, (lin_qkv, lin_q, lin_kv, lin_o), ln, H, p
         ctx.saved = (x2, kv_src, qkv, kvp, stats, O, a, mean, rstd, q4, k4, v4)
         ctx.mask = (key_mask, causal)
@@ -158,10 +170,10 @@ class AttnBlockFn(torch.autograd.Function):
         ctx.dkv_pre = dkv_all.view(B * Sk, -1)[:, kv_col0:kv_col0 + 2 * d] if hoisted else None
         ctx.dkv_all = dkv_all if (hoisted and return_dkv_all) else None
         ctx.shape = (B, Sq, d, Sk)
-        return y.view(B, Sq, d)
+        return y.view(B, Sq, d), y32
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dy32=None):
         rt, ln, H = ctx.rt, ctx.ln, ctx.H
         lin_qkv, lin_q, lin_kv, lin_o = ctx.lins
         x2, kv_src, qkv, kvp, stats, O, a, mean, rstd, q4, k4, v4 = ctx.saved
@@ -197,7 +209,7 @@ class AttnBlockFn(torch.autograd.Function):
         ctx.saved = None
         # hoisted cross K/V: every layer wrote its slice of the shared gradient buffer in place; the
         # block that runs last in the backward pass (layer 0) hands the whole buffer to autograd.
-        return (dsum.view(B, Sq, d), dkv_src, ctx.dkv_all) + (None,) * 13
+        return (dsum.view(B, Sq, d), None, dkv_src, ctx.dkv_all) + (None,) * 13
 
 
 class MlpBlockFn(torch.autograd.Function):
@@ -205,7 +217,8 @@ class MlpBlockFn(torch.autograd.Function):
     MFULL:647-653, 658-664, 738-744, 868-878) or y = z (the ClipCap prefix MLP, MFULL:111-123)."""
 
     @staticmethod
-    def forward(ctx, x, anchor, rt: Runtime, lin1: Lin, lin2: Lin, act: int, ln: Optional[LN]):
+    def forward(ctx, x, x32, anchor, rt: Runtime, lin1: Lin, lin2: Lin, act: int, ln: Optional[LN]):
+        """Returns (y bf16, y32 fp32 or None); x32 = fp32 copy of x (residual stream) or None."""
         shp = x.shape
         d_in = shp[-1]
         x2 = x.reshape(-1, d_in)
@@ -213,9 +226,16 @@ class MlpBlockFn(torch.autograd.Function):
         aux = torch.empty(rows, lin1.out_f, dtype=torch.bfloat16, device=x.device) if act == K.ACT_GELU else None
         h = K.gemm(x2, lin1.w16, bias=lin1.b32, act=act, aux_out=aux)
         z = K.gemm(h, lin2.w16, bias=lin2.b32)
+        y32 = None
         if ln is not None:
             p = rt.drop
-            y, mean, rstd = K.add_layernorm_fwd(z, x2, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt)
+            if rt.res_fp32:
+                y, mean, rstd, y32 = K.add_layernorm_fwd(z, x2, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt, want_y32=True,
+                                                         res32=None if x32 is None else x32.reshape(-1, d_in))
+                y32 = y32.view(shp)
+                ctx.mark_non_differentiable(y32)
+            else:
+                y, mean, rstd = K.add_layernorm_fwd(z, x2, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt)
             ctx.lnstate = (z, mean, rstd, p)
             out = y.view(shp)
         else:
@@ -224,10 +244,10 @@ class MlpBlockFn(torch.autograd.Function):
         ctx.rt, ctx.lin1, ctx.lin2, ctx.act, ctx.ln = rt, lin1, lin2, act, ln
         ctx.saved = (x2, aux, h)
         ctx.in_shape = shp
-        return out
+        return out, y32
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dy32=None):
         rt, lin1, lin2, act, ln = ctx.rt, ctx.lin1, ctx.lin2, ctx.act, ctx.ln
         x2, aux, h = ctx.saved
         rows = x2.shape[0]
@@ -252,7 +272,7 @@ class MlpBlockFn(torch.autograd.Function):
         else:
             dx = None
         ctx.saved = None
-        return (dx,) + (None,) * 6
+        return (dx,) + (None,) * 7
 
 
 class LinearFn(torch.autograd.Function):
@@ -291,23 +311,30 @@ class EmbedFn(torch.autograd.Function):
     """y = dropout(LN(tok[ids] + pos[t + offset]))  (MFULL:1243-1249, 1254-1260, 1555-1563)."""
 
     @staticmethod
-    def forward(ctx, anchor, ids, rt: Runtime, tok_p, pos_p, ln: LN, pos_offset: int, pad_id: int):
+    def forward(ctx, anchor, ids, rt: Runtime, tok_p, pos_p, ln: LN, pos_offset: int, pad_id: int, pos_ids=None):
+        """Returns (y bf16, y32 fp32 or None).  `pos_ids` (int32, one per id): explicit positions for packed rows."""
         st = rt.store
         tok16, pos16 = st.w16(tok_p), st.w16(pos_p)
         p = rt.drop
-        y, mean, rstd = K.embed_ln_fwd(ids, tok16, pos16, ln.g, ln.b, pos_offset=pos_offset, p_drop=p, rng=rt.rng,
-                                       salt=ln.salt)
-        ctx.rt, ctx.ln, ctx.args = rt, ln, (ids, tok_p, pos_p, tok16, pos16, mean, rstd, pos_offset, pad_id, p)
-        return y
+        y32 = None
+        if rt.res_fp32:
+            y, mean, rstd, y32 = K.embed_ln_fwd(ids, tok16, pos16, ln.g, ln.b, pos_offset=pos_offset, p_drop=p, rng=rt.rng,
+                                                salt=ln.salt, want_y32=True, pos_ids=pos_ids)
+            ctx.mark_non_differentiable(y32)
+        else:
+            y, mean, rstd = K.embed_ln_fwd(ids, tok16, pos16, ln.g, ln.b, pos_offset=pos_offset, p_drop=p, rng=rt.rng,
+                                           salt=ln.salt, pos_ids=pos_ids)
+        ctx.rt, ctx.ln, ctx.args = rt, ln, (ids, tok_p, pos_p, tok16, pos16, mean, rstd, pos_offset, pad_id, p, pos_ids)
+        return y, y32
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dy32=None):
         rt, ln = ctx.rt, ctx.ln
-        ids, tok_p, pos_p, tok16, pos16, mean, rstd, pos_offset, pad_id, p = ctx.args
+        ids, tok_p, pos_p, tok16, pos16, mean, rstd, pos_offset, pad_id, p, pos_ids = ctx.args
         st = rt.store
         K.embed_ln_bwd(dy.contiguous(), ids, tok16, pos16, ln.g, mean, rstd, st.g32(tok_p), st.g32(pos_p), ln.gg, ln.gb,
-                       pos_offset=pos_offset, pad_id=pad_id, p_drop=p, rng=rt.rng, salt=ln.salt)
-        return (None,) * 8
+                       pos_offset=pos_offset, pad_id=pad_id, p_drop=p, rng=rt.rng, salt=ln.salt, pos_ids=pos_ids)
+        return (None,) * 9
 
 
 class NerMapFn(torch.autograd.Function):

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256)
 decode_embed_ln_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ cur_len_p,
                        const __nv_bfloat16* __restrict__ tok, const __nv_bfloat16* __restrict__ pos,
                        const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                       int R, int maxT, int d, int pos_offset, int pingpong, float eps) {
+                       int R, int maxT, int d, int pos_offset, int pingpong, float eps, float* __restrict__ y32) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -81,6 +81,11 @@ decode_embed_ln_kernel(const int32_t* __restrict__ seq, const int32_t* __restric
     u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
     u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
     yp[vi] = u;
+    if (y32) {  // fp32 residual stream (same as the teacher-forced forward)
+      float4* y4 = reinterpret_cast<float4*>(y32 + static_cast<long long>(row) * d) + vi * 2;
+      y4[0] = make_float4(o[0], o[1], o[2], o[3]);
+      y4[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
   }
 }
 
@@ -718,7 +723,7 @@ using namespace vb;
 
 extern "C" int vacnic_decode_embed_ln(const int32_t* seq, const int32_t* cur_len, const void* tok, const void* pos,
                                       const float* gamma, const float* beta, void* y, int32_t R, int32_t maxT, int32_t d,
-                                      int32_t pos_offset, int32_t pingpong, float eps, void* stream) {
+                                      int32_t pos_offset, int32_t pingpong, float eps, float* y32, void* stream) {
   VB_REQUIRE(seq && cur_len && tok && pos && gamma && beta && y, "decode_embed_ln: null pointer");
   VB_REQUIRE(R > 0 && maxT > 0 && d > 0 && d % 256 == 0 && d <= 1024, "decode_embed_ln: d must be 256/512/768/1024");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -727,10 +732,10 @@ extern "C" int vacnic_decode_embed_ln(const int32_t* seq, const int32_t* cur_len
   const __nv_bfloat16* ps = static_cast<const __nv_bfloat16*>(pos);
   __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
   switch (d / 256) {
-    case 1: launch_pdl(decode_embed_ln_kernel<1>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
-    case 2: launch_pdl(decode_embed_ln_kernel<2>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
-    case 3: launch_pdl(decode_embed_ln_kernel<3>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
-    default: launch_pdl(decode_embed_ln_kernel<4>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps); break;
+    case 1: launch_pdl(decode_embed_ln_kernel<1>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps, y32); break;
+    case 2: launch_pdl(decode_embed_ln_kernel<2>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps, y32); break;
+    case 3: launch_pdl(decode_embed_ln_kernel<3>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps, y32); break;
+    default: launch_pdl(decode_embed_ln_kernel<4>, grid, dim3(256), 0, s, seq, cur_len, tk, ps, gamma, beta, yy, R, maxT, d, pos_offset, pingpong, eps, y32); break;
   }
   count_launch();
   return check_last("decode_embed_ln");

@@ -56,6 +56,8 @@ struct LnArgs {
   float p_drop;
   const unsigned long long* rng;  // device step counter (null when p_drop == 0)
   uint32_t salt;
+  const float* res32;  // [rows, d] fp32 residual (takes precedence over `res`), or null
+  float* y32;          // [rows, d] fp32 copy of the output = the next block's residual (contiguous rows), or null
 };
 
 // v[j][e] for lane: vector index (lane + 32*j), element e.
@@ -100,7 +102,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
       for (int e = 0; e < 8; ++e)
         v[j][e] = keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + vi * 8 + e, thr) ? v[j][e] * inv_keep : 0.f;
     }
-    if (rp) {
+    if (a.res32) {  // residual stream carried in fp32 (what torch.autocast keeps: LayerNorm outputs stay fp32)
+      const float4* r4 = reinterpret_cast<const float4*>(a.res32 + row * a.d) + vi * 2;
+      const float4 r0 = __ldg(r4), r1 = __ldg(r4 + 1);
+      v[j][0] += r0.x; v[j][1] += r0.y; v[j][2] += r0.z; v[j][3] += r0.w;
+      v[j][4] += r1.x; v[j][5] += r1.y; v[j][6] += r1.z; v[j][7] += r1.w;
+    } else if (rp) {
       float r[8];
       unpack8(__ldg(rp + vi), r);
 #pragma unroll
@@ -114,6 +121,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
     if (a.rstd) a.rstd[row] = rstd;
   }
   uint4* yp = reinterpret_cast<uint4*>(a.y + (row / a.rpg) * a.y_gs + (row % a.rpg) * a.d);
+  float4* y4 = a.y32 ? reinterpret_cast<float4*>(a.y32 + row * a.d) : nullptr;
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     const int vi = lane + 32 * j;
@@ -127,6 +135,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * g[e] + b[e];
     yp[vi] = pack8(o);
+    if (y4) {
+      y4[vi * 2] = make_float4(o[0], o[1], o[2], o[3]);
+      y4[vi * 2 + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
   }
 }
 
@@ -270,6 +282,8 @@ struct EmbArgs {
   float eps, p_drop;
   const unsigned long long* rng;
   uint32_t salt;
+  float* y32;              // [rows, d] fp32 copy of the output, or null
+  const int* pos_ids;      // [rows] explicit position (before pos_offset) of every row, or null = row % seq_len
 };
 
 template <int VPL>
@@ -278,7 +292,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) embed_ln_fwd_kernel(const
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= a.rows) return;
   const long long id = a.ids[row];
-  const int p = static_cast<int>(row % a.seq_len) + a.pos_offset;
+  const int p = (a.pos_ids ? a.pos_ids[row] : static_cast<int>(row % a.seq_len)) + a.pos_offset;
   const uint4* tp = reinterpret_cast<const uint4*>(a.tok + id * a.d);
   const uint4* pp = reinterpret_cast<const uint4*>(a.pos + static_cast<long long>(p) * a.d);
   float v[VPL][8];
@@ -301,6 +315,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) embed_ln_fwd_kernel(const
   const uint32_t thr = drop_thresh(a.p_drop);
   const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
   uint4* yp = reinterpret_cast<uint4*>(a.y + row * a.d);
+  float4* y4 = a.y32 ? reinterpret_cast<float4*>(a.y32 + row * a.d) : nullptr;
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     const int vi = lane + 32 * j;
@@ -317,6 +332,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) embed_ln_fwd_kernel(const
       if (drop) o[e] = keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + vi * 8 + e, thr) ? o[e] * inv_keep : 0.f;
     }
     yp[vi] = pack8(o);
+    if (y4) {
+      y4[vi * 2] = make_float4(o[0], o[1], o[2], o[3]);
+      y4[vi * 2 + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
   }
 }
 
@@ -337,6 +356,7 @@ struct EmbBwdArgs {
   float p_drop;
   const unsigned long long* rng;
   uint32_t salt;
+  const int* pos_ids;
 };
 
 template <int VPL>
@@ -355,7 +375,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) embed_ln_bwd_kernel(const
   const long long wstride = static_cast<long long>(gridDim.x) * kWarpsPerBlock;
   for (long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; row < a.rows; row += wstride) {
     const long long id = a.ids[row];
-    const int p = static_cast<int>(row % a.seq_len) + a.pos_offset;
+    const int p = (a.pos_ids ? a.pos_ids[row] : static_cast<int>(row % a.seq_len)) + a.pos_offset;
     const uint4* tp = reinterpret_cast<const uint4*>(a.tok + id * a.d);
     const uint4* pp = reinterpret_cast<const uint4*>(a.pos + static_cast<long long>(p) * a.d);
     const uint4* dyp = reinterpret_cast<const uint4*>(a.dy + row * a.d);
@@ -488,8 +508,11 @@ using namespace vb;
 extern "C" int vacnic_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta,
                                         void* y, float* mean, float* rstd, int64_t rows, int32_t d,
                                         int64_t rows_per_group, int64_t y_group_stride, float eps, float p_drop,
-                                        const uint64_t* rng_state, uint32_t salt, void* stream) {
+                                        const uint64_t* rng_state, uint32_t salt, const float* res32, float* y32,
+                                        void* stream) {
   VB_REQUIRE(x && gamma && beta && y, "add_layernorm_fwd: null pointer");
+  VB_REQUIRE(((reinterpret_cast<uintptr_t>(res32) | reinterpret_cast<uintptr_t>(y32)) & 15) == 0,
+             "add_layernorm_fwd: fp32 residual buffers must be 16-byte aligned");
   VB_REQUIRE(rows >= 0 && d > 0 && d % 256 == 0, "add_layernorm_fwd: bad shape rows=%lld d=%d", (long long)rows, d);
   VB_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng_state), "add_layernorm_fwd: bad dropout args");
   if (rows == 0) return VACNIC_OK;
@@ -501,6 +524,7 @@ extern "C" int vacnic_add_layernorm_fwd(const void* x, const void* res, const fl
   a.y_gs = rows_per_group > 0 ? y_group_stride : 0;
   VB_REQUIRE(a.y_gs % 8 == 0, "add_layernorm_fwd: group stride must be a multiple of 8 elements");
   a.eps = eps; a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
+  a.res32 = res32; a.y32 = y32;
   const int grid = static_cast<int>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   VB_DISPATCH_VPL(d, (launch_pdl(add_layernorm_fwd_kernel<VPL>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, a)));
@@ -538,7 +562,8 @@ extern "C" int vacnic_add_layernorm_bwd(const void* dy, const void* x, const voi
 extern "C" int vacnic_embed_ln_fwd(const int64_t* ids, const void* tok, const void* pos, const float* gamma,
                                    const float* beta, void* y, float* mean, float* rstd, int64_t rows,
                                    int32_t seq_len, int32_t pos_offset, int32_t d, float eps, float p_drop,
-                                   const uint64_t* rng_state, uint32_t salt, void* stream) {
+                                   const uint64_t* rng_state, uint32_t salt, float* y32, const int32_t* pos_ids,
+                                   void* stream) {
   VB_REQUIRE(ids && tok && pos && gamma && beta && y, "embed_ln_fwd: null pointer");
   VB_REQUIRE(rows >= 0 && seq_len > 0 && d > 0 && d % 256 == 0, "embed_ln_fwd: bad shape");
   VB_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng_state), "embed_ln_fwd: bad dropout args");
@@ -549,6 +574,7 @@ extern "C" int vacnic_embed_ln_fwd(const int64_t* ids, const void* tok, const vo
   a.y = static_cast<__nv_bfloat16*>(y); a.mean = mean; a.rstd = rstd; a.rows = rows; a.seq_len = seq_len;
   a.pos_offset = pos_offset; a.d = d; a.eps = eps; a.p_drop = p_drop;
   a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
+  a.y32 = y32; a.pos_ids = pos_ids;
   const int grid = static_cast<int>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   VB_DISPATCH_VPL(d, (embed_ln_fwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(a)));
@@ -560,7 +586,7 @@ extern "C" int vacnic_embed_ln_bwd(const void* dy, const int64_t* ids, const voi
                                    const float* gamma, const float* mean, const float* rstd, float* dtok,
                                    float* dpos, float* dgamma, float* dbeta, int64_t rows, int32_t seq_len,
                                    int32_t pos_offset, int32_t d, int32_t pad_id, float p_drop,
-                                   const uint64_t* rng_state, uint32_t salt, void* stream) {
+                                   const uint64_t* rng_state, uint32_t salt, const int32_t* pos_ids, void* stream) {
   VB_REQUIRE(dy && ids && tok && pos && gamma && mean && rstd, "embed_ln_bwd: null pointer");
   VB_REQUIRE(rows >= 0 && seq_len > 0 && d > 0 && d % 256 == 0, "embed_ln_bwd: bad shape");
   if (rows == 0) return VACNIC_OK;
@@ -570,6 +596,7 @@ extern "C" int vacnic_embed_ln_bwd(const void* dy, const int64_t* ids, const voi
   a.gamma = gamma; a.mean = mean; a.rstd = rstd; a.dtok = dtok; a.dpos = dpos; a.dgamma = dgamma; a.dbeta = dbeta;
   a.rows = rows; a.seq_len = seq_len; a.pos_offset = pos_offset; a.d = d; a.pad_id = pad_id; a.p_drop = p_drop;
   a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
+  a.pos_ids = pos_ids;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = bwd_grid(rows);
   VB_DISPATCH_VPL(d, (embed_ln_bwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(a)));

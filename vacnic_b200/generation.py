@@ -49,6 +49,7 @@ class Generator:
             return torch.empty(*shape, dtype=dtype, device=dev)
 
         self.x, self.x2, self.attn, self.proj, self.qb = (buf(R, d) for _ in range(5))
+        self.x32, self.x32b = buf(R, d, dtype=f32), buf(R, d, dtype=f32)  # fp32 residual stream, like the training forward
         self.qkv, self.h = buf(R, 3 * d), buf(R, f)
         self.ldp = (V + 7) // 8 * 8
         self.logits = buf(R, self.ldp, dtype=f32)
@@ -132,26 +133,28 @@ class Generator:
         d, H, V = cfg.d_model, cfg.heads, cfg.vocab
         beam = self.nb > 1
         x, x2 = self.x, self.x2
+        r32, r32b = (self.x32, self.x32b) if model.rt.res_fp32 else (None, None)
         K.decode_embed_ln(st["run_seq"] if beam else st["seq"], st["cur_len"], store.w16(dec.embed_tokens.weight),
                           store.w16(dec.embed_positions.weight), dec.ln_emb.g, dec.ln_emb.b, x, self.maxT, pos_offset=2,
-                          pingpong=beam)
+                          pingpong=beam, y32=r32)
         anc = st["run_anc"] if beam else None
         for l, layer in enumerate(dec.layers):
             a = layer.self_attn
             K.gemm(x, a.lin_qkv.w16, out=self.qkv, bias=a.lin_qkv.b32)
             K.decode_self_attn(self.qkv, self.kc[l], self.vc[l], anc, st["cur_len"], self.attn, H, self.maxT)
             K.gemm(self.attn, a.lin_o.w16, out=self.proj, bias=a.lin_o.b32)
-            K.add_layernorm_fwd(self.proj, x, a.ln.g, a.ln.b, out=x2, want_stats=False)
+            K.add_layernorm_fwd(self.proj, x, a.ln.g, a.ln.b, out=x2, want_stats=False, res32=r32, y32_out=r32b)
             a = layer.encoder_attn
             K.gemm(x2, a.lin_q.w16, out=self.qb, bias=a.lin_q.b32)
             K.decode_cross_attn(self.qb, self.cross_kv[l, :, 0], self.cross_kv[l, :, 1], self.key_mask, self.key_len, self.attn,
                                 self.nb)
             K.gemm(self.attn, a.lin_o.w16, out=self.proj, bias=a.lin_o.b32)
-            K.add_layernorm_fwd(self.proj, x2, a.ln.g, a.ln.b, out=x, want_stats=False)
+            K.add_layernorm_fwd(self.proj, x2, a.ln.g, a.ln.b, out=x, want_stats=False, res32=r32b, y32_out=r32)
             K.gemm(x, layer.lin_fc1.w16, out=self.h, bias=layer.lin_fc1.b32, act=K.ACT_GELU)
             K.gemm(self.h, layer.lin_fc2.w16, out=self.proj, bias=layer.lin_fc2.b32)
-            K.add_layernorm_fwd(self.proj, x, layer.ln_final.g, layer.ln_final.b, out=x2, want_stats=False)
+            K.add_layernorm_fwd(self.proj, x, layer.ln_final.g, layer.ln_final.b, out=x2, want_stats=False, res32=r32, y32_out=r32b)
             x, x2 = x2, x
+            r32, r32b = r32b, r32
         K.gemm(x, model.lin_lm.w16, out=self.logits[:, :V], bias=model.final_logits_bias.view(-1))
         K.decode_topk(self.logits, V, self.Kc, self.top_lp, self.top_idx)
         if beam:

@@ -171,21 +171,27 @@ class Rng:
 
 
 def add_layernorm_fwd(x, res, gamma, beta, out=None, rows_per_group=0, group_stride=0, p_drop=0.0, rng=None, salt=0,
-                      want_stats=True):
+                      want_stats=True, res32=None, want_y32=False, y32_out=None):
     """y = LN(res + dropout(x)); returns (y, mean, rstd).  `out` may be a [rows, d] view whose groups of
     `rows_per_group` rows are `group_stride` elements apart (slice of the prefix/NER concat buffer).
-    `want_stats=False` (inference) skips the per-row statistics the backward pass needs."""
+    `want_stats=False` (inference) skips the per-row statistics the backward pass needs.
+    `res32` (fp32 residual, replaces `res`) / `want_y32` (also return the output in fp32 as a 4th value): the fp32
+    residual stream."""
     d = x.shape[-1]
     rows = x.numel() // d
     _c(x, torch.bfloat16, "x"); _c(res, torch.bfloat16, "res"); _c(gamma, torch.float32, "gamma"); _c(beta, torch.float32, "beta")
+    _c(res32, torch.float32, "res32")
     if out is None:
         out = torch.empty_like(x)
+    y32 = y32_out if y32_out is not None else (torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_y32 else None)
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
     check(lib().vacnic_add_layernorm_fwd(ptr(x), ptr(res), ptr(gamma), ptr(beta), ptr(out), ptr(mean), ptr(rstd), rows, d,
                                          rows_per_group, group_stride, LN_EPS, p_drop,
                                          rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt,
-                                         stream_ptr()), "vacnic_add_layernorm_fwd")
+                                         ptr(res32), ptr(y32), stream_ptr()), "vacnic_add_layernorm_fwd")
+    if want_y32:
+        return out, mean, rstd, y32
     return out, mean, rstd
 
 
@@ -206,27 +212,31 @@ def add_layernorm_bwd(dy, x, res, gamma, mean, rstd, dgamma, dbeta, dbias=None, 
     return dsum, dx
 
 
-def embed_ln_fwd(ids, tok, pos, gamma, beta, pos_offset=2, p_drop=0.0, rng=None, salt=0):
-    _c(ids, torch.int64, "ids"); _c(tok, torch.bfloat16, "tok"); _c(pos, torch.bfloat16, "pos")
+def embed_ln_fwd(ids, tok, pos, gamma, beta, pos_offset=2, p_drop=0.0, rng=None, salt=0, want_y32=False, pos_ids=None):
+    _c(ids, torch.int64, "ids"); _c(tok, torch.bfloat16, "tok"); _c(pos, torch.bfloat16, "pos"); _c(pos_ids, torch.int32, "pos_ids")
     d = tok.shape[1]
     rows, seq = ids.numel(), ids.shape[-1]
     y = torch.empty(tuple(ids.shape) + (d,), dtype=torch.bfloat16, device=ids.device)
     mean = torch.empty(rows, dtype=torch.float32, device=ids.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=ids.device)
+    y32 = torch.empty(y.shape, dtype=torch.float32, device=ids.device) if want_y32 else None
     check(lib().vacnic_embed_ln_fwd(ptr(ids), ptr(tok), ptr(pos), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows,
                                     seq, pos_offset, d, LN_EPS, p_drop,
-                                    rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt, stream_ptr()),
+                                    rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt, ptr(y32),
+                                    ptr(pos_ids), stream_ptr()),
           "vacnic_embed_ln_fwd")
+    if want_y32:
+        return y, mean, rstd, y32
     return y, mean, rstd
 
 
 def embed_ln_bwd(dy, ids, tok, pos, gamma, mean, rstd, dtok, dpos, dgamma, dbeta, pos_offset=2, pad_id=1, p_drop=0.0,
-                 rng=None, salt=0):
+                 rng=None, salt=0, pos_ids=None):
     d = tok.shape[1]
     check(lib().vacnic_embed_ln_bwd(ptr(dy), ptr(ids), ptr(tok), ptr(pos), ptr(gamma), ptr(mean), ptr(rstd), ptr(dtok),
                                     ptr(dpos), ptr(dgamma), ptr(dbeta), ids.numel(), ids.shape[-1], pos_offset, d, pad_id,
                                     p_drop, rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt,
-                                    stream_ptr()), "vacnic_embed_ln_bwd")
+                                    ptr(pos_ids), stream_ptr()), "vacnic_embed_ln_bwd")
 
 
 def names_embed(ids3, tok, pos, gamma, beta):
@@ -428,10 +438,10 @@ def concat_rows(a, b, out):
 # ------------------------------------------------------------------------------------------------
 # cached decoding / device-side search (csrc/decode.cu)
 # ------------------------------------------------------------------------------------------------
-def decode_embed_ln(seq, cur_len, tok, pos, gamma, beta, y, maxT, pos_offset=2, pingpong=False):
+def decode_embed_ln(seq, cur_len, tok, pos, gamma, beta, y, maxT, pos_offset=2, pingpong=False, y32=None):
     R, d = y.shape
     check(lib().vacnic_decode_embed_ln(ptr(seq), ptr(cur_len), ptr(tok), ptr(pos), ptr(gamma), ptr(beta), ptr(y), R, maxT, d,
-                                       pos_offset, int(pingpong), LN_EPS, stream_ptr()), "vacnic_decode_embed_ln")
+                                       pos_offset, int(pingpong), LN_EPS, ptr(y32), stream_ptr()), "vacnic_decode_embed_ln")
     return y
 
 

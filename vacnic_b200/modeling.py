@@ -134,33 +134,36 @@ class BartEncoderLayer(nn.Module):
                 self.ln_face = LN(st, self.face_layer_norm, rt.new_salt())
 
     def forward(self, h, key_mask, img=None, face=None, ner=None, face_name_mask=None):
-        """BartEncoderLayer.forward with every layer a fusion layer (MFULL:645-744 / MVIS:591-690)."""
+        """BartEncoderLayer.forward with every layer a fusion layer (MFULL:645-744 / MVIS:591-690).  Every state is a
+        pair (bf16 tensor the GEMMs read, fp32 copy carried as the residual -- or None)."""
         rt, cfg, H = self.rt, self.cfg, self.cfg.heads
         kv = None
+        (h, h32), (img, img32), (face, face32), (ner, ner32) = h, img or (None, None), face or (None, None), ner or (None, None)
         if not cfg.stock:
-            img = Bk.MlpBlockFn.apply(img, rt.fwd_anchor, rt, self.lin_iup, self.lin_idown, K.ACT_GELU, self.ln_img)
+            img, img32 = Bk.MlpBlockFn.apply(img, img32, rt.fwd_anchor, rt, self.lin_iup, self.lin_idown, K.ACT_GELU, self.ln_img)
             img_kv, img = Bk.fanout(img, 2)
             if not cfg.only_image:
-                face = Bk.MlpBlockFn.apply(face, rt.fwd_anchor, rt, self.lin_fup, self.lin_fdown, K.ACT_GELU, self.ln_face)
+                face, face32 = Bk.MlpBlockFn.apply(face, face32, rt.fwd_anchor, rt, self.lin_fup, self.lin_fdown, K.ACT_GELU,
+                                                   self.ln_face)
                 face_kv, face = Bk.fanout(face, 2)
                 ner_q, ner_kv = Bk.fanout(ner, 2)
                 a = self.self_attn_img_name
-                ner = Bk.AttnBlockFn.apply(ner_q, Bk.Concat2Fn.apply(face_kv, ner_kv), None, rt, None, a.lin_q, a.lin_kv,
-                                           a.lin_o, a.ln, H, face_name_mask, False, False, 0, None, False)
+                ner, ner32 = Bk.AttnBlockFn.apply(ner_q, ner32, Bk.Concat2Fn.apply(face_kv, ner_kv), None, rt, None, a.lin_q,
+                                                  a.lin_kv, a.lin_o, a.ln, H, face_name_mask, False, False, 0, None, False)
                 ner_map, ner = Bk.fanout(ner, 2)
                 prefix = Bk.NerMapFn.apply(ner_map, rt, self.lin_nup, self.lin_ndown, self.ln_nmap)
                 kv = Bk.Concat2Fn.apply(img_kv, prefix)
             else:
                 kv = img_kv
         a = self.self_attn
-        h = Bk.AttnBlockFn.apply(h, None, None, rt, a.lin_qkv, None, None, a.lin_o, a.ln, H, key_mask, False, True, 0,
-                                 None, False)
+        h, h32 = Bk.AttnBlockFn.apply(h, h32, None, None, rt, a.lin_qkv, None, None, a.lin_o, a.ln, H, key_mask, False, True, 0,
+                                      None, False)
         if not cfg.stock:
             a = self.cross_attn_img_ner
-            h = Bk.AttnBlockFn.apply(h, kv, None, rt, None, a.lin_q, a.lin_kv, a.lin_o, a.ln, H, None, False, True, 0,
-                                     None, False)
-        h = Bk.MlpBlockFn.apply(h, rt.fwd_anchor, rt, self.lin_fc1, self.lin_fc2, K.ACT_GELU, self.ln_final)
-        return h, face, ner, img
+            h, h32 = Bk.AttnBlockFn.apply(h, h32, kv, None, rt, None, a.lin_q, a.lin_kv, a.lin_o, a.ln, H, None, False, True, 0,
+                                          None, False)
+        h, h32 = Bk.MlpBlockFn.apply(h, h32, rt.fwd_anchor, rt, self.lin_fc1, self.lin_fc2, K.ACT_GELU, self.ln_final)
+        return (h, h32), (face, face32), (ner, ner32), (img, img32)
 
 
 class BartDecoderLayer(nn.Module):
@@ -260,18 +263,21 @@ class BartEncoder(nn.Module):
                 ner = Bk.EmbedFn.apply(rt.fwd_anchor, name_ids.contiguous(), rt, self.embed_tokens_ner.weight,
                                        self.embed_positions_ner.weight, self.ln_emb_ner, 2, cfg.pad_token_id)
                 fn_mask = Bk.KeyMask(torch.cat((face_mask, name_mask), dim=1))  # MFULL:1262
-                face = Bk.LinearFn.apply(face_features.to(torch.bfloat16), rt.fwd_anchor, rt, self.lin_face, torch.bfloat16, False, None,
-                                         None)
-            z = Bk.MlpBlockFn.apply(image_features.to(torch.bfloat16), rt.fwd_anchor, rt, self.lin_p0, self.lin_p2, K.ACT_TANH, None)
+                face = (Bk.LinearFn.apply(face_features.to(torch.bfloat16), rt.fwd_anchor, rt, self.lin_face, torch.bfloat16, False,
+                                          None, None), None)
+            z, _ = Bk.MlpBlockFn.apply(image_features.to(torch.bfloat16), None, rt.fwd_anchor, rt, self.lin_p0, self.lin_p2,
+                                       K.ACT_TANH, None)
             img = z.view(B, cfg.prompt_size, CLIP_DIM)  # MFULL:1276
             if cfg.d_model == 1024:
                 img = Bk.LinearFn.apply(img, rt.fwd_anchor, rt, self.lin_vmap, torch.bfloat16, True, None, None)
+            img = (img, None)
         states = []
         for i, layer in enumerate(self.layers):
             if output_hidden_states:
-                states.append(h)
-            h = Bk.grad_mark(h, rt, ("enc", i))  # backward: gradients of encoder layers >= i are final
+                states.append(h[0])
+            h = (Bk.grad_mark(h[0], rt, ("enc", i)), h[1])  # backward: gradients of encoder layers >= i are final
             h, face, ner, img = layer(h, key_mask, img, face, ner, fn_mask)
+        h, img, face, ner = h[0], img and img[0], face and face[0], ner and ner[0]
         if output_hidden_states:
             states.append(h)
         # field order matters: encoder_outputs[-1/-2/-3] = face / ner / img (MFULL:1852-1854)
@@ -314,8 +320,8 @@ class BartDecoder(nn.Module):
         st = rt.store
         B, T = input_ids.shape
         d, H = cfg.d_model, cfg.heads
-        x = Bk.EmbedFn.apply(rt.fwd_anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
-                             self.ln_emb, 2, cfg.pad_token_id)
+        x, x32 = Bk.EmbedFn.apply(rt.fwd_anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
+                                  self.ln_emb, 2, cfg.pad_token_id)
         enc_mask = None if encoder_attention_mask is None else Bk.KeyMask(encoder_attention_mask)
         dec_mask = None if attention_mask is None else Bk.KeyMask(attention_mask)
         # backward: once this marker fires, the decoder (incl. the hoisted cross K/V projection) and the LM head are done
@@ -327,12 +333,12 @@ class BartDecoder(nn.Module):
             if output_hidden_states:
                 states.append(x)
             a = l.self_attn
-            x = Bk.AttnBlockFn.apply(x, None, None, rt, a.lin_qkv, None, None, a.lin_o, a.ln, H, dec_mask, T > 1, True, 0,
-                                     None, False)
+            x, x32 = Bk.AttnBlockFn.apply(x, x32, None, None, rt, a.lin_qkv, None, None, a.lin_o, a.ln, H, dec_mask, T > 1, True, 0,
+                                          None, False)
             a = l.encoder_attn
-            x = Bk.AttnBlockFn.apply(x, None, kv_all, rt, None, a.lin_q, None, a.lin_o, a.ln, H, enc_mask, False, True,
-                                     i * 2 * d, dkv_all, i == 0)
-            x = Bk.MlpBlockFn.apply(x, rt.fwd_anchor, rt, l.lin_fc1, l.lin_fc2, K.ACT_GELU, l.ln_final)
+            x, x32 = Bk.AttnBlockFn.apply(x, x32, None, kv_all, rt, None, a.lin_q, None, a.lin_o, a.ln, H, enc_mask, False, True,
+                                          i * 2 * d, dkv_all, i == 0)
+            x, x32 = Bk.MlpBlockFn.apply(x, x32, rt.fwd_anchor, rt, l.lin_fc1, l.lin_fc2, K.ACT_GELU, l.ln_final)
         if output_hidden_states:
             states.append(x)
         return VacnicOutput(last_hidden_state=x, past_key_values=None,
