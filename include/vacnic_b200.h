@@ -37,6 +37,7 @@ extern "C" {
 #define VACNIC_ACT_NONE 0
 #define VACNIC_ACT_GELU 1 /* exact erf GELU: ACT2FN["gelu"], MFULL:579 */
 #define VACNIC_ACT_TANH 2 /* MLPClipCap, MFULL:111-123 */
+#define VACNIC_ACT_QUICKGELU 3 /* x * sigmoid(1.702 x): MLP of the frozen CLIP ViT image tower (clip.model.QuickGELU), forward only */
 
 #define VACNIC_MASK_NONE 0   /* all-zero additive mask (prefix cross-attention, MFULL:1282-1296) */
 #define VACNIC_MASK_KEYPAD 1 /* per-batch key mask bytes, _expand_mask MFULL:387-398 */
@@ -110,11 +111,13 @@ int vacnic_gemm(const vacnic_gemm_desc* d, void* stream);
  * concat buffer (torch.cat at MFULL:691).  rows_per_group = 0 means contiguous output.
  * res32 (optional, fp32 [rows, d]): the residual in fp32 (used instead of `res`); y32 (optional, fp32 [rows, d]): fp32 copy
  * of the output.  Together they carry the residual stream in fp32 from block to block, like the reference under
- * torch.autocast (LayerNorm runs and returns fp32 there) -- the GEMMs still consume the bf16 `y`. */
+ * torch.autocast (LayerNorm runs and returns fp32 there) -- the GEMMs still consume the bf16 `y`.
+ * sum32 (optional, fp32 [rows, d]): res + dropout(x) BEFORE normalisation -- the residual stream of a pre-LN block (the CLIP
+ * ViT: x = x + attn(ln_1(x))); x may be null when res32 is given (plain LayerNorm of the fp32 stream). */
 int vacnic_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
                              float* mean, float* rstd, int64_t rows, int32_t d, int64_t rows_per_group,
                              int64_t y_group_stride, float eps, float p_drop, const uint64_t* rng_state,
-                             uint32_t salt, const float* res32, float* y32, void* stream);
+                             uint32_t salt, const float* res32, float* y32, float* sum32, void* stream);
 /* Gradients of the above: dsum = d(res + dropout(x)) (written or accumulated), dx = dropout-masked
  * dsum (skipped when dx == dsum or null), dgamma/dbeta/dbias are accumulated atomically (fp32);
  * dbias is the bias gradient of the linear layer that produced x (column sums of dx). */
@@ -209,6 +212,20 @@ int vacnic_dp_adamw_shard(const uint64_t* grad_ptrs, const uint64_t* shadow_ptrs
 int vacnic_clip_grad_scale(const float* g, int64_t n, float max_norm, float base_scale, float* scratch, float* scale_out,
                            float* norm_out, void* stream);
 int vacnic_rng_advance(uint64_t* state, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * Frozen CLIP ViT image tower (extract_clip_img_feat, TRAIN:220-240; OpenAI CLIP VisionTransformer): the step
+ * immediately upstream of the ClipCap prefix MLP.  Forward only.
+ * ------------------------------------------------------------------------------------------ */
+/* conv1 (kernel = stride = patch, no bias) as a GEMM: out bf16 [batch * (H/p) * (W/p), C*p*p] = non-overlapping patches of
+ * images fp32 [batch, C, H, W], column order (c, ky, kx) = conv1.weight.view(width, -1). */
+int vacnic_vit_patchify(const float* images, void* out, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                        int32_t patch, void* stream);
+/* y32[b, 0] = LN(class_embedding + pos[0]); y32[b, i] = LN(tok[b, i-1] + pos[i]) (ln_pre), fp32 [batch, tokens, d];
+ * tok bf16 [batch, tokens-1, d] = the patch projections. */
+int vacnic_vit_embed_ln(const void* tok, const float* cls, const float* pos, const float* gamma, const float* beta, float* y32,
+                        int64_t batch, int32_t tokens, int32_t d, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Losses (script-level code in the reference, TRAIN:284-363).

@@ -12,7 +12,7 @@ F64 = C.c_double
 # name -> argtypes (restype is int for all of these)
 SIGNATURES = {
     "vacnic_gemm": [P, P],
-    "vacnic_add_layernorm_fwd": [P, P, P, P, P, P, P, I64, I32, I64, I64, F32, F32, P, U32, P, P, P],
+    "vacnic_add_layernorm_fwd": [P, P, P, P, P, P, P, I64, I32, I64, I64, F32, F32, P, U32, P, P, P, P],
     "vacnic_add_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, I64, I64, F32, P, U32, I32, P],
     "vacnic_embed_ln_fwd": [P, P, P, P, P, P, P, P, I64, I32, I32, I32, F32, F32, P, U32, P, P, P],
     "vacnic_embed_ln_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, I32, I32, I32, F32, P, U32, P, P],
@@ -31,6 +31,8 @@ SIGNATURES = {
     "vacnic_adamw": [P, P, P, P, P, I64, P, P],
     "vacnic_optim_schedule": [P, P, F64, F64, F64, F32, F32, I64, I64, F32, P],
     "vacnic_dp_adamw_shard": [P, P, U64, U64, I32, I32, P, P, P, P, I64, I64, I32, P],
+    "vacnic_vit_patchify": [P, P, I32, I32, I32, I32, I32, P],
+    "vacnic_vit_embed_ln": [P, P, P, P, P, P, I64, I32, I32, F32, P],
     "vacnic_rng_advance": [P, P],
     "vacnic_clip_grad_scale": [P, I64, F32, F32, P, P, P, P],
     "vacnic_ce_fwd": [P, P, P, P, P, I64, I32, I64, I64, P],

@@ -204,7 +204,7 @@ class AttnBlockFn(torch.autograd.Function):
             if ctx.dkv_pre is None:
                 kv2 = kv_src.view(B * Sk, d)
                 _wgrad(rt, lin_kv, dkvp, kv2, bias_from=dkvp)
-                if ctx.needs_input_grad[1]:
+                if ctx.needs_input_grad[2]:  # kv_src (inputs: x, x32, kv_src, kv_pre, ...)
                     dkv_src = K.gemm(dkvp, lin_kv.w16, b_mn=True).view(B, Sk, d)
         ctx.saved = None
         # hoisted cross K/V: every layer wrote its slice of the shared gradient buffer in place; the

@@ -127,6 +127,32 @@ __global__ void optim_schedule_kernel(long long* __restrict__ step, float* __res
   hyper[7] = grad_scale;
 }
 
+
+// im2col of non-overlapping patches (conv1 of the CLIP ViT, kernel = stride = patch; TRAIN:225): images fp32 [B, C, H, W]
+// -> bf16 [B * (H/p) * (W/p), C * p * p] with column order (c, ky, kx) = conv1.weight.view(width, -1).  One thread per
+// 8 consecutive kx (p is a multiple of 8): two 16-byte loads, one 16-byte store.
+__global__ void __launch_bounds__(256)
+vit_patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int p) {
+  pdl_sync();
+  const int gw = W / p, gh = H / p;
+  const int cols = C * p * p;
+  const long long groups = static_cast<long long>(B) * gh * gw * (cols / 8);
+  const long long gi = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (gi >= groups) return;
+  const int cg = static_cast<int>(gi % (cols / 8));
+  const long long prow = gi / (cols / 8);
+  const int col = cg * 8;
+  const int c = col / (p * p), ky = (col / p) % p, kx = col % p;
+  const int px = static_cast<int>(prow % gw), py = static_cast<int>((prow / gw) % gh);
+  const long long b = prow / (static_cast<long long>(gw) * gh);
+  const float* src = img + ((b * C + c) * H + (py * p + ky)) * static_cast<long long>(W) + px * p + kx;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(src)), a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  uint4 u;
+  u.x = pack_bf16x2(a0.x, a0.y); u.y = pack_bf16x2(a0.z, a0.w);
+  u.z = pack_bf16x2(a1.x, a1.y); u.w = pack_bf16x2(a1.z, a1.w);
+  *reinterpret_cast<uint4*>(out + prow * cols + col) = u;
+}
+
 // out = a + b (+ c) on bf16, fp32 math; gradient fan-in of the residual / state streams
 __global__ void __launch_bounds__(256)
 add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
@@ -309,6 +335,21 @@ extern "C" int vacnic_optim_schedule(int64_t* step, float* hyper, double base_lr
              static_cast<long long>(total_steps), grad_scale);
   count_launch();
   return check_last("optim_schedule");
+}
+
+
+extern "C" int vacnic_vit_patchify(const float* images, void* out, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                                   int32_t patch, void* stream) {
+  VB_REQUIRE(images && out, "vit_patchify: null pointer");
+  VB_REQUIRE(batch >= 0 && channels > 0 && patch > 0 && patch % 8 == 0 && height % patch == 0 && width % patch == 0 && width % 4 == 0,
+             "vit_patchify: patch must be a multiple of 8 that divides height and width");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(images) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "vit_patchify: misaligned");
+  if (batch == 0) return VACNIC_OK;
+  const long long groups = static_cast<long long>(batch) * (height / patch) * (width / patch) * (channels * patch * patch / 8);
+  launch_pdl(vit_patchify_kernel, dim3(static_cast<unsigned>((groups + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             images, static_cast<__nv_bfloat16*>(out), batch, channels, height, width, patch);
+  count_launch();
+  return check_last("vit_patchify");
 }
 
 extern "C" int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream) {

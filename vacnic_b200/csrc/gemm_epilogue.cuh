@@ -51,6 +51,7 @@ struct GemmCfg {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == VACNIC_ACT_GELU) return gelu_erf(v);
   if (act == VACNIC_ACT_TANH) return tanh_fast(v);
+  if (act == VACNIC_ACT_QUICKGELU) return quick_gelu(v);
   return v;
 }
 __device__ __forceinline__ float apply_dact(float aux, int dact) {
@@ -104,6 +105,9 @@ __device__ __forceinline__ void epilogue_act(const GemmArgs& g, float (&v)[32]) 
   } else if (g.act == VACNIC_ACT_TANH) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
+  } else if (g.act == VACNIC_ACT_QUICKGELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
   }
 }
 

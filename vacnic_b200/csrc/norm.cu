@@ -58,6 +58,7 @@ struct LnArgs {
   uint32_t salt;
   const float* res32;  // [rows, d] fp32 residual (takes precedence over `res`), or null
   float* y32;          // [rows, d] fp32 copy of the output = the next block's residual (contiguous rows), or null
+  float* sum32;        // [rows, d] fp32 res + dropout(x) BEFORE normalisation (pre-LN residual stream of the ViT), or null
 };
 
 // v[j][e] for lane: vector index (lane + 32*j), element e.
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= a.rows) return;
-  const uint4* xp = reinterpret_cast<const uint4*>(a.x + row * a.d);
+  const uint4* xp = a.x ? reinterpret_cast<const uint4*>(a.x + row * a.d) : nullptr;
   const uint4* rp = a.res ? reinterpret_cast<const uint4*>(a.res + row * a.d) : nullptr;
   const bool drop = a.p_drop > 0.f;
   const uint32_t seed = drop ? static_cast<uint32_t>(*a.rng) : 0u;
@@ -96,7 +97,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     const int vi = lane + 32 * j;
-    unpack8(__ldg(xp + vi), v[j]);
+    if (xp) {
+      unpack8(__ldg(xp + vi), v[j]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+    }
     if (drop) {
 #pragma unroll
       for (int e = 0; e < 8; ++e)
@@ -112,6 +118,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
       unpack8(__ldg(rp + vi), r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[j][e] += r[e];
+    }
+    if (a.sum32) {
+      float4* s4 = reinterpret_cast<float4*>(a.sum32 + row * a.d) + vi * 2;
+      s4[0] = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+      s4[1] = make_float4(v[j][4], v[j][5], v[j][6], v[j][7]);
     }
   }
   float mean, rstd;
@@ -139,6 +150,51 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
       y4[vi * 2] = make_float4(o[0], o[1], o[2], o[3]);
       y4[vi * 2 + 1] = make_float4(o[4], o[5], o[6], o[7]);
     }
+  }
+}
+
+// ViT token assembly + ln_pre of the CLIP image tower (clip.model.VisionTransformer.forward as used by
+// extract_clip_img_feat, TRAIN:220-232): row (b, 0) = class_embedding + pos[0]; row (b, i) = patch_tok[b, i-1] + pos[i];
+// y32 = LN(row) in fp32 -- the start of the (pre-LN) residual stream.
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+vit_embed_ln_kernel(const __nv_bfloat16* __restrict__ tok, const float* __restrict__ cls, const float* __restrict__ pos,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y32,
+                    long long rows, int tokens, int d, float eps) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long b = row / tokens;
+  const int i = static_cast<int>(row % tokens);
+  float v[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+    const float4* p4 = reinterpret_cast<const float4*>(pos + static_cast<long long>(i) * d) + vi * 2;
+    const float4 p0 = __ldg(p4), p1 = __ldg(p4 + 1);
+    if (i == 0) {
+      const float4* c4 = reinterpret_cast<const float4*>(cls) + vi * 2;
+      const float4 c0 = __ldg(c4), c1 = __ldg(c4 + 1);
+      v[j][0] = c0.x; v[j][1] = c0.y; v[j][2] = c0.z; v[j][3] = c0.w; v[j][4] = c1.x; v[j][5] = c1.y; v[j][6] = c1.z; v[j][7] = c1.w;
+    } else {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(tok + (b * (tokens - 1) + i - 1) * d) + vi), v[j]);
+    }
+    v[j][0] += p0.x; v[j][1] += p0.y; v[j][2] += p0.z; v[j][3] += p0.w;
+    v[j][4] += p1.x; v[j][5] += p1.y; v[j][6] += p1.z; v[j][7] += p1.w;
+  }
+  float mean, rstd;
+  ln_row_stats<VPL>(v, d, eps, mean, rstd);
+  float4* y4 = reinterpret_cast<float4*>(y32 + row * d);
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + vi * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + vi * 2 + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + vi * 2), b1 = __ldg(reinterpret_cast<const float4*>(beta) + vi * 2 + 1);
+    y4[vi * 2] = make_float4((v[j][0] - mean) * rstd * g0.x + b0.x, (v[j][1] - mean) * rstd * g0.y + b0.y,
+                             (v[j][2] - mean) * rstd * g0.z + b0.z, (v[j][3] - mean) * rstd * g0.w + b0.w);
+    y4[vi * 2 + 1] = make_float4((v[j][4] - mean) * rstd * g1.x + b1.x, (v[j][5] - mean) * rstd * g1.y + b1.y,
+                                 (v[j][6] - mean) * rstd * g1.z + b1.z, (v[j][7] - mean) * rstd * g1.w + b1.w);
   }
 }
 
@@ -509,9 +565,9 @@ extern "C" int vacnic_add_layernorm_fwd(const void* x, const void* res, const fl
                                         void* y, float* mean, float* rstd, int64_t rows, int32_t d,
                                         int64_t rows_per_group, int64_t y_group_stride, float eps, float p_drop,
                                         const uint64_t* rng_state, uint32_t salt, const float* res32, float* y32,
-                                        void* stream) {
-  VB_REQUIRE(x && gamma && beta && y, "add_layernorm_fwd: null pointer");
-  VB_REQUIRE(((reinterpret_cast<uintptr_t>(res32) | reinterpret_cast<uintptr_t>(y32)) & 15) == 0,
+                                        float* sum32, void* stream) {
+  VB_REQUIRE((x || res32) && gamma && beta && y, "add_layernorm_fwd: null pointer");
+  VB_REQUIRE(((reinterpret_cast<uintptr_t>(res32) | reinterpret_cast<uintptr_t>(y32) | reinterpret_cast<uintptr_t>(sum32)) & 15) == 0,
              "add_layernorm_fwd: fp32 residual buffers must be 16-byte aligned");
   VB_REQUIRE(rows >= 0 && d > 0 && d % 256 == 0, "add_layernorm_fwd: bad shape rows=%lld d=%d", (long long)rows, d);
   VB_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng_state), "add_layernorm_fwd: bad dropout args");
@@ -524,7 +580,7 @@ extern "C" int vacnic_add_layernorm_fwd(const void* x, const void* res, const fl
   a.y_gs = rows_per_group > 0 ? y_group_stride : 0;
   VB_REQUIRE(a.y_gs % 8 == 0, "add_layernorm_fwd: group stride must be a multiple of 8 elements");
   a.eps = eps; a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
-  a.res32 = res32; a.y32 = y32;
+  a.res32 = res32; a.y32 = y32; a.sum32 = sum32;
   const int grid = static_cast<int>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   VB_DISPATCH_VPL(d, (launch_pdl(add_layernorm_fwd_kernel<VPL>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, a)));
@@ -617,4 +673,18 @@ extern "C" int vacnic_names_embed(const int64_t* ids, const void* tok, const voi
                          static_cast<const __nv_bfloat16*>(pos), gamma, beta, out, spans, len, d, eps)));
   count_launch();
   return check_last("names_embed");
+}
+
+extern "C" int vacnic_vit_embed_ln(const void* tok, const float* cls, const float* pos, const float* gamma, const float* beta,
+                                   float* y32, int64_t batch, int32_t tokens, int32_t d, float eps, void* stream) {
+  VB_REQUIRE(tok && cls && pos && gamma && beta && y32, "vit_embed_ln: null pointer");
+  VB_REQUIRE(batch >= 0 && tokens >= 2 && d > 0 && d % 256 == 0, "vit_embed_ln: bad shape");
+  if (batch == 0) return VACNIC_OK;
+  const long long rows = batch * tokens;
+  const int grid = static_cast<int>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VB_DISPATCH_VPL(d, (launch_pdl(vit_embed_ln_kernel<VPL>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s,
+                                 static_cast<const __nv_bfloat16*>(tok), cls, pos, gamma, beta, y32, rows, tokens, d, eps)));
+  count_launch();
+  return check_last("vit_embed_ln");
 }

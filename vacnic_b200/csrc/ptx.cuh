@@ -226,6 +226,11 @@ __device__ __forceinline__ float tanh_fast(float x) {
   const float e = ex2_approx(x * 2.88539008177792681472f);
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
+// QuickGELU of OpenAI CLIP's ViT MLP: x * sigmoid(1.702 x) = x / (1 + exp(-1.702 x)); 1 MUFU.EX2 + 1 MUFU.RCP
+__device__ __forceinline__ float quick_gelu(float x) {
+  const float e = ex2_approx(x * -2.45546696f);  // -1.702 * log2(e)
+  return __fdividef(x, 1.0f + e);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   float r, e;
   erf_exp_pos(fabsf(x) * 0.70710678118654752440f, r, e);

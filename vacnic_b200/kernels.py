@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import lib as _l
-from .lib import (ACT_GELU, ACT_NONE, ACT_TANH, DT_BF16, DT_F32, MASK_CAUSAL, MASK_KEYPAD,  # noqa: F401
+from .lib import (ACT_GELU, ACT_NONE, ACT_QUICKGELU, ACT_TANH, DT_BF16, DT_F32, MASK_CAUSAL, MASK_KEYPAD,  # noqa: F401
                   MASK_NONE, AttnDesc, GemmDesc, check, lib, ptr, stream_ptr)
 
 
@@ -171,25 +171,27 @@ class Rng:
 
 
 def add_layernorm_fwd(x, res, gamma, beta, out=None, rows_per_group=0, group_stride=0, p_drop=0.0, rng=None, salt=0,
-                      want_stats=True, res32=None, want_y32=False, y32_out=None):
+                      want_stats=True, res32=None, want_y32=False, y32_out=None, sum32_out=None):
     """y = LN(res + dropout(x)); returns (y, mean, rstd).  `out` may be a [rows, d] view whose groups of
     `rows_per_group` rows are `group_stride` elements apart (slice of the prefix/NER concat buffer).
     `want_stats=False` (inference) skips the per-row statistics the backward pass needs.
     `res32` (fp32 residual, replaces `res`) / `want_y32` (also return the output in fp32 as a 4th value): the fp32
     residual stream."""
-    d = x.shape[-1]
-    rows = x.numel() // d
+    x_ptr = ptr(x)                       # x may be None (null pointer): plain LayerNorm of the fp32 stream `res32`
+    src = x if x is not None else res32
+    d = src.shape[-1]
+    rows = src.numel() // d
     _c(x, torch.bfloat16, "x"); _c(res, torch.bfloat16, "res"); _c(gamma, torch.float32, "gamma"); _c(beta, torch.float32, "beta")
-    _c(res32, torch.float32, "res32")
+    _c(res32, torch.float32, "res32"); _c(sum32_out, torch.float32, "sum32_out")
     if out is None:
-        out = torch.empty_like(x)
-    y32 = y32_out if y32_out is not None else (torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_y32 else None)
-    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
-    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
-    check(lib().vacnic_add_layernorm_fwd(ptr(x), ptr(res), ptr(gamma), ptr(beta), ptr(out), ptr(mean), ptr(rstd), rows, d,
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    y32 = y32_out if y32_out is not None else (torch.empty(src.shape, dtype=torch.float32, device=src.device) if want_y32 else None)
+    mean = torch.empty(rows, dtype=torch.float32, device=src.device) if want_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=src.device) if want_stats else None
+    check(lib().vacnic_add_layernorm_fwd(x_ptr, ptr(res), ptr(gamma), ptr(beta), ptr(out), ptr(mean), ptr(rstd), rows, d,
                                          rows_per_group, group_stride, LN_EPS, p_drop,
                                          rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt,
-                                         ptr(res32), ptr(y32), stream_ptr()), "vacnic_add_layernorm_fwd")
+                                         ptr(res32), ptr(y32), ptr(sum32_out), stream_ptr()), "vacnic_add_layernorm_fwd")
     if want_y32:
         return out, mean, rstd, y32
     return out, mean, rstd
@@ -237,6 +239,25 @@ def embed_ln_bwd(dy, ids, tok, pos, gamma, mean, rstd, dtok, dpos, dgamma, dbeta
                                     ptr(dpos), ptr(dgamma), ptr(dbeta), ids.numel(), ids.shape[-1], pos_offset, d, pad_id,
                                     p_drop, rng.state.data_ptr() if (rng is not None and p_drop > 0) else 0, salt,
                                     ptr(pos_ids), stream_ptr()), "vacnic_embed_ln_bwd")
+
+
+def vit_patchify(images, patch):
+    """fp32 [B, C, H, W] -> bf16 [B * (H/p) * (W/p), C*p*p] (conv1 of the CLIP ViT as a GEMM operand)."""
+    _c(images, torch.float32, "images")
+    B, Cc, H, W = images.shape
+    out = torch.empty(B * (H // patch) * (W // patch), Cc * patch * patch, dtype=torch.bfloat16, device=images.device)
+    check(lib().vacnic_vit_patchify(ptr(images), ptr(out), B, Cc, H, W, patch, stream_ptr()), "vacnic_vit_patchify")
+    return out
+
+
+def vit_embed_ln(tok, cls, pos, gamma, beta, batch, tokens):
+    """class token + positional embedding + ln_pre -> fp32 [batch, tokens, d] (start of the ViT residual stream)."""
+    _c(tok, torch.bfloat16, "tok"); _c(cls, torch.float32, "cls"); _c(pos, torch.float32, "pos")
+    d = tok.shape[-1]
+    y32 = torch.empty(batch, tokens, d, dtype=torch.float32, device=tok.device)
+    check(lib().vacnic_vit_embed_ln(ptr(tok), ptr(cls), ptr(pos), ptr(gamma), ptr(beta), ptr(y32), batch, tokens, d, LN_EPS,
+                                    stream_ptr()), "vacnic_vit_embed_ln")
+    return y32
 
 
 def names_embed(ids3, tok, pos, gamma, beta):

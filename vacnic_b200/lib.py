@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libvacnic_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 DT_BF16, DT_F32 = 0, 1
-ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_TANH, ACT_QUICKGELU = 0, 1, 2, 3
 MASK_NONE, MASK_KEYPAD, MASK_CAUSAL = 0, 1, 2
 
 
