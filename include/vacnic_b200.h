@@ -322,6 +322,15 @@ typedef struct vacnic_attn_desc {
   void* dk; int64_t lddk, dk_sh, dk_sb;
   void* dv; int64_t lddv, dv_sh, dv_sb;
   float* delta; /* fp32 [B][H][Sq] scratch: rowsum(dO * O) */
+  /* Packed (varlen) mode -- active when q_start != NULL.  The collate's padding (DNYT:957-972, TRAIN:255-271) never
+   * reaches the device: the rows of all sequences are stored back to back.  Sequence b (0 <= b < B) owns query rows
+   * [q_start[b], q_start[b] + q_len[b]) of q / out / dout / dq (each a [total_q rows] x [H*64] matrix: row stride ld*,
+   * head stride *_sh, batch strides ignored) and key rows [k_start[b], k_start[b] + k_len[b]) of k / v / dk / dv
+   * (total_k rows).  Sq / Sk are then the MAXIMUM q_len / k_len (they size the grid), key_mask / key_len must be NULL,
+   * causal compares positions inside the sequence, stats is fp32 [H][total_q][2] and delta fp32 [H][total_q].
+   * All four arrays are int32 device pointers of length B. */
+  const int32_t* q_start; const int32_t* q_len; const int32_t* k_start; const int32_t* k_len;
+  int32_t total_q, total_k;
 } vacnic_attn_desc;
 int vacnic_attn_fwd(const vacnic_attn_desc* d, void* stream);
 /* dq, dk, dv of the above (dq/dk carry the head_dim^-0.5 factor).  `out` must hold the forward result. */

@@ -43,7 +43,30 @@ struct AttnArgs {
   __nv_bfloat16* out;       // out[b*o_sb + row*ldo + h*64 + c]
   long long ldo, o_sb;
   float* stats;             // [B][H][Sq][2] = {row max in the log2 domain, 1 / row sum}, or null
+  // packed (varlen) mode, active when q_start != null: sequence b owns query rows [q_start[b], +q_len[b]) of a buffer of
+  // total_q rows and key rows [k_start[b], +k_len[b]) of a buffer of total_k rows; the batch strides / Sq / Sk above are
+  // then only upper bounds (grid sizing) and stats is [H][total_q][2]
+  const int32_t* q_start; const int32_t* q_len; const int32_t* k_start; const int32_t* k_len;
+  int total_q;
 };
+
+// per-CTA view of "its" sequence: row counts, first rows in the (possibly packed) buffers, batch coordinate for TMA
+struct SeqGeo {
+  int Sq, Sk, qr0, kr0, bq;
+  long long sbase;  // index of query row 0 of this (sequence, head) in stats / delta
+};
+template <typename Args>
+__device__ __forceinline__ SeqGeo seq_geo(const Args& a, int b, int h) {
+  SeqGeo g;
+  if (a.q_start != nullptr) {
+    g.qr0 = a.q_start[b]; g.Sq = a.q_len[b]; g.kr0 = a.k_start[b]; g.Sk = a.k_len[b]; g.bq = 0;
+    g.sbase = static_cast<long long>(h) * a.total_q + g.qr0;
+  } else {
+    g.qr0 = 0; g.kr0 = 0; g.Sq = a.Sq; g.Sk = a.Sk; g.bq = b;
+    g.sbase = (static_cast<long long>(b) * a.H + h) * a.Sq;
+  }
+  return g;
+}
 
 struct AttnSmem {
   uint64_t q_full, ring_full[kRing], ring_empty[kRing], s_full, s_empty, p_full, p_empty, o_full;
@@ -81,11 +104,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * kAQ;
-  pdl_sync();  // key_len / key_mask below are global reads
+  pdl_sync();  // key_len / key_mask / sequence geometry below are global reads
+  const SeqGeo geo = seq_geo(a, b, h);
+  if (q0 >= geo.Sq) return;  // packed mode: this sequence has no query rows in this tile (uniform for the whole CTA)
 
   // number of key blocks that can contribute
-  int kmax = a.Sk;
-  if (a.key_len != nullptr) {
+  int kmax = geo.Sk;
+  if (a.key_len != nullptr && a.q_start == nullptr) {
     const int kl = a.key_len[b];
     if (kl > 0 && kl < kmax) kmax = kl;  // kl == 0: fully masked rows are uniform over ALL keys -> keep every block
   }
@@ -119,12 +144,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int tid = static_cast<int>(threadIdx.x) - 64;
     for (int j = tid; j < nkb; j += kCompThreads) {
       const int k0 = j * kAK;
-      sh->blk_flag[j] = ((k0 + kAK > a.Sk) || (a.causal && k0 + kAK - 1 > q0)) ? 1 : 0;
+      sh->blk_flag[j] = ((k0 + kAK > geo.Sk) || (a.causal && k0 + kAK - 1 > q0)) ? 1 : 0;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (a.key_mask != nullptr) {
       const uint8_t* mk = a.key_mask + static_cast<long long>(b) * a.Sk;
-      const int kend = min(nkb * kAK, a.Sk);
+      const int kend = min(nkb * kAK, geo.Sk);
       for (int k = tid * 16; k < kend; k += kCompThreads * 16) {
         bool z = false;
 #pragma unroll
@@ -144,13 +169,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(&sh->q_full, kTile);
-      tma_load_4d(sQ, &tmQ, &sh->q_full, 0, q0, h, b);
+      tma_load_4d(sQ, &tmQ, &sh->q_full, 0, geo.qr0 + q0, h, geo.bq);
       int slot = 0;
       uint32_t phase = 0;
       auto push = [&](const CUtensorMap* tm, int row0) {
         mbar_wait(&sh->ring_empty[slot], phase ^ 1u);
         mbar_expect_tx(&sh->ring_full[slot], kTile);
-        tma_load_4d(sRing + slot * kTile, tm, &sh->ring_full[slot], 0, row0, h, b);
+        tma_load_4d(sRing + slot * kTile, tm, &sh->ring_full[slot], 0, geo.kr0 + row0, h, geo.bq);
         if (++slot == kRing) { slot = 0; phase ^= 1u; }
       };
       // consumption order of the MMA thread, which runs QK^T one block ahead of PV: K0, K1, V0, K2, V1, ...
@@ -216,7 +241,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t it = 0;
     // masked score in the log2 domain
     auto masked = [&](float s, int key) -> float {
-      if (key >= a.Sk) return -INFINITY;
+      if (key >= geo.Sk) return -INFINITY;
       if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) return -FLT_MAX;
       return s * c2;
     };
@@ -322,8 +347,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t o0[32];
     tmem_ld_32x32(tmem_o + (static_cast<uint32_t>(quad * 32) << 16) + half * 32, o0);
     tmem_ld_wait();
-    if (row < a.Sq) {
-      __nv_bfloat16* op = a.out + static_cast<long long>(b) * a.o_sb + static_cast<long long>(row) * a.ldo + h * kHD + half * 32;
+    if (row < geo.Sq) {
+      __nv_bfloat16* op = a.out + static_cast<long long>(geo.bq) * a.o_sb + static_cast<long long>(geo.qr0 + row) * a.ldo + h * kHD + half * 32;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 u;
@@ -334,7 +359,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         reinterpret_cast<uint4*>(op)[q] = u;
       }
       if (a.stats != nullptr && half == 0)
-        reinterpret_cast<float2*>(a.stats)[(static_cast<long long>(b) * a.H + h) * a.Sq + row] = make_float2(m, inv);
+        reinterpret_cast<float2*>(a.stats)[geo.sbase + row] = make_float2(m, inv);
     }
   }
 
@@ -370,6 +395,8 @@ struct AttnBwdArgs {
   __nv_bfloat16* dq; long long lddq, dq_sh, dq_sb;
   __nv_bfloat16* dk; long long lddk, dk_sh, dk_sb;
   __nv_bfloat16* dv; long long lddv, dv_sh, dv_sb;
+  const int32_t* q_start; const int32_t* q_len; const int32_t* k_start; const int32_t* k_len;  // packed mode, see AttnArgs
+  int total_q;
 };
 
 struct BwdSmem {
@@ -452,8 +479,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   pdl_sync();  // key_len / key_mask / stats below are global reads
   const int q0 = qb * kAQ;
-  int kmax = a.Sk;
-  if (a.key_len != nullptr) {
+  const SeqGeo geo = seq_geo(a, b, h);
+  if (q0 >= geo.Sq) return;  // packed mode: no query rows of this sequence in this tile
+  int kmax = geo.Sk;
+  if (a.key_len != nullptr && a.q_start == nullptr) {
     const int kl = a.key_len[b];
     if (kl > 0 && kl < kmax) kmax = kl;
   }
@@ -467,15 +496,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
       mbar_expect_tx(&sh->in_full, 3 * kTile);
-      tma_load_4d(sQ, &tmQ, &sh->in_full, 0, q0, h, b);
-      tma_load_4d(sDO, &tmDO, &sh->in_full, 0, q0, h, b);
-      tma_load_4d(sDS, &tmO, &sh->in_full, 0, q0, h, b);
+      tma_load_4d(sQ, &tmQ, &sh->in_full, 0, geo.qr0 + q0, h, geo.bq);
+      tma_load_4d(sDO, &tmDO, &sh->in_full, 0, geo.qr0 + q0, h, geo.bq);
+      tma_load_4d(sDS, &tmO, &sh->in_full, 0, geo.qr0 + q0, h, geo.bq);
       for (int j = 0; j < nkb; ++j) {
         const int st = j & 1;
         mbar_wait(&sh->st_empty[st], ((j >> 1) & 1u) ^ 1u);
         mbar_expect_tx(&sh->st_full[st], 2 * kHalfTile);
-        tma_load_4d(sKV + st * kTile, &tmK, &sh->st_full[st], 0, j * 64, h, b);
-        tma_load_4d(sKV + st * kTile + kHalfTile, &tmV, &sh->st_full[st], 0, j * 64, h, b);
+        tma_load_4d(sKV + st * kTile, &tmK, &sh->st_full[st], 0, geo.kr0 + j * 64, h, geo.bq);
+        tma_load_4d(sKV + st * kTile + kHalfTile, &tmV, &sh->st_full[st], 0, geo.kr0 + j * 64, h, geo.bq);
       }
     }
   } else if (warp == 1) {
@@ -531,11 +560,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int tid = static_cast<int>(threadIdx.x) - 64;
       for (int j = tid; j < nkb; j += kCompThreads) {
         const int kb0 = j * 64;
-        sh->blk_flag[j] = ((kb0 + 64 > a.Sk) || (a.causal && kb0 + 63 > q0)) ? 1 : 0;
+        sh->blk_flag[j] = ((kb0 + 64 > geo.Sk) || (a.causal && kb0 + 63 > q0)) ? 1 : 0;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (mk != nullptr) {
-        const int kend = min(nkb * 64, a.Sk);
+        const int kend = min(nkb * 64, geo.Sk);
         for (int k = tid * 16; k < kend; k += kCompThreads * 16) {
           bool z = false;
 #pragma unroll
@@ -566,9 +595,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     // every thread has read its O row before any thread overwrites the buffer with dS
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    float m = 0.f, coef = 0.f;
-    if (row < a.Sq) {
-      const long long si = (static_cast<long long>(b) * a.H + h) * a.Sq + row;
+    // rows past the sequence end (TMA zero fill, or -- packed mode -- the next sequence's rows): reference maximum +big, so
+    // every p = 2^(t - m) underflows to exactly 0 whatever those rows hold
+    float m = 1.0e30f, coef = 0.f;
+    if (row < geo.Sq) {
+      const long long si = geo.sbase + row;
       const float2 st = reinterpret_cast<const float2*>(a.stats)[si];
       m = st.x;
       coef = st.y * a.scale;  // 1/rowsum * head_dim^-0.5
@@ -596,7 +627,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           float t = fmaf(__uint_as_float(xs[c]), c2, -m);  // log2-domain score minus the row maximum
           if (need) {
             const int key = kb0 + c;
-            if (key >= a.Sk) t = -INFINITY;
+            if (key >= geo.Sk) t = -INFINITY;
             else if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) t = -FLT_MAX - m;
           }
           ds[e] = ex2f(t) * (__uint_as_float(xp[c]) - delta) * coef;
@@ -617,8 +648,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t o0[32];
     tmem_ld_32x32(tmem_base + lane_off + 128 + half * 32, o0);
     tmem_ld_wait();
-    if (row < a.Sq)
-      store_row32(a.dq + static_cast<long long>(b) * a.dq_sb + h * a.dq_sh + static_cast<long long>(row) * a.lddq + half * 32, o0);
+    if (row < geo.Sq)
+      store_row32(a.dq + static_cast<long long>(geo.bq) * a.dq_sb + h * a.dq_sh + static_cast<long long>(geo.qr0 + row) * a.lddq + half * 32, o0);
   }
   tc_fence_before();
   __syncthreads();
@@ -646,7 +677,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   pdl_sync();  // key_len / key_mask / stats below are global reads
   const int k0 = kb * kAK;
-  const int kl = a.key_len != nullptr ? a.key_len[b] : 0;
+  const SeqGeo geo = seq_geo(a, b, h);
+  if (k0 >= geo.Sk) return;  // packed mode: no key rows of this sequence in this tile (legacy mode: never true)
+  const int kl = (a.key_len != nullptr && a.q_start == nullptr) ? a.key_len[b] : 0;
   if (kl > 0 && k0 >= kl) {
     // every key of this block is masked for every query: dK = dV = 0
     if (warp >= 2 && warp < 6) {
@@ -661,7 +694,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     return;
   }
   const int i0 = a.causal ? k0 / 64 : 0;           // query blocks entirely above the diagonal contribute nothing
-  const int nqb = (a.Sq + 63) / 64;
+  const int nqb = (geo.Sq + 63) / 64;
   bwd_init(sh, warp, lane);
   const uint32_t tmem_base = sh->tmem_slot;
 
@@ -670,14 +703,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmDO);
       mbar_expect_tx(&sh->in_full, 2 * kTile);
-      tma_load_4d(sK, &tmK, &sh->in_full, 0, k0, h, b);
-      tma_load_4d(sV, &tmV, &sh->in_full, 0, k0, h, b);
+      tma_load_4d(sK, &tmK, &sh->in_full, 0, geo.kr0 + k0, h, geo.bq);
+      tma_load_4d(sV, &tmV, &sh->in_full, 0, geo.kr0 + k0, h, geo.bq);
       for (int i = i0, n = 0; i < nqb; ++i, ++n) {
         const int st = n & 1;
         mbar_wait(&sh->st_empty[st], ((n >> 1) & 1u) ^ 1u);
         mbar_expect_tx(&sh->st_full[st], 2 * kHalfTile);
-        tma_load_4d(sQD + st * kTile, &tmQ, &sh->st_full[st], 0, i * 64, h, b);
-        tma_load_4d(sQD + st * kTile + kHalfTile, &tmDO, &sh->st_full[st], 0, i * 64, h, b);
+        tma_load_4d(sQD + st * kTile, &tmQ, &sh->st_full[st], 0, geo.qr0 + i * 64, h, geo.bq);
+        tma_load_4d(sQD + st * kTile + kHalfTile, &tmDO, &sh->st_full[st], 0, geo.qr0 + i * 64, h, geo.bq);
       }
     }
   } else if (warp == 1) {
@@ -730,18 +763,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int key = k0 + r;
     const int tid = threadIdx.x - 64;  // 0..255
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const bool key_oob = key >= a.Sk;
+    const bool key_oob = key >= geo.Sk;
     const bool key_masked = !key_oob && a.key_mask != nullptr && a.key_mask[static_cast<long long>(b) * a.Sk + key] == 0;
     const float c2 = a.scale_log2;
     const bool warp_plain = !a.causal && __all_sync(0xffffffffu, !(key_oob || key_masked));
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     const uint32_t pt_row = smem_u32(sPT) + r * 128, dst_row = smem_u32(sDST) + r * 128;
-    const long long sbase = (static_cast<long long>(b) * a.H + h) * a.Sq;
+    const long long sbase = geo.sbase;
     // row statistics of a 64-query block (threads 0..63): {reference max, 1/row sum, delta, scale/row sum}
     auto load_stat = [&](int i) -> float4 {
       const int qrow = i * 64 + tid;
-      float4 st = make_float4(0.f, 0.f, 0.f, 0.f);  // query rows beyond Sq: 1/sum = 0 -> p = 0
-      if (qrow < a.Sq) {
+      float4 st = make_float4(1.0e30f, 0.f, 0.f, 0.f);  // query rows beyond the sequence: max = +big, 1/sum = 0 -> p = 0 exactly
+      if (qrow < geo.Sq) {
         const float2 s2 = reinterpret_cast<const float2*>(a.stats)[sbase + qrow];
         st = make_float4(s2.x, s2.y, a.delta[sbase + qrow], s2.y * a.scale);
       }
@@ -827,8 +860,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_ld_32x32(tmem_base + lane_off + 192 + half * 32, o1);
     tmem_ld_wait();
     if (!key_oob) {
-      store_row32(a.dv + static_cast<long long>(b) * a.dv_sb + h * a.dv_sh + static_cast<long long>(key) * a.lddv + half * 32, o0);
-      store_row32(a.dk + static_cast<long long>(b) * a.dk_sb + h * a.dk_sh + static_cast<long long>(key) * a.lddk + half * 32, o1);
+      store_row32(a.dv + static_cast<long long>(geo.bq) * a.dv_sb + h * a.dv_sh + static_cast<long long>(geo.kr0 + key) * a.lddv + half * 32, o0);
+      store_row32(a.dk + static_cast<long long>(geo.bq) * a.dk_sb + h * a.dk_sh + static_cast<long long>(geo.kr0 + key) * a.lddk + half * 32, o1);
     }
   }
   tc_fence_before();
@@ -854,12 +887,19 @@ extern "C" int vacnic_attn_fwd(const vacnic_attn_desc* d, void* stream) {
   VB_REQUIRE(d->head_dim == 64, "attn_fwd: head_dim must be 64 (BART-base / BART-large)");
   VB_REQUIRE(d->B > 0 && d->H > 0 && d->Sq > 0 && d->Sk > 0 && d->Sk <= kMaxKB * kAK, "attn_fwd: bad shape (Sk <= %d)", kMaxKB * kAK);
   VB_REQUIRE(d->ldo % 8 == 0 && d->o_sb % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "attn_fwd: out must be 16-byte aligned");
+  const bool packed = d->q_start != nullptr;
+  if (packed) {
+    VB_REQUIRE(d->q_len && d->k_start && d->k_len && d->total_q > 0 && d->total_k > 0, "attn_fwd: packed mode needs q_len, k_start, k_len, total_q, total_k");
+    VB_REQUIRE(d->key_mask == nullptr && d->key_len == nullptr, "attn_fwd: packed mode takes no key_mask / key_len");
+  }
+  // packed mode: one [total rows] x [H*64] matrix per operand (batch dimension of the tensor map = 1)
+  const int rows_q = packed ? d->total_q : d->Sq, rows_k = packed ? d->total_k : d->Sk, nb = packed ? 1 : d->B;
   CUtensorMap tq, tk, tv;
-  int rc = make_operand_map(&tq, d->q, false, d->Sq, 64, d->ldq, d->H, d->q_sh, d->B, d->q_sb, kAQ);
+  int rc = make_operand_map(&tq, d->q, false, rows_q, 64, d->ldq, d->H, d->q_sh, nb, packed ? 0 : d->q_sb, kAQ);
   if (rc != VACNIC_OK) return rc;
-  rc = make_operand_map(&tk, d->k, false, d->Sk, 64, d->ldk, d->H, d->k_sh, d->B, d->k_sb, kAK);
+  rc = make_operand_map(&tk, d->k, false, rows_k, 64, d->ldk, d->H, d->k_sh, nb, packed ? 0 : d->k_sb, kAK);
   if (rc != VACNIC_OK) return rc;
-  rc = make_operand_map(&tv, d->v, false, d->Sk, 64, d->ldv, d->H, d->v_sh, d->B, d->v_sb, kAK);
+  rc = make_operand_map(&tv, d->v, false, rows_k, 64, d->ldv, d->H, d->v_sh, nb, packed ? 0 : d->v_sb, kAK);
   if (rc != VACNIC_OK) return rc;
   AttnArgs a;
   a.B = d->B; a.H = d->H; a.Sq = d->Sq; a.Sk = d->Sk; a.causal = d->causal;
@@ -867,6 +907,7 @@ extern "C" int vacnic_attn_fwd(const vacnic_attn_desc* d, void* stream) {
   a.key_mask = d->key_mask; a.key_len = d->key_len;
   a.out = static_cast<__nv_bfloat16*>(d->out); a.ldo = d->ldo; a.o_sb = d->o_sb;
   a.stats = d->stats;
+  a.q_start = d->q_start; a.q_len = d->q_len; a.k_start = d->k_start; a.k_len = d->k_len; a.total_q = d->total_q;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
@@ -888,20 +929,26 @@ extern "C" int vacnic_attn_bwd(const vacnic_attn_desc* d, void* stream) {
     VB_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "attn_bwd: gradient buffers must be 16-byte aligned");
   VB_REQUIRE(d->lddq % 8 == 0 && d->lddk % 8 == 0 && d->lddv % 8 == 0 && d->dq_sh % 8 == 0 && d->dk_sh % 8 == 0 && d->dv_sh % 8 == 0 &&
                  d->dq_sb % 8 == 0 && d->dk_sb % 8 == 0 && d->dv_sb % 8 == 0, "attn_bwd: gradient strides must be multiples of 8");
+  const bool packed = d->q_start != nullptr;
+  if (packed) {
+    VB_REQUIRE(d->q_len && d->k_start && d->k_len && d->total_q > 0 && d->total_k > 0, "attn_bwd: packed mode needs q_len, k_start, k_len, total_q, total_k");
+    VB_REQUIRE(d->key_mask == nullptr && d->key_len == nullptr, "attn_bwd: packed mode takes no key_mask / key_len");
+  }
+  const int rows_q = packed ? d->total_q : d->Sq, rows_k = packed ? d->total_k : d->Sk, nb = packed ? 1 : d->B;
   CUtensorMap q128, q64, k128, k64, v128, v64, do128, do64, o128;
   int rc;
 #define VB_MAP(tm, base, rows, ld, sh, sb, box)                                                        \
-  rc = make_operand_map(&tm, base, false, rows, 64, ld, d->H, sh, d->B, sb, box);                      \
+  rc = make_operand_map(&tm, base, false, rows, 64, ld, d->H, sh, nb, packed ? 0 : sb, box);           \
   if (rc != VACNIC_OK) return rc;
-  VB_MAP(q128, d->q, d->Sq, d->ldq, d->q_sh, d->q_sb, 128)
-  VB_MAP(q64, d->q, d->Sq, d->ldq, d->q_sh, d->q_sb, 64)
-  VB_MAP(k128, d->k, d->Sk, d->ldk, d->k_sh, d->k_sb, 128)
-  VB_MAP(k64, d->k, d->Sk, d->ldk, d->k_sh, d->k_sb, 64)
-  VB_MAP(v128, d->v, d->Sk, d->ldv, d->v_sh, d->v_sb, 128)
-  VB_MAP(v64, d->v, d->Sk, d->ldv, d->v_sh, d->v_sb, 64)
-  VB_MAP(do128, d->dout, d->Sq, d->lddo, 64, d->do_sb, 128)
-  VB_MAP(do64, d->dout, d->Sq, d->lddo, 64, d->do_sb, 64)
-  VB_MAP(o128, d->out, d->Sq, d->ldo, 64, d->o_sb, 128)
+  VB_MAP(q128, d->q, rows_q, d->ldq, d->q_sh, d->q_sb, 128)
+  VB_MAP(q64, d->q, rows_q, d->ldq, d->q_sh, d->q_sb, 64)
+  VB_MAP(k128, d->k, rows_k, d->ldk, d->k_sh, d->k_sb, 128)
+  VB_MAP(k64, d->k, rows_k, d->ldk, d->k_sh, d->k_sb, 64)
+  VB_MAP(v128, d->v, rows_k, d->ldv, d->v_sh, d->v_sb, 128)
+  VB_MAP(v64, d->v, rows_k, d->ldv, d->v_sh, d->v_sb, 64)
+  VB_MAP(do128, d->dout, rows_q, d->lddo, 64, d->do_sb, 128)
+  VB_MAP(do64, d->dout, rows_q, d->lddo, 64, d->do_sb, 64)
+  VB_MAP(o128, d->out, rows_q, d->ldo, 64, d->o_sb, 128)
 #undef VB_MAP
   AttnBwdArgs a;
   a.B = d->B; a.H = d->H; a.Sq = d->Sq; a.Sk = d->Sk; a.causal = d->causal;
@@ -911,6 +958,7 @@ extern "C" int vacnic_attn_bwd(const vacnic_attn_desc* d, void* stream) {
   a.dq = static_cast<__nv_bfloat16*>(d->dq); a.lddq = d->lddq; a.dq_sh = d->dq_sh; a.dq_sb = d->dq_sb;
   a.dk = static_cast<__nv_bfloat16*>(d->dk); a.lddk = d->lddk; a.dk_sh = d->dk_sh; a.dk_sb = d->dk_sb;
   a.dv = static_cast<__nv_bfloat16*>(d->dv); a.lddv = d->lddv; a.dv_sh = d->dv_sh; a.dv_sb = d->dv_sb;
+  a.q_start = d->q_start; a.q_len = d->q_len; a.k_start = d->k_start; a.k_len = d->k_len; a.total_q = d->total_q;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdDqSmemBytes);

@@ -516,7 +516,21 @@ def advance_len(cur_len):
 # ------------------------------------------------------------------------------------------------
 # fused attention (csrc/attn_sm100.cu)
 # ------------------------------------------------------------------------------------------------
-def _attn_desc(q4, k4, v4, key_mask, key_len, causal):
+class Packed:
+    """Varlen geometry of one attention call (device int32 arrays of length n_seq + host-known bounds): sequence b owns
+    query rows [q_start[b], +q_len[b]) and key rows [k_start[b], +k_len[b]) of the packed row buffers."""
+    __slots__ = ("q_start", "q_len", "k_start", "k_len", "n_seq", "max_q", "max_k")
+
+    def __init__(self, q_start, q_len, k_start, k_len, max_q: int, max_k: int):
+        for t in (q_start, q_len, k_start, k_len):
+            _c(t, torch.int32, "packed attention geometry")
+        if not (q_start.numel() == q_len.numel() == k_start.numel() == k_len.numel()):
+            raise ValueError("packed attention geometry: the four arrays must have one entry per sequence")
+        self.q_start, self.q_len, self.k_start, self.k_len = q_start, q_len, k_start, k_len
+        self.n_seq, self.max_q, self.max_k = q_start.numel(), int(max_q), int(max_k)
+
+
+def _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed: "Packed | None" = None):
     B, H, Sq, hd = q4.shape
     Sk = k4.shape[2]
     for t in (q4, k4, v4):
@@ -531,14 +545,22 @@ def _attn_desc(q4, k4, v4, key_mask, key_len, causal):
     d.k, d.ldk, d.k_sh, d.k_sb = k4.data_ptr(), k4.stride(2), k4.stride(1), k4.stride(0)
     d.v, d.ldv, d.v_sh, d.v_sb = v4.data_ptr(), v4.stride(2), v4.stride(1), v4.stride(0)
     d.key_mask, d.key_len = ptr(key_mask), ptr(key_len)
+    if packed is not None:
+        # q4 / k4 / v4 are [1, H, total rows, 64] views of the packed buffers; B / Sq / Sk become sequence count and maxima
+        if B != 1 or key_mask is not None or key_len is not None:
+            raise ValueError("packed attention: operands must be [1, H, rows, 64] views and take no key mask")
+        d.B, d.Sq, d.Sk = packed.n_seq, packed.max_q, packed.max_k
+        d.total_q, d.total_k = Sq, Sk
+        d.q_start, d.q_len, d.k_start, d.k_len = (ptr(t) for t in (packed.q_start, packed.q_len, packed.k_start, packed.k_len))
     return d
 
 
-def attn_fwd(q4, k4, v4, key_mask=None, key_len=None, causal=False, want_stats=True):
+def attn_fwd(q4, k4, v4, key_mask=None, key_len=None, causal=False, want_stats=True, packed=None):
     """Fused softmax(q k^T * hd^-0.5 + mask) v.  q4 [B,H,Sq,64], k4/v4 [B,H,Sk,64] strided views.
-    Returns (O bf16 [B,Sq,H*64], stats fp32 [B,H,Sq,2] or None)."""
+    Returns (O bf16 [B,Sq,H*64], stats fp32 [B,H,Sq,2] or None).  `packed` (kernels.Packed): varlen mode -- q4/k4/v4 are
+    [1,H,rows,64] views of packed row buffers, O is [1,total_q,H*64], stats [1,H,total_q,2]."""
     B, H, Sq, hd = q4.shape
-    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal)
+    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed)
     out = torch.empty(B, Sq, H * hd, dtype=torch.bfloat16, device=q4.device)
     stats = torch.empty(B, H, Sq, 2, dtype=torch.float32, device=q4.device) if want_stats else None
     d.out, d.ldo, d.o_sb, d.stats = out.data_ptr(), out.stride(1), out.stride(0), ptr(stats)
@@ -546,11 +568,11 @@ def attn_fwd(q4, k4, v4, key_mask=None, key_len=None, causal=False, want_stats=T
     return out, stats
 
 
-def attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, key_mask=None, key_len=None, causal=False):
+def attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, key_mask=None, key_len=None, causal=False, packed=None):
     """Gradients of attn_fwd.  dO / O bf16 [B,Sq,H*64] (row stride = stride(1), innermost 1); dq4/dk4/dv4 are
     [B,H,S,64] strided views that receive the results (dq, dk include the hd^-0.5 factor)."""
     B, H, Sq, hd = q4.shape
-    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal)
+    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed)
     for t in (dO, O):
         if t.dtype != torch.bfloat16 or t.stride(2) != 1 or tuple(t.shape) != (B, Sq, H * hd):
             raise ValueError("attn_bwd: dO / O must be bf16 [B,Sq,H*hd] with innermost stride 1")

@@ -50,6 +50,8 @@ class AttnDesc(C.Structure):
         ("dk", C.c_void_p), ("lddk", C.c_int64), ("dk_sh", C.c_int64), ("dk_sb", C.c_int64),
         ("dv", C.c_void_p), ("lddv", C.c_int64), ("dv_sh", C.c_int64), ("dv_sb", C.c_int64),
         ("delta", C.c_void_p),
+        ("q_start", C.c_void_p), ("q_len", C.c_void_p), ("k_start", C.c_void_p), ("k_len", C.c_void_p),
+        ("total_q", C.c_int32), ("total_k", C.c_int32),
     ]
 
 
