@@ -104,8 +104,21 @@ class KeyMask:
         self.len = K.mask_key_len(self.mask)
 
 
-def sdpa_fwd(q4, k4, v4, key_mask: Optional[KeyMask], causal, want_stats=True):
+class PackedMask:
+    """Takes the place of a KeyMask when the rows of a batch are PACKED (varlen): `geo` (kernels.Packed) says which query
+    and key rows each sequence owns; `k_tail` = number of trailing rows of the key-side buffers that belong to no
+    sequence's key range (the row padding of the packed batch) -- their dK / dV are never written by the kernels and must
+    read as zero for the weight-gradient GEMMs."""
+    __slots__ = ("geo", "k_tail")
+
+    def __init__(self, geo, k_tail: int = 0):
+        self.geo, self.k_tail = geo, int(k_tail)
+
+
+def sdpa_fwd(q4, k4, v4, key_mask, causal, want_stats=True):
     """q4 [B,H,Sq,hd], k4/v4 [B,H,Sk,hd] (strided views).  Returns (O [B,Sq,H*hd], stats [B,H,Sq,2])."""
+    if isinstance(key_mask, PackedMask):
+        return K.attn_fwd(q4, k4, v4, causal=causal, want_stats=want_stats, packed=key_mask.geo)
     if key_mask is not None and tuple(key_mask.mask.shape) != (q4.shape[0], k4.shape[2]):
         raise ValueError(f"Attention mask should be of size {(q4.shape[0], 1, q4.shape[2], k4.shape[2])}, but is "
                          f"{(key_mask.mask.shape[0], 1, q4.shape[2], key_mask.mask.shape[1])}")  # MFULL:516-520
@@ -113,7 +126,9 @@ def sdpa_fwd(q4, k4, v4, key_mask: Optional[KeyMask], causal, want_stats=True):
                       key_mask.len if key_mask is not None else None, causal, want_stats=want_stats)
 
 
-def sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask: Optional[KeyMask], causal, dq4, dk4, dv4):
+def sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4):
+    if isinstance(key_mask, PackedMask):
+        return K.attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, causal=causal, packed=key_mask.geo)
     K.attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, key_mask.mask if key_mask is not None else None,
                key_mask.len if key_mask is not None else None, causal)
 
@@ -137,21 +152,26 @@ class AttnBlockFn(torch.autograd.Function):
         B, Sq, d = x.shape
         hd = d // H
         x2 = x.view(B * Sq, d)
+        # packed (varlen) rows: the attention kernels see ONE [rows, H*64] matrix per operand + per-sequence row ranges
+        packed = isinstance(key_mask, PackedMask)
+        Bq, Rq = (1, B * Sq) if packed else (B, Sq)
         if lin_qkv is not None:  # self attention, fused [k; v; q] projection (MFULL:444-446 order)
             qkv = K.gemm(x2, lin_qkv.w16, bias=lin_qkv.b32)
-            Sk = Sq
-            k4, v4, q4 = (_heads(qkv, B, Sq, H, c * d, hd) for c in range(3))
+            Bk, Sk = Bq, Rq
+            k4, v4, q4 = (_heads(qkv, Bq, Rq, H, c * d, hd) for c in range(3))
             kvp = None
         else:
             qkv = K.gemm(x2, lin_q.w16, bias=lin_q.b32)
-            q4 = _heads(qkv, B, Sq, H, 0, hd)
-            if kv_pre is not None:  # [B, Sk, n_layers*2d]: this layer's k|v live at columns [kv_col0, +2d)
-                Sk = kv_pre.shape[1]
-                kvp = kv_pre.view(B * Sk, -1)[:, kv_col0:kv_col0 + 2 * d]
+            q4 = _heads(qkv, Bq, Rq, H, 0, hd)
+            if kv_pre is not None:  # [Bk, Sk, n_layers*2d]: this layer's k|v live at columns [kv_col0, +2d)
+                Bk, Sk = kv_pre.shape[0], kv_pre.shape[1]
+                kvp = kv_pre.view(Bk * Sk, -1)[:, kv_col0:kv_col0 + 2 * d]
             else:
-                Sk = kv_src.shape[1]
-                kvp = K.gemm(kv_src.view(B * Sk, d), lin_kv.w16, bias=lin_kv.b32)
-            k4, v4 = _heads(kvp, B, Sk, H, 0, hd), _heads(kvp, B, Sk, H, d, hd)
+                Bk, Sk = kv_src.shape[0], kv_src.shape[1]
+                kvp = K.gemm(kv_src.view(Bk * Sk, d), lin_kv.w16, bias=lin_kv.b32)
+            if packed:
+                Bk, Sk = 1, Bk * Sk
+            k4, v4 = _heads(kvp, Bk, Sk, H, 0, hd), _heads(kvp, Bk, Sk, H, d, hd)
         O, stats = sdpa_fwd(q4, k4, v4, key_mask, causal, want_stats=not rt.store.frozen)
         a = K.gemm(O.view(B * Sq, d), lin_o.w16, bias=lin_o.b32)
         p = rt.drop if use_dropout else 0.0
@@ -167,9 +187,9 @@ class AttnBlockFn(torch.autograd.Function):
         ctx.saved = (x2, kv_src, qkv, kvp, stats, O, a, mean, rstd, q4, k4, v4)
         ctx.mask = (key_mask, causal)
         hoisted = kv_pre is not None and dkv_all is not None
-        ctx.dkv_pre = dkv_all.view(B * Sk, -1)[:, kv_col0:kv_col0 + 2 * d] if hoisted else None
+        ctx.dkv_pre = dkv_all.view(Bk * Sk, -1)[:, kv_col0:kv_col0 + 2 * d] if hoisted else None
         ctx.dkv_all = dkv_all if (hoisted and return_dkv_all) else None
-        ctx.shape = (B, Sq, d, Sk)
+        ctx.shape = (B, Sq, d, Sk, Bq, Rq, Bk)
         return y.view(B, Sq, d), y32
 
     @staticmethod
@@ -178,34 +198,42 @@ class AttnBlockFn(torch.autograd.Function):
         lin_qkv, lin_q, lin_kv, lin_o = ctx.lins
         x2, kv_src, qkv, kvp, stats, O, a, mean, rstd, q4, k4, v4 = ctx.saved
         key_mask, causal = ctx.mask
-        B, Sq, d, Sk = ctx.shape
+        B, Sq, d, Sk, Bq, Rq, Bk = ctx.shape
         hd = d // H
+        k_tail = key_mask.k_tail if isinstance(key_mask, PackedMask) else 0
         dy = dy.contiguous()
         dsum, da = K.add_layernorm_bwd(dy.view(B * Sq, d), a, x2, ln.g, mean, rstd, ln.gg, ln.gb, dbias=lin_o.gb,
                                        want_dx=True, p_drop=ctx.p, rng=rt.rng, salt=ln.salt)
         O2 = O.view(B * Sq, d)
         _wgrad(rt, lin_o, da, O2)
-        dO = K.gemm(da, lin_o.w16, b_mn=True).view(B, Sq, d)
+        dO = K.gemm(da, lin_o.w16, b_mn=True).view(Bq, Rq, d)
         dkv_src = None
         if lin_qkv is not None:
             dqkv = torch.empty_like(qkv)
-            dk4, dv4, dq4 = (_heads(dqkv, B, Sq, H, c * d, hd) for c in range(3))
+            if k_tail:  # key rows no sequence owns: the kernels never write their dK / dV (their dQ is written afterwards)
+                dqkv[-k_tail:].zero_()
+            dk4, dv4, dq4 = (_heads(dqkv, Bq, Rq, H, c * d, hd) for c in range(3))
             sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4)
             _wgrad(rt, lin_qkv, dqkv, x2, bias_from=dqkv)
             K.gemm(dqkv, lin_qkv.w16, out=dsum, b_mn=True, accumulate=True)  # dx = dsum + dqkv W
         else:
             dq = torch.empty_like(qkv)
-            dq4 = _heads(dq, B, Sq, H, 0, hd)
-            dkvp = ctx.dkv_pre if ctx.dkv_pre is not None else torch.empty_like(kvp)
-            dk4, dv4 = _heads(dkvp, B, Sk, H, 0, hd), _heads(dkvp, B, Sk, H, d, hd)
+            dq4 = _heads(dq, Bq, Rq, H, 0, hd)
+            if ctx.dkv_pre is not None:
+                dkvp = ctx.dkv_pre  # (its unowned rows were zeroed where the shared buffer was allocated)
+            else:
+                dkvp = torch.empty_like(kvp)
+                if k_tail:
+                    dkvp[-k_tail:].zero_()
+            dk4, dv4 = _heads(dkvp, Bk, Sk, H, 0, hd), _heads(dkvp, Bk, Sk, H, d, hd)
             sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4)
             _wgrad(rt, lin_q, dq, x2, bias_from=dq)
             K.gemm(dq, lin_q.w16, out=dsum, b_mn=True, accumulate=True)
             if ctx.dkv_pre is None:
-                kv2 = kv_src.view(B * Sk, d)
+                kv2 = kv_src.reshape(Bk * Sk, d)
                 _wgrad(rt, lin_kv, dkvp, kv2, bias_from=dkvp)
                 if ctx.needs_input_grad[2]:  # kv_src (inputs: x, x32, kv_src, kv_pre, ...)
-                    dkv_src = K.gemm(dkvp, lin_kv.w16, b_mn=True).view(B, Sk, d)
+                    dkv_src = K.gemm(dkvp, lin_kv.w16, b_mn=True).view(kv_src.shape)
         ctx.saved = None
         # hoisted cross K/V: every layer wrote its slice of the shared gradient buffer in place; the
         # block that runs last in the backward pass (layer 0) hands the whole buffer to autograd.
