@@ -133,9 +133,10 @@ class BartEncoderLayer(nn.Module):
                 self.lin_fdown = st.lin([self._face_down.weight], [self._face_down.bias])
                 self.ln_face = LN(st, self.face_layer_norm, rt.new_salt())
 
-    def forward(self, h, key_mask, img=None, face=None, ner=None, face_name_mask=None):
+    def forward(self, h, key_mask, img=None, face=None, ner=None, face_name_mask=None, pack=None):
         """BartEncoderLayer.forward with every layer a fusion layer (MFULL:645-744 / MVIS:591-690).  Every state is a
-        pair (bf16 tensor the GEMMs read, fp32 copy carried as the residual -- or None)."""
+        pair (bf16 tensor the GEMMs read, fp32 copy carried as the residual -- or None).  `pack` (varlen.ArticlePack):
+        the article rows `h` are packed [1, rows, d]; the attention kernels get row ranges instead of `key_mask`."""
         rt, cfg, H = self.rt, self.cfg, self.cfg.heads
         kv = None
         (h, h32), (img, img32), (face, face32), (ner, ner32) = h, img or (None, None), face or (None, None), ner or (None, None)
@@ -156,12 +157,12 @@ class BartEncoderLayer(nn.Module):
             else:
                 kv = img_kv
         a = self.self_attn
-        h, h32 = Bk.AttnBlockFn.apply(h, h32, None, None, rt, a.lin_qkv, None, None, a.lin_o, a.ln, H, key_mask, False, True, 0,
-                                      None, False)
+        h, h32 = Bk.AttnBlockFn.apply(h, h32, None, None, rt, a.lin_qkv, None, None, a.lin_o, a.ln, H,
+                                      key_mask if pack is None else pack.self_mask, False, True, 0, None, False)
         if not cfg.stock:
             a = self.cross_attn_img_ner
-            h, h32 = Bk.AttnBlockFn.apply(h, h32, kv, None, rt, None, a.lin_q, a.lin_kv, a.lin_o, a.ln, H, None, False, True, 0,
-                                          None, False)
+            h, h32 = Bk.AttnBlockFn.apply(h, h32, kv, None, rt, None, a.lin_q, a.lin_kv, a.lin_o, a.ln, H,
+                                          None if pack is None else pack.prefix_mask, False, True, 0, None, False)
         h, h32 = Bk.MlpBlockFn.apply(h, h32, rt.fwd_anchor, rt, self.lin_fc1, self.lin_fc2, K.ACT_GELU, self.ln_final)
         return (h, h32), (face, face32), (ner, ner32), (img, img32)
 
@@ -241,22 +242,29 @@ class BartEncoder(nn.Module):
             l.bind(rt)
 
     def forward(self, input_ids=None, attention_mask=None, image_features=None, name_ids=None, name_mask=None,
-                face_features=None, face_mask=None, add_ner_ffn=True, output_hidden_states=True, **unused):
-        """BartEncoder.forward, MFULL:1172-1381 (only-visual MVIS:1086-1251)."""
+                face_features=None, face_mask=None, add_ner_ffn=True, output_hidden_states=True, pack=None, **unused):
+        """BartEncoder.forward, MFULL:1172-1381 (only-visual MVIS:1086-1251).  `pack` (varlen.ArticlePack, extension): the
+        article tokens arrive packed (no padding rows); `input_ids` / `attention_mask` are then ignored and
+        `last_hidden_state` is the packed [1, rows, d] memory."""
         rt, cfg = self.rt, self.cfg
-        if not input_ids.is_cuda:
+        if not (pack.ids if pack is not None else input_ids).is_cuda:
             raise K._l.VacnicError("vacnic_b200 runs on CUDA tensors only (no CPU fallback)")
         if not add_ner_ffn:
             raise ValueError("add_ner_ffn=False is broken in the reference (mask size mismatch, MFULL:666 vs :1296) "
                              "and is not provided")
         rt.training = self.training
         st = rt.store
-        B, L = input_ids.shape
-        if attention_mask is None:
-            attention_mask = torch.ones_like(input_ids)
-        key_mask = Bk.KeyMask(attention_mask)
-        h = Bk.EmbedFn.apply(rt.fwd_anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
-                             self.ln_emb, 2, cfg.pad_token_id)
+        if pack is not None:
+            B, key_mask = pack.B, None
+            h = Bk.EmbedFn.apply(rt.fwd_anchor, pack.ids.view(1, -1), rt, self.embed_tokens.weight, self.embed_positions.weight,
+                                 self.ln_emb, 2, cfg.pad_token_id, pack.pos)
+        else:
+            B, L = input_ids.shape
+            if attention_mask is None:
+                attention_mask = torch.ones_like(input_ids)
+            key_mask = Bk.KeyMask(attention_mask)
+            h = Bk.EmbedFn.apply(rt.fwd_anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
+                                 self.ln_emb, 2, cfg.pad_token_id)
         img = face = ner = fn_mask = None
         if not cfg.stock:
             if not cfg.only_image:
@@ -276,7 +284,7 @@ class BartEncoder(nn.Module):
             if output_hidden_states:
                 states.append(h[0])
             h = (Bk.grad_mark(h[0], rt, ("enc", i)), h[1])  # backward: gradients of encoder layers >= i are final
-            h, face, ner, img = layer(h, key_mask, img, face, ner, fn_mask)
+            h, face, ner, img = layer(h, key_mask, img, face, ner, fn_mask, pack)
         h, img, face, ner = h[0], img and img[0], face and face[0], ner and ner[0]
         if output_hidden_states:
             states.append(h)
@@ -313,8 +321,9 @@ class BartDecoder(nn.Module):
         self.lin_cross_kv = st.lin(ws, bs)
 
     def forward(self, input_ids=None, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
-                output_hidden_states=True, **unused):
-        """BartDecoder.forward (training / teacher-forced path), MFULL:1453-1675."""
+                output_hidden_states=True, pack=None, **unused):
+        """BartDecoder.forward (training / teacher-forced path), MFULL:1453-1675.  `pack`: `encoder_hidden_states` is the
+        packed [1, rows, d] memory of varlen.ArticlePack (cross-attention gets row ranges instead of the mask)."""
         rt, cfg = self.rt, self.cfg
         rt.training = self.training
         st = rt.store
@@ -322,12 +331,19 @@ class BartDecoder(nn.Module):
         d, H = cfg.d_model, cfg.heads
         x, x32 = Bk.EmbedFn.apply(rt.fwd_anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
                                   self.ln_emb, 2, cfg.pad_token_id)
-        enc_mask = None if encoder_attention_mask is None else Bk.KeyMask(encoder_attention_mask)
+        if pack is not None:
+            if T != pack.cross_mask.geo.max_q:
+                raise ValueError("ArticlePack was built for a different decoder length")
+            enc_mask = pack.cross_mask
+        else:
+            enc_mask = None if encoder_attention_mask is None else Bk.KeyMask(encoder_attention_mask)
         dec_mask = None if attention_mask is None else Bk.KeyMask(attention_mask)
         # backward: once this marker fires, the decoder (incl. the hoisted cross K/V projection) and the LM head are done
         encoder_hidden_states = Bk.grad_mark(encoder_hidden_states, rt, ("dec", 0))
         kv_all = Bk.LinearFn.apply(encoder_hidden_states, rt.fwd_anchor, rt, self.lin_cross_kv, torch.bfloat16, True, None, None)
         dkv_all = torch.empty_like(kv_all) if (torch.is_grad_enabled() and kv_all.requires_grad) else None
+        if dkv_all is not None and pack is not None:
+            dkv_all[:, -pack.cross_mask.k_tail:].zero_()  # bucket-padding rows: no caption attends to them, nobody writes them
         states = []
         for i, l in enumerate(self.layers):
             if output_hidden_states:
@@ -445,10 +461,13 @@ class VacnicBart(nn.Module):
                 head_mask=None, decoder_head_mask=None, cross_attn_head_mask=None, encoder_outputs=None,
                 past_key_values=None, inputs_embeds=None, decoder_inputs_embeds=None, labels=None, use_cache=None,
                 output_attentions=None, output_hidden_states=None, return_dict=None, image_features=None,
-                face_features=None, face_mask=None, name_ids=None, name_mask=None, add_ner_ffn=True, ce_targets=None):
+                face_features=None, face_mask=None, name_ids=None, name_mask=None, add_ner_ffn=True, ce_targets=None,
+                article_pack=None):
         """Signature of BartForMultiModalGeneration.forward (MFULL:1929-1953; MVIS:1783-1802 lacks the four
         face/name arguments).  `ce_targets` (extension): fuse the script's CrossEntropyLoss(ignore_index=pad)
-        (TRAIN:287) into the LM head; the result is returned under "loss"."""
+        (TRAIN:287) into the LM head; the result is returned under "loss".  `article_pack` (extension,
+        varlen.ArticlePack): the article arrives as packed rows instead of padded `input_ids` + `attention_mask`;
+        `encoder_last_hidden_state` is then the packed memory (varlen.unpack_rows restores the padded layout)."""
         cfg = self.cfg
         for unsupported, name in ((head_mask, "head_mask"), (decoder_head_mask, "decoder_head_mask"),
                                   (cross_attn_head_mask, "cross_attn_head_mask"), (inputs_embeds, "inputs_embeds"),
@@ -483,10 +502,11 @@ class VacnicBart(nn.Module):
         if encoder_outputs is None:
             encoder_outputs = self.model.encoder(input_ids=input_ids, attention_mask=attention_mask,
                                                  image_features=image_features, name_ids=name_ids, name_mask=name_mask,
-                                                 face_features=face_features, face_mask=face_mask, add_ner_ffn=add_ner_ffn)
+                                                 face_features=face_features, face_mask=face_mask, add_ner_ffn=add_ner_ffn,
+                                                 pack=article_pack)
         enc_h = encoder_outputs["last_hidden_state"] if isinstance(encoder_outputs, dict) else encoder_outputs[0]
         dec = self.model.decoder(input_ids=decoder_input_ids, attention_mask=decoder_attention_mask,
-                                 encoder_hidden_states=enc_h, encoder_attention_mask=attention_mask)
+                                 encoder_hidden_states=enc_h, encoder_attention_mask=attention_mask, pack=article_pack)
         x = dec["last_hidden_state"]
         x_lm, x_out = Bk.fanout(x, 2)
         loss = None

@@ -19,6 +19,7 @@ from . import blocks as Bk
 from . import kernels as K
 from .dp import GradBuckets, PeerShards, vacnic_bucket_prefixes
 from .modeling import VacnicBart, shift_tokens_right
+from .varlen import ArticlePack, pack_articles
 
 
 def linear_schedule(step: int, warmup: int, total: int) -> float:
@@ -33,7 +34,7 @@ class TrainStep:
                  betas=(0.9, 0.999), eps: float = 1e-8, warmup_steps: int = 0, total_steps: int = 1_000_000,
                  margin: float = 1.0, alpha: float = 0.5, secla_weight: float = 1.0, use_graph: bool = True,
                  process_group=None, pipeline_optimizer: Optional[bool] = None, max_grad_norm: Optional[float] = None,
-                 exchange: Optional[str] = None):
+                 exchange: Optional[str] = None, varlen: bool = False):
         """`exchange` (world > 1): "p2p" = rank-sharded optimizer over NVLink peer memory (one fused reduce-scatter + AdamW +
         all-gather kernel per bucket, csrc/dp.cu; needs the model's store in symmetric memory), "p2p-mc" = the same through
         the NVSwitch multicast object (multimem.ld_reduce / multimem.st), "nccl" = in-place NCCL all-reduce of the fp32
@@ -58,10 +59,14 @@ class TrainStep:
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)  # optimizer updates applied so far (device truth)
         self.step_no = 0                                               # host mirror (bookkeeping only)
-        self.graph = None
+        self.graph = None                                  # graph / static inputs / losses of the bucket used last
         self.static: Dict[str, torch.Tensor] = {}
         self.losses: Dict[str, torch.Tensor] = {}
+        self._graphs: Dict[int, tuple] = {}                # shape bucket -> (graph, static inputs, loss tensors)
+        self._pool = None
         self.launches_per_step = 0
+        # packed (varlen) article rows: the collate's padding never reaches the device (vacnic_b200.varlen)
+        self.varlen = bool(varlen)
         self.buckets: Optional[GradBuckets] = None
         self.p2p: Optional[PeerShards] = None
         if exchange is None:
@@ -132,12 +137,14 @@ class TrainStep:
         self._ready.append((i, ev))
 
     # ------------------------------------------------------------------ the step body (capturable)
-    def _body(self, b: Dict[str, torch.Tensor]):
+    def _body(self, b: Dict[str, torch.Tensor], dry: bool = False):
+        """`dry`: forward + backward only (graph warm-up): no schedule tick, no exchange, no optimizer, no collective."""
         model, guide, cfg = self.model, self.guide, self.cfg
         st = model.store
-        # t += 1; hyper = {lr_t, betas, eps, wd, bias corrections, 1/world} -- computed by a device kernel inside the step
-        K.optim_schedule(self.step_dev, self.hyper, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.warmup,
-                         self.total, 1.0 / self.world)
+        if not dry:
+            # t += 1; hyper = {lr_t, betas, eps, wd, bias corrections, 1/world} -- a device kernel inside the step
+            K.optim_schedule(self.step_dev, self.hyper, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.warmup,
+                             self.total, 1.0 / self.world)
         st.begin_step()
         # the backward-pass markers call into THIS step object (another TrainStep may share the model)
         model.rt.grad_hook = self._on_grad_ready if self.buckets is not None else None
@@ -147,8 +154,14 @@ class TrainStep:
         model.rt.rng.advance()
         src, tgt = b["article_ids"], b["caption_ids"]
         dec_in = b["decoder_input_ids"]
+        pack = None
+        if "pk_ids" in b:  # packed article rows (varlen.pack_articles on the host batch)
+            B_, L_ = src.shape
+            prefix = 0 if cfg.stock else cfg.prompt_size + (0 if cfg.only_image else cfg.max_ner_type_len_gt)
+            pack = ArticlePack({k[3:]: b[k] for k in ("pk_ids", "pk_pos", "pk_start", "pk_len", "pk_qlen")}, B_, L_, prefix,
+                               dec_in.shape[1])
         kw = dict(input_ids=src, attention_mask=b["src_mask"], decoder_input_ids=dec_in,
-                  image_features=b["image_features"], ce_targets=tgt)
+                  image_features=b["image_features"], ce_targets=tgt, article_pack=pack)
         if not cfg.only_image:
             kw.update(face_features=b["face_emb"], face_mask=b["face_mask"], name_ids=b["names_art_ids"],
                       name_mask=b["name_mask"])
@@ -157,7 +170,7 @@ class TrainStep:
         losses = {"txt": out["loss"]}
         if guide is not None:
             with torch.no_grad():
-                gout = guide(input_ids=src, attention_mask=b["src_mask"], decoder_input_ids=dec_in)
+                gout = guide(input_ids=src, attention_mask=b["src_mask"], decoder_input_ids=dec_in, article_pack=pack)
             margin = Bk.ColamFn.apply(out["decoder_hidden_states"][-1], gout["decoder_hidden_states"][-1], tgt, self.margin,
                                       cfg.pad_token_id)
             heads.append(margin); grads.append(self._g_margin)
@@ -171,6 +184,8 @@ class TrainStep:
             losses["secla"] = secla
         torch.autograd.backward(heads, grads)
         st.finish_backward()
+        if dry:
+            return losses
         if self.p2p is not None:
             # rank-sharded optimizer over NVLink peer memory.  Per bucket, on the communication stream: wait for the
             # backward-pass marker, barrier (every rank's gradients of the bucket are final and nobody reads its weights
@@ -247,9 +262,12 @@ class TrainStep:
 
     # ------------------------------------------------------------------ host side
     @staticmethod
-    def prepare(batch: Dict[str, torch.Tensor], cfg) -> Dict[str, torch.Tensor]:
-        """Host-side derived inputs of the training loop (TRAIN:267-271): decoder inputs and pad masks."""
+    def prepare(batch: Dict[str, torch.Tensor], cfg, varlen: bool = False) -> Dict[str, torch.Tensor]:
+        """Host-side derived inputs of the training loop (TRAIN:267-271): decoder inputs and pad masks; with `varlen` also
+        the packed article rows (varlen.pack_articles: the device-side replacement of the collate's padding)."""
         b = dict(batch)
+        if varlen:
+            b.update({"pk_" + k: v for k, v in pack_articles(batch["article_ids"].cpu(), cfg.pad_token_id).items()})
         b["decoder_input_ids"] = shift_tokens_right(batch["caption_ids"], cfg.pad_token_id, cfg.eos_token_id)
         b["src_mask"] = (batch["article_ids"] != 1).to(torch.int64)
         if "face_emb" in batch:
@@ -266,18 +284,61 @@ class TrainStep:
         self.step_no = int(t)
         self.step_dev.fill_(int(t))
 
-    def _load_static(self, b: Dict[str, torch.Tensor]):
+    def _load_static(self, static: Dict[str, torch.Tensor], b: Dict[str, torch.Tensor]):
         for k, v in b.items():
-            if k not in self.static:
-                self.static[k] = torch.empty(v.shape, dtype=v.dtype, device=self.model.store.device)
-            if self.static[k].shape != v.shape:
-                raise ValueError(f"batch field {k} changed shape {tuple(self.static[k].shape)} -> {tuple(v.shape)}: "
-                                 "the captured step is shape-specialised; build one TrainStep per bucket")
-            self.static[k].copy_(v, non_blocking=True)
+            if k not in static:
+                static[k] = torch.empty(v.shape, dtype=v.dtype, device=self.model.store.device)
+            if static[k].shape != v.shape:
+                raise ValueError(f"batch field {k} changed shape {tuple(static[k].shape)} -> {tuple(v.shape)}: "
+                                 "the captured step is shape-specialised (only the packed article rows may vary, by bucket)")
+            static[k].copy_(v, non_blocking=True)
+
+    @staticmethod
+    def _bucket_key(b: Dict[str, torch.Tensor]) -> int:
+        """Captured graphs are specialised on tensor shapes; with packed (varlen) articles the only shape that varies from
+        batch to batch is the packed row count, a multiple of varlen.ROW_BUCKET."""
+        return int(b["pk_ids"].numel()) if "pk_ids" in b else 0
+
+    def _capture(self, key: int, b: Dict[str, torch.Tensor]):
+        """Warm-up (allocator, lazy kernel attribute setup) + capture of the step for one shape bucket.  The warm-up runs
+        forward + backward only -- no schedule tick, no gradient exchange, no optimizer -- so it changes no state and issues
+        no collective: under data parallelism ranks meet different buckets at different steps, and a rank that has to
+        capture must not run more collectives than the ranks that merely replay."""
+        model = self.model
+        static: Dict[str, torch.Tensor] = {}
+        self._load_static(static, b)
+        rng_saved = model.rt.rng.state.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._body(static, dry=True)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        model.rt.rng.state.copy_(rng_saved)
+        if not self._graphs and self.world > 1:
+            # FIRST capture (every rank is here at its first step): one eager collective of the largest bucket size, so
+            # that NCCL / the symmetric-memory barrier have done their lazy allocations before any of them is captured
+            with torch.cuda.stream(self.comm_stream):
+                if self.p2p is not None:
+                    self.p2p.barrier(0)
+                elif self.buckets is not None and self.buckets.group is not None:
+                    n = max(b_ - a_ for rs in self.buckets.buckets + [self.buckets.rest] for a_, b_ in rs)
+                    torch.distributed.all_reduce(torch.zeros(n, dtype=torch.float32, device=model.store.device), group=self.pg)
+            torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        c0 = K._l.launch_count()
+        with torch.cuda.graph(graph, pool=self._pool):  # every bucket's graph shares one memory pool (they never overlap)
+            losses = self._body(static)
+        if self._pool is None:
+            self._pool = graph.pool()
+        self.launches_per_step = K._l.launch_count() - c0
+        self._graphs[key] = (graph, static, losses)
+        return self._graphs[key]
 
     def step(self, batch: Dict[str, torch.Tensor], prepared: bool = False) -> Dict[str, torch.Tensor]:
         """Run one optimisation step on a (host or device) batch; returns device scalars {txt, margin, secla}."""
-        b = batch if prepared else self.prepare(batch, self.cfg)
+        b = batch if prepared else self.prepare(batch, self.cfg, varlen=self.varlen)
         model, guide = self.model, self.guide
         if not model.training:
             model.train()
@@ -299,28 +360,13 @@ class TrainStep:
                 self.losses = self._body(b)
                 self.launches_per_step = K._l.launch_count() - c0
                 return self.losses
-            self._load_static(b)
-            if self.graph is None:
-                # warm-up on a side stream (allocator, lazy kernel attribute setup), then capture
-                saved = (st.master.clone(), self.m.clone(), self.v.clone(), model.rt.rng.state.clone(), self.step_dev.clone())
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    for _ in range(2):
-                        self._body(self.static)
-                torch.cuda.current_stream().wait_stream(s)
-                torch.cuda.synchronize()
-                # the warm-up steps must not count as optimisation steps
-                st.master.copy_(saved[0]); self.m.copy_(saved[1]); self.v.copy_(saved[2])
-                model.rt.rng.state.copy_(saved[3]); self.step_dev.copy_(saved[4])
-                st.master_sharded = False  # the complete master was just restored on every rank
-                st.refresh_shadow()
-                del saved
-                self.graph = torch.cuda.CUDAGraph()
-                c0 = K._l.launch_count()
-                with torch.cuda.graph(self.graph):
-                    self.losses = self._body(self.static)
-                self.launches_per_step = K._l.launch_count() - c0
+            key = self._bucket_key(b)
+            entry = self._graphs.get(key)
+            if entry is None:
+                entry = self._capture(key, b)
+            else:
+                self._load_static(entry[1], b)
+            self.graph, self.static, self.losses = entry
             self.graph.replay()
             return self.losses
         finally:
@@ -335,7 +381,9 @@ class TrainStep:
             self.gather_master()  # COLLECTIVE: leave every rank with the complete fp32 master
             self.model.store.gather_master = None
         self.graph = None
-        self.static.clear()
+        self._graphs.clear()
+        self._pool = None
+        self.static = {}
         self.losses = {}
         if getattr(self.model.rt, "grad_hook", None) is not None:
             self.model.rt.grad_hook = None
