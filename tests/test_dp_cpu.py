@@ -130,3 +130,18 @@ def test_shard_of_range_partitions_every_range_exactly_once():
                 assert lo == pos, (world, a, b, covered)
                 pos = hi
             assert pos == b, (world, a, b, covered)
+
+
+def test_balance_shards_is_a_partition_and_evens_out_token_totals():
+    import random
+    from vacnic_b200.dp import balance_shards
+    rnd = random.Random(3)
+    for world, per in ((1, 16), (2, 16), (8, 16), (4, 3)):
+        lens = [rnd.randint(512, 1024) for _ in range(world * per)]
+        sh = balance_shards(lens, world, per)
+        assert sorted(i for s in sh for i in s) == list(range(world * per)) and all(len(s) == per for s in sh)
+        totals = [sum(lens[i] for i in s) for s in sh]
+        naive = [sum(lens[r * per:(r + 1) * per]) for r in range(world)]          # DistributedSampler-style contiguous deal
+        assert max(totals) - min(totals) <= max(lens)                            # within one article of each other
+        assert max(totals) <= max(naive)
+        assert balance_shards(lens, world, per) == sh                            # deterministic

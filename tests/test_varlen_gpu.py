@@ -91,7 +91,7 @@ def test_trainstep_varlen_buckets_and_matches_padded(cuda_device):
     dev = cuda_device
     cfg = spec.VacnicConfig(d_model=768, heads=12, ffn=1024, enc_layers=2, dec_layers=2, prompt_size=4, max_pos=1024)
     gcfg = spec.VacnicConfig(**{**cfg.as_dict(), "stock": True})
-    batches = [synthetic.make_batch(B=4, L=400, T=10, seed=s) for s in (11, 12, 13, 11)]
+    batches = [synthetic.make_batch(B=4, L=800, T=10, seed=s) for s in (11, 12, 13, 11)]   # row buckets 3072, 3072, 2560, 3072
     losses = {}
     for vl in (False, True):
         m = VacnicBart(cfg, device=dev, p_drop=0.0, seed=3)

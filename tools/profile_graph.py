@@ -18,15 +18,19 @@ from vacnic_b200.trainer import TrainStep  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--small", action="store_true")
 ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--no-varlen", action="store_true")
+ap.add_argument("--pdl", default=None, help="set VACNIC_PDL (0 = kernel durations do not overlap)")
 args = ap.parse_args()
+if args.pdl is not None:
+    os.environ["VACNIC_PDL"] = args.pdl
 dev = torch.device("cuda:0")
 cfg = spec.bart_base() if args.small else spec.bart_large()
 gcfg = spec.bart_base(stock=True) if args.small else spec.VacnicConfig(stock=True)
 model = VacnicBart(cfg, device=dev, p_drop=0.1, seed=1)
 guide = VacnicBart(gcfg, device=dev, p_drop=0.0, seed=2, frozen=True)
-ts = TrainStep(model, guide, use_graph=True)
+ts = TrainStep(model, guide, use_graph=True, varlen=not args.no_varlen)
 L, T = (512, 40) if args.small else (1024, 64)
-b = {k: v.to(dev) for k, v in TrainStep.prepare(synthetic.make_batch(B=args.batch, L=L, T=T, seed=1), cfg).items()}
+b = {k: v.to(dev) for k, v in TrainStep.prepare(synthetic.make_batch(B=args.batch, L=L, T=T, seed=1), cfg, varlen=not args.no_varlen).items()}
 for _ in range(4):
     ts.step(b, prepared=True)
 torch.cuda.synchronize()

@@ -172,3 +172,22 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     base, extra = divmod(n_items, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def balance_shards(lengths: Sequence[int], world: int, per_rank: int) -> List[List[int]]:
+    """Length-balanced assignment of the samples of a global batch to `world` ranks, `per_rank` samples each
+    (len(lengths) == world * per_rank): longest first, each sample goes to the rank with the smallest token total that
+    still has a free slot.  With packed (varlen) article rows a rank's step time is proportional to its token total, and a
+    synchronous data-parallel step waits for the slowest rank; the reference's DistributedSampler (TRAIN:775) deals the
+    samples out at random, which is harmless there only because every rank pads to the same [B, L] rectangle.  The
+    gradient average is over the same global batch whichever rank processes which sample.  Deterministic."""
+    if len(lengths) != world * per_rank:
+        raise ValueError(f"balance_shards: {len(lengths)} samples for {world} ranks x {per_rank}")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    shards: List[List[int]] = [[] for _ in range(world)]
+    totals = [0] * world
+    for i in order:
+        r = min((r for r in range(world) if len(shards[r]) < per_rank), key=lambda r: (totals[r], r))
+        shards[r].append(i)
+        totals[r] += int(lengths[i])
+    return [sorted(sh) for sh in shards]
