@@ -183,6 +183,10 @@ int vacnic_pad_rows(const void* src, void* dst, int64_t rows, int32_t n, int32_t
 /* dst[j] (+)= sum_p src[p*len + j] (fp32): reduces split partial weight gradients. */
 int vacnic_sum_partials(const float* src, float* dst, int32_t parts, int64_t len, int32_t accumulate, void* stream);
 int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream); /* out = a + b (+ c) */
+/* Packed (varlen) rows -> the collate's right-padded layout (DNYT:957-972): dst[b, t, :] = src[start[b] + t, :] for
+ * t < len[b], zeros otherwise; src bf16 [rows, d], dst bf16 [batch, L, d], start / len int32 [batch]. */
+int vacnic_unpack_rows(const void* src, const int32_t* start, const int32_t* len, void* dst, int32_t batch, int32_t L, int32_t d,
+                       void* stream);
 /* Fused AdamW over a flat parameter buffer (TRAIN:91-107,371-373).  hyper (device, fp32[8]) =
  * {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}; also refreshes the bf16
  * compute shadow p16 (may be null). */

@@ -109,3 +109,30 @@ def test_trainstep_varlen_buckets_and_matches_padded(cuda_device):
     for a, b in zip(losses[False], losses[True]):
         for k in a:
             assert abs(a[k] - b[k]) <= 5e-3 * max(1.0, abs(a[k])), (k, losses)
+
+
+def test_generation_with_packed_encoder_is_identical(cuda_device):
+    """Decode engine: the packed encoder gives BIT-IDENTICAL memory on the valid tokens (same per-row arithmetic, same key
+    blocks), hence identical beam-4 / greedy token ids; pad rows of the un-packed memory are zero and never attended."""
+    from vacnic_b200 import generation
+    from vacnic_b200.modeling import VacnicBart
+    dev = cuda_device
+    cfg = spec.VacnicConfig(d_model=768, heads=12, ffn=1024, enc_layers=2, dec_layers=2, prompt_size=4, max_pos=1024)
+    m = VacnicBart(cfg, device=dev, p_drop=0.0)
+    m.load_reference_state_dict(spec.test_state_dict(cfg, 9, lm_scale=8.0))
+    m.eval()
+    batch = synthetic.to_device(synthetic.make_batch(B=6, L=300, T=8, seed=4), dev)
+    kw = _kw(cfg, batch)
+    outs = {}
+    for vl in (False, True):
+        for nb in (1, 4):
+            eng = generation.Generator(m, 6, nb, 300, 14, length_penalty=2.0, varlen=vl)
+            enc = eng.encode(generation._enc_inputs(m, *(kw[k] for k in ("input_ids", "attention_mask", "image_features",
+                                                                         "face_features", "face_mask", "name_ids", "name_mask"))))
+            outs[(vl, nb)] = (eng.decode().clone(), enc["last_hidden_state"].clone(), eng.cross_kv.clone(), eng.key_len.clone())
+    valid = kw["attention_mask"].bool()
+    for nb in (1, 4):
+        (ids_a, h_a, kv_a, kl_a), (ids_b, h_b, kv_b, kl_b) = outs[(False, nb)], outs[(True, nb)]
+        assert torch.equal(ids_a, ids_b)
+        assert torch.equal(h_a[valid], h_b[valid]) and bool((h_b[~valid] == 0).all())
+        assert torch.equal(kl_a, kl_b)

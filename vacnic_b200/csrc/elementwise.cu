@@ -153,6 +153,24 @@ vit_patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ o
   *reinterpret_cast<uint4*>(out + prow * cols + col) = u;
 }
 
+
+// Packed rows -> right-padded [B, L, d] (bf16): dst[b, t] = src[start[b] + t] for t < len[b], else 0.  Restores the
+// collate's layout (DNYT:957-972) where a consumer needs one row block per sample (the per-caption cross-attention K/V
+// projection of the decode engine).  One warp per destination row, 16-byte accesses.
+__global__ void __launch_bounds__(256)
+unpack_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ start, const int32_t* __restrict__ len,
+                   __nv_bfloat16* __restrict__ dst, long long rows, int L, int d) {
+  pdl_sync();
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(row / L), t = static_cast<int>(row % L);
+  const bool valid = t < len[b];
+  const uint4* sp = reinterpret_cast<const uint4*>(src + (static_cast<long long>(start[b]) + t) * d);
+  uint4* dp = reinterpret_cast<uint4*>(dst + row * d);
+  for (int v = lane; v < d / 8; v += 32) dp[v] = valid ? __ldg(sp + v) : make_uint4(0, 0, 0, 0);
+}
+
 // out = a + b (+ c) on bf16, fp32 math; gradient fan-in of the residual / state streams
 __global__ void __launch_bounds__(256)
 add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
@@ -350,6 +368,20 @@ extern "C" int vacnic_vit_patchify(const float* images, void* out, int32_t batch
              images, static_cast<__nv_bfloat16*>(out), batch, channels, height, width, patch);
   count_launch();
   return check_last("vit_patchify");
+}
+
+
+extern "C" int vacnic_unpack_rows(const void* src, const int32_t* start, const int32_t* len, void* dst, int32_t batch, int32_t L,
+                                  int32_t d, void* stream) {
+  VB_REQUIRE(src && start && len && dst, "unpack_rows: null pointer");
+  VB_REQUIRE(batch >= 0 && L > 0 && d > 0 && d % 8 == 0, "unpack_rows: d must be a multiple of 8");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "unpack_rows: misaligned");
+  if (batch == 0) return VACNIC_OK;
+  const long long rows = static_cast<long long>(batch) * L;
+  launch_pdl(unpack_rows_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             static_cast<const __nv_bfloat16*>(src), start, len, static_cast<__nv_bfloat16*>(dst), rows, L, d);
+  count_launch();
+  return check_last("unpack_rows");
 }
 
 extern "C" int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream) {

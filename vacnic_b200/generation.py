@@ -26,7 +26,7 @@ class Generator:
     """Decode engine specialised for (captions, beams, article length, max_length) on one model."""
 
     def __init__(self, model, captions: int, beams: int, L: int, max_length: int, length_penalty: float = 1.0,
-                 use_graph: bool = True, poll_every: int = 4):
+                 use_graph: bool = True, poll_every: int = 4, varlen: bool = True):
         cfg = model.cfg
         if max_length < 2 or max_length > 256:
             raise ValueError("max_length must be in 2..256")
@@ -40,6 +40,10 @@ class Generator:
         self.R = captions * beams
         self.maxT = max_length
         self.use_graph, self.poll_every = use_graph, max(1, poll_every)
+        # packed (varlen) article rows through the encoder: the padding of the batch never enters a GEMM / LayerNorm /
+        # attention tile (vacnic_b200.varlen); the memory is un-packed once for the per-caption cross K/V projection
+        self.varlen = bool(varlen)
+        self.flags_host = torch.zeros(max_length + 1, 2, dtype=torch.int32).pin_memory()
         dev = model.store.device
         d, f, V = cfg.d_model, cfg.ffn, cfg.vocab
         R, nl = self.R, cfg.dec_layers
@@ -105,11 +109,15 @@ class Generator:
         encoder = model.model.encoder
         was_training = encoder.training
         encoder.training = False  # dropout off for this call only; no train()/eval() round trip (that would re-cast the shadow)
+        pack = self._pack(enc_inputs) if self.varlen else None
         try:
-            enc = encoder(output_hidden_states=False, **enc_inputs)
+            enc = encoder(output_hidden_states=False, pack=pack, **enc_inputs)
         finally:
             encoder.training = was_training
         h = enc["last_hidden_state"]
+        if pack is not None:  # packed [1, rows, d] -> [C, L, d] (pad rows zero: never attended, key_len below)
+            h = K.unpack_rows(h[0], pack.start, pack.len, self.L)
+            enc["last_hidden_state"] = h
         C, L, d = h.shape
         if (C, L) != (self.C, self.L):
             raise ValueError(f"generator built for {self.C} captions x {self.L} tokens, got {C} x {L}")
@@ -124,6 +132,34 @@ class Generator:
             K.gemm(h, lin.w16[l * 2 * d:(l + 1) * 2 * d].unsqueeze(0).expand(C, 2 * d, d), out=self.cross_kv[l],
                    bias=lin.b32[l * 2 * d:(l + 1) * 2 * d], head_major=(64, 2 * d * L, 0, L * 64))
         return enc
+
+    def _pack(self, enc_inputs: dict):
+        """Device-side batch assembly for the encoder (the collate's padding, DNYT:957-972, stays out of the compute):
+        article tokens packed back to back, rows rounded up to varlen.ROW_BUCKET.  One small device -> host read (the
+        lengths) sizes the buffers; everything else is index arithmetic on the device."""
+        from .varlen import ROW_BUCKET, ArticlePack
+        ids, mask = enc_inputs["input_ids"], enc_inputs.get("attention_mask")
+        C, L = ids.shape
+        if mask is None:
+            return None
+        mb = mask.bool()
+        lens = mb.sum(1)
+        ar = torch.arange(L, device=ids.device)
+        if not bool((mb == (ar[None, :] < lens[:, None])).all()) or int(lens.min()) < 1:
+            return None  # not the collate's right padding (or an empty article): keep the padded path
+        M = int(lens.sum())
+        M_pad = (M + ROW_BUCKET - 1) // ROW_BUCKET * ROW_BUCKET
+        pid = torch.full((M_pad,), self.cfg.pad_token_id, dtype=torch.int64, device=ids.device)
+        pos = torch.zeros(M_pad, dtype=torch.int32, device=ids.device)
+        pid[:M] = ids[mb]
+        pos[:M] = ar.to(torch.int32)[None, :].expand(C, L)[mb]
+        ln = lens.to(torch.int32)
+        start = (torch.cumsum(lens, 0) - lens).to(torch.int32)
+        qlen = ln.clone()
+        qlen[-1] += M_pad - M
+        cfg = self.cfg
+        prefix = 0 if cfg.stock else cfg.prompt_size + (0 if cfg.only_image else cfg.max_ner_type_len_gt)
+        return ArticlePack({"ids": pid, "pos": pos, "start": start, "len": ln, "qlen": qlen}, C, L, prefix, 1)
 
     # ------------------------------------------------------------------ one decoding step (capturable)
     def _step(self):
@@ -187,7 +223,19 @@ class Generator:
             self._reset_state()
             self._capture()
         self._reset_state()
-        t, stop_t = 1, None
+        # Search loop.  The host enqueues `poll_every` graph replays at a time and looks at the stop flags of the PREVIOUS
+        # chunk (copied into pinned memory behind that chunk) while the GPU is already working on the current one, so the
+        # device never idles on the stop test.  At most one extra chunk runs after every caption has finished; finished
+        # hypotheses are frozen by the step kernels (`unsat` / `unfinished`), so the result does not depend on it.
+        t, stop_t, pending = 1, None, None
+
+        def check(p):
+            ev, t0, n = p
+            ev.synchronize()  # device -> host read: the stop test of the search loop
+            fl = self.flags_host[t0:t0 + n]
+            go = (fl[:, 0] != 0) & (fl[:, 1] != 0)
+            return None if bool(go.all()) else t0 + int((~go).nonzero()[0])
+
         while t < self.max_len:
             n = min(self.poll_every, self.max_len - t)
             for _ in range(n):
@@ -197,12 +245,17 @@ class Generator:
                     c0 = K._l.launch_count()
                     self._step()
                     self.launches_per_step = K._l.launch_count() - c0
-            flags = self.st["flags"][t:t + n].cpu()  # device -> host read: the stop test of the search loop
-            go = (flags[:, 0] != 0) & (flags[:, 1] != 0)
+            self.flags_host[t:t + n].copy_(self.st["flags"][t:t + n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:
+                stop_t = check(pending)
+            pending = (ev, t, n)
             t += n
-            if not bool(go.all()):
-                stop_t = t - n + int((~go).nonzero()[0])
+            if stop_t is not None:
                 break
+        if stop_t is None and pending is not None:
+            stop_t = check(pending)
         self.steps_run = t - 1
         if stop_t is None:
             stop_t = self.max_len - 1

@@ -260,6 +260,16 @@ def vit_embed_ln(tok, cls, pos, gamma, beta, batch, tokens):
     return y32
 
 
+def unpack_rows(src2d, start, lens, L, out=None):
+    """bf16 packed rows [rows, d] -> right-padded [B, L, d] (pad rows zero)."""
+    _c(src2d, torch.bfloat16, "packed rows"); _c(start, torch.int32, "start"); _c(lens, torch.int32, "len")
+    B, d = start.numel(), src2d.shape[-1]
+    if out is None:
+        out = torch.empty(B, L, d, dtype=torch.bfloat16, device=src2d.device)
+    check(lib().vacnic_unpack_rows(ptr(src2d), ptr(start), ptr(lens), ptr(out), B, L, d, stream_ptr()), "vacnic_unpack_rows")
+    return out
+
+
 def names_embed(ids3, tok, pos, gamma, beta):
     """get_embedding_ner (TRAIN:112-133): ids [B,N,len] -> fp32 [B,N,d]."""
     _c(ids3, torch.int64, "names_ids")
