@@ -47,6 +47,20 @@ def timeit(fn):
     return best
 
 
+if os.environ.get("PACKED"):
+    # the same work through the packed (varlen) interface: one [B*S, .] row buffer, per-sequence row ranges, no mask bytes
+    q1, k1, v1 = (t.as_strided((1, H, B * S, hd), (B * S * ld, hd, ld, 1), t.storage_offset()) for t in (q4, k4, v4))
+    dq1, dk1, dv1 = (t.as_strided((1, H, B * S, hd), (B * S * ld, hd, ld, 1), t.storage_offset()) for t in (dq4, dk4, dv4))
+    start = (torch.arange(B, device=dev, dtype=torch.int32) * S)
+    geo = K.Packed(start, kl.to(torch.int32), start, kl.to(torch.int32), S, S)
+    outp, statsp = K.attn_fwd(q1, k1, v1, packed=geo)
+    dO1 = dO.view(1, B * S, d)
+    flops = 4.0 * float((kl.float() * kl.float()).sum()) * hd * H
+    t_f = timeit(lambda: K.attn_fwd(q1, k1, v1, packed=geo))
+    t_b = timeit(lambda: K.attn_bwd(dO1, outp, statsp, q1, k1, v1, dq1, dk1, dv1, packed=geo))
+    print(f"PACKED S={S} fwd {t_f * 1e3:.1f} us ({flops / 1e12 / (t_f / 1e3):.0f} TF/s on len^2 work)   bwd(dq+dkv) {t_b * 1e3:.1f} us "
+          f"({2.5 * flops / 1e12 / (t_b / 1e3):.0f} TF/s)")
+    sys.exit(0)
 t_f = timeit(lambda: K.attn_fwd(q4, k4, v4, mask, kl, False))
 t_b = timeit(lambda: K.attn_bwd(dO, out, stats, q4, k4, v4, dq4, dk4, dv4, mask, kl, False))
 t_f2 = timeit(lambda: K.attn_fwd(q4, k4, v4, mask, kl, False))

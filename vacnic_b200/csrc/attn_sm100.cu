@@ -146,8 +146,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int k0 = j * kAK;
       sh->blk_flag[j] = ((k0 + kAK > geo.Sk) || (a.causal && k0 + kAK - 1 > q0)) ? 1 : 0;
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (a.key_mask != nullptr) {
+    if (a.key_mask != nullptr) {  // (packed mode and mask-free call sites skip the scan and its barrier)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint8_t* mk = a.key_mask + static_cast<long long>(b) * a.Sk;
       const int kend = min(nkb * kAK, geo.Sk);
       for (int k = tid * 16; k < kend; k += kCompThreads * 16) {
@@ -268,12 +268,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float bm = -INFINITY;
       const float kk = need ? 1.0f : c2;
       if (need) {
+        if (mk == nullptr && !a.causal) {
+          // only the sequence end can cut this block (packed rows / no padding mask): columns >= nv are out of range.
+          // Two compares per element instead of the general path's byte loads and branches.
+          const int nv = geo.Sk - kb;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float t0 = masked(__uint_as_float(x0[c]), kb + c), t1 = masked(__uint_as_float(x1[c]), kb + 32 + c);
-          x0[c] = __float_as_uint(t0);
-          x1[c] = __float_as_uint(t1);
-          bm = fmaxf(bm, fmaxf(t0, t1));
+          for (int c = 0; c < 32; ++c) {
+            const float t0 = c < nv ? __uint_as_float(x0[c]) * c2 : -INFINITY;
+            const float t1 = c + 32 < nv ? __uint_as_float(x1[c]) * c2 : -INFINITY;
+            x0[c] = __float_as_uint(t0);
+            x1[c] = __float_as_uint(t1);
+            bm = fmaxf(bm, fmaxf(t0, t1));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float t0 = masked(__uint_as_float(x0[c]), kb + c), t1 = masked(__uint_as_float(x1[c]), kb + 32 + c);
+            x0[c] = __float_as_uint(t0);
+            x1[c] = __float_as_uint(t1);
+            bm = fmaxf(bm, fmaxf(t0, t1));
+          }
         }
       } else {
 #pragma unroll
@@ -295,14 +309,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         m = bm;
         l *= f;
       }
-      // exponentials in place (registers), before waiting for PV_{j-1}
+      // exponentials, packed to bf16 pairs right away (the fp32 scores die as they are consumed: 32 live registers of
+      // packed P instead of 64 of fp32 P -- the 64-register version spilled to local memory), before waiting for PV_{j-1}
+      uint32_t pk[32];
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float p0 = ex2f(fmaf(__uint_as_float(x0[c]), kk, -m)), p1 = ex2f(fmaf(__uint_as_float(x1[c]), kk, -m));
-        l += p0 + p1;
-        x0[c] = __float_as_uint(p0);
-        x1[c] = __float_as_uint(p1);
+      for (int c = 0; c < 32; c += 2) {
+        const float a0 = ex2f(fmaf(__uint_as_float(x0[c]), kk, -m)), a1 = ex2f(fmaf(__uint_as_float(x0[c + 1]), kk, -m));
+        const float b0 = ex2f(fmaf(__uint_as_float(x1[c]), kk, -m)), b1 = ex2f(fmaf(__uint_as_float(x1[c + 1]), kk, -m));
+        l0 += a0 + a1;
+        l1 += b0 + b1;
+        pk[c >> 1] = pack_bf16x2(a0, a1);
+        pk[16 + (c >> 1)] = pack_bf16x2(b0, b1);
       }
+      l += l0 + l1;
       if (j > 0) {
         mbar_wait(&sh->p_empty, (j - 1) & 1u);  // PV_{j-1} retired: P buffer free, O quiescent
         tc_fence_after();
@@ -320,18 +340,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        st_shared_v4(atom + ((static_cast<uint32_t>(q) ^ sw) << 4),
-                     pack_bf16x2(__uint_as_float(x0[8 * q]), __uint_as_float(x0[8 * q + 1])),
-                     pack_bf16x2(__uint_as_float(x0[8 * q + 2]), __uint_as_float(x0[8 * q + 3])),
-                     pack_bf16x2(__uint_as_float(x0[8 * q + 4]), __uint_as_float(x0[8 * q + 5])),
-                     pack_bf16x2(__uint_as_float(x0[8 * q + 6]), __uint_as_float(x0[8 * q + 7])));
+        st_shared_v4(atom + ((static_cast<uint32_t>(q) ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        st_shared_v4(atom + ((static_cast<uint32_t>(4 + q) ^ sw) << 4),
-                     pack_bf16x2(__uint_as_float(x1[8 * q]), __uint_as_float(x1[8 * q + 1])),
-                     pack_bf16x2(__uint_as_float(x1[8 * q + 2]), __uint_as_float(x1[8 * q + 3])),
-                     pack_bf16x2(__uint_as_float(x1[8 * q + 4]), __uint_as_float(x1[8 * q + 5])),
-                     pack_bf16x2(__uint_as_float(x1[8 * q + 6]), __uint_as_float(x1[8 * q + 7])));
+        st_shared_v4(atom + ((static_cast<uint32_t>(4 + q) ^ sw) << 4), pk[16 + 4 * q], pk[16 + 4 * q + 1], pk[16 + 4 * q + 2],
+                     pk[16 + 4 * q + 3]);
       tc_fence_before();
       fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor pipe (async proxy)
       mbar_arrive(&sh->p_full);
@@ -562,8 +575,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int kb0 = j * 64;
         sh->blk_flag[j] = ((kb0 + 64 > geo.Sk) || (a.causal && kb0 + 63 > q0)) ? 1 : 0;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (mk != nullptr) {
+      if (mk != nullptr) {  // (packed mode and mask-free call sites skip the scan and its barrier)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int kend = min(nkb * 64, geo.Sk);
         for (int k = tid * 16; k < kend; k += kCompThreads * 16) {
           bool z = false;
