@@ -157,18 +157,6 @@ int vacnic_softmax_bwd(const void* probs, const float* dprobs, void* dscores, in
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * NER-prefix map (MFULL:682-687): rows = B*d_model rows of E contiguous bf16 elements (the
- * reference's reshape(B, d, E) reinterpretation of [B, E, d]); z1 = x W_up^T + b_up (bf16 [rows, U],
- * kept for the backward), z2 = gelu(z1) W_down^T + b_down (bf16 [rows, G]).  E, U <= 80, G <= 32.
- * The backward writes dx and atomically accumulates the fp32 parameter gradients.
- * ------------------------------------------------------------------------------------------ */
-int vacnic_ner_map_fwd(const void* x, const void* w_up, const float* b_up, const void* w_down, const float* b_down,
-                       void* z1, void* z2, int64_t rows, int32_t E, int32_t U, int32_t G, void* stream);
-int vacnic_ner_map_bwd(const void* dz2, const void* z1, const void* x, const void* w_up, const void* w_down, void* dx,
-                       float* dw_up, float* db_up, float* dw_down, float* db_down, int64_t rows, int32_t E, int32_t U,
-                       int32_t G, void* stream);
-
-/* ------------------------------------------------------------------------------------------
  * Elementwise / reduction helpers.
  * ------------------------------------------------------------------------------------------ */
 int vacnic_colsum(const void* x, float* out, int64_t rows, int32_t n, int64_t ld, void* stream); /* out[c] += sum_r x[r,c] : nn.Linear bias gradients */

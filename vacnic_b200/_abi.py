@@ -19,8 +19,6 @@ SIGNATURES = {
     "vacnic_names_embed": [P, P, P, P, P, P, I64, I32, I32, F32, P],
     "vacnic_softmax_fwd": [P, P, P, I32, I32, I32, I32, I32, I32, I32, P],
     "vacnic_softmax_bwd": [P, P, P, I64, I32, I32, P],
-    "vacnic_ner_map_fwd": [P, P, P, P, P, P, P, I64, I32, I32, I32, P],
-    "vacnic_ner_map_bwd": [P, P, P, P, P, P, P, P, P, P, I64, I32, I32, I32, P],
     "vacnic_colsum": [P, P, I64, I32, I64, P],
     "vacnic_cast_f32_bf16": [P, P, I64, P],
     "vacnic_concat_rows": [P, P, P, I32, I64, I64, I32, P],

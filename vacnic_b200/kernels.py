@@ -435,27 +435,6 @@ def secla_bwd(ws, names, gscale, coef, dface, accumulate=False):
     return dface
 
 
-def ner_map_fwd(x_rows, w_up, b_up, w_down, b_down):
-    """x_rows bf16 [rows, E] -> (z1 bf16 [rows, U], z2 bf16 [rows, G]); MFULL:682-687."""
-    _c(x_rows, torch.bfloat16, "ner_map x"); _c(w_up, torch.bfloat16, "w_up"); _c(w_down, torch.bfloat16, "w_down")
-    rows, E = x_rows.shape
-    U, G = w_up.shape[0], w_down.shape[0]
-    z1 = torch.empty(rows, U, dtype=torch.bfloat16, device=x_rows.device)
-    z2 = torch.empty(rows, G, dtype=torch.bfloat16, device=x_rows.device)
-    check(lib().vacnic_ner_map_fwd(ptr(x_rows), ptr(w_up), ptr(b_up), ptr(w_down), ptr(b_down), ptr(z1), ptr(z2), rows, E, U, G,
-                                   stream_ptr()), "vacnic_ner_map_fwd")
-    return z1, z2
-
-
-def ner_map_bwd(dz2, z1, x_rows, w_up, w_down, dw_up, db_up, dw_down, db_down):
-    rows, E = x_rows.shape
-    U, G = w_up.shape[0], w_down.shape[0]
-    dx = torch.empty_like(x_rows)
-    check(lib().vacnic_ner_map_bwd(ptr(dz2), ptr(z1), ptr(x_rows), ptr(w_up), ptr(w_down), ptr(dx), ptr(dw_up), ptr(db_up),
-                                   ptr(dw_down), ptr(db_down), rows, E, U, G, stream_ptr()), "vacnic_ner_map_bwd")
-    return dx
-
-
 def concat_rows(a, b, out):
     """out[B, Sa+Sb, d] = cat(a [B,Sa,d], b [B,Sb,d]) along dim 1 (bf16, contiguous)."""
     a, b = a.contiguous(), b.contiguous()
