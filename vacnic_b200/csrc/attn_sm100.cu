@@ -90,6 +90,9 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// GENERAL = false: no padding-mask bytes and no causal mask (packed rows, prefix / CLIP attention): only the sequence end can
+// cut a key block.  Keeping the byte-load path out of this instantiation is what keeps it free of local-memory spills.
+template <bool GENERAL>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
@@ -239,8 +242,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint8_t* mk = a.key_mask ? a.key_mask + static_cast<long long>(b) * a.Sk : nullptr;
     const float c2 = a.scale_log2;
     uint32_t it = 0;
-    // masked score in the log2 domain
-    auto masked = [&](float s, int key) -> float {
+    // Sequence-end masking (both variants) happens in the RAW score domain, in place -- a key past the end becomes -inf
+    // (probability exactly 0) and the scale rides on the FFMA in front of the exponential -- so that cut and uncut blocks
+    // leave the scores in the same registers (scaling in place made the compiler shuffle all 64 of them on the uncut
+    // path).  Padding-mask bytes and the causal mask (GENERAL variant) are applied to the scaled score: a masked key gets
+    // -FLT_MAX = finfo.min, so a fully masked row is uniform like the reference.
+    auto masked = [&](float s, int key) -> float {  // GENERAL variant only: scaled + masked score (log2 domain)
       if (key >= geo.Sk) return -INFINITY;
       if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) return -FLT_MAX;
       return s * c2;
@@ -262,25 +269,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&sh->s_empty);  // all of S_j is in registers: the tensor pipe may overwrite it
-      // block maximum of this half in the log2 domain.  Blocks that need mask decisions are scaled and masked in place
-      // (kk = 1 below); the others stay raw -- their scale rides on the FFMA in front of the exponential (kk = c2 > 0,
-      // so max(raw) * c2 == max(raw * c2)), as in the backward kernels
-      float bm = -INFINITY;
-      const float kk = need ? 1.0f : c2;
+      float bm = -INFINITY, kk = c2;
+      bool have_max = false;
       if (need) {
-        if (mk == nullptr && !a.causal) {
-          // only the sequence end can cut this block (packed rows / no padding mask): columns >= nv are out of range.
-          // Two compares per element instead of the general path's byte loads and branches.
+        if (!GENERAL || (mk == nullptr && !a.causal)) {
+          // only the sequence end can cut this block (packed rows / no padding mask): columns >= nv are out of range
           const int nv = geo.Sk - kb;
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            const float t0 = c < nv ? __uint_as_float(x0[c]) * c2 : -INFINITY;
-            const float t1 = c + 32 < nv ? __uint_as_float(x1[c]) * c2 : -INFINITY;
-            x0[c] = __float_as_uint(t0);
-            x1[c] = __float_as_uint(t1);
-            bm = fmaxf(bm, fmaxf(t0, t1));
+            if (c >= nv) x0[c] = 0xff800000u;       // -inf
+            if (c + 32 >= nv) x1[c] = 0xff800000u;
           }
-        } else {
+        } else if constexpr (GENERAL) {
+          // padding-mask bytes / causal mask: scale and mask in place (kk = 1 below)
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             const float t0 = masked(__uint_as_float(x0[c]), kb + c), t1 = masked(__uint_as_float(x1[c]), kb + 32 + c);
@@ -288,8 +289,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             x1[c] = __float_as_uint(t1);
             bm = fmaxf(bm, fmaxf(t0, t1));
           }
+          kk = 1.0f;
+          have_max = true;
         }
-      } else {
+      }
+      if (!have_max) {
+        // block maximum of this half in the log2 domain (c2 > 0, so max(raw) * c2 == max(raw * c2))
 #pragma unroll
         for (int c = 0; c < 32; ++c) bm = fmaxf(bm, fmaxf(__uint_as_float(x0[c]), __uint_as_float(x1[c])));
         bm *= c2;
@@ -923,12 +928,17 @@ extern "C" int vacnic_attn_fwd(const vacnic_attn_desc* d, void* stream) {
   a.q_start = d->q_start; a.q_len = d->q_len; a.k_start = d->k_start; a.k_len = d->k_len; a.total_q = d->total_q;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
     if (e != cudaSuccess) return fail(VACNIC_ECUDA, "attn_fwd: cudaFuncSetAttribute(smem=%d): %s", kAttnSmemBytes, cudaGetErrorString(e));
     configured = true;
   }
   const dim3 grid((d->Sq + kAQ - 1) / kAQ, d->H, d->B);
-  launch_pdl(attn_fwd_kernel, grid, dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, a);
+  if (d->key_mask != nullptr || d->causal)
+    launch_pdl(attn_fwd_kernel<true>, grid, dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, a);
+  else
+    launch_pdl(attn_fwd_kernel<false>, grid, dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, a);
   count_launch();
   return check_last("attn_fwd launch");
 }
