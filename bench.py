@@ -56,7 +56,9 @@ def train_flops_per_sample(cfg, L, T, with_guide=True):
     prefix = 2 * 768 * 384 * P + 2 * 384 * P * 768 * P + (2 * P * 768 * d if d == 1024 else 0) + (2 * F * 512 * d if full else 0)
     fwd = cfg.enc_layers * enc + cfg.dec_layers * dec + head + prefix
     stock_enc = 8 * L * d * d + 4 * L * L * d + 4 * L * d * f
-    guide = cfg.enc_layers * stock_enc + cfg.dec_layers * dec + head  # HF forward of the frozen guide computes its logits too
+    # the frozen guide: encoder + decoder only.  (HF's forward also computes the guide's logits; CoLaM never reads them
+    # (TRAIN:293-296), this implementation skips that GEMM and does not count it: 6.6 of SURVEY 8(d)'s 444.9 GF)
+    guide = cfg.enc_layers * stock_enc + cfg.dec_layers * dec
     return 3 * fwd + (guide if with_guide else 0), fwd, guide
 
 

@@ -204,6 +204,10 @@ int vacnic_dp_adamw_shard(const uint64_t* grad_ptrs, const uint64_t* shadow_ptrs
 int vacnic_clip_grad_scale(const float* g, int64_t n, float max_norm, float base_scale, float* scratch, float* scale_out,
                            float* norm_out, void* stream);
 int vacnic_rng_advance(uint64_t* state, void* stream);
+/* x = dropout(x) in place (bf16, n elements contiguous): config.activation_dropout after the FFN activation (MFULL:649, 660,
+ * 684, 740, 874).  Counter-based mask keyed by (*rng_state, salt, element index): calling it again on the gradient with
+ * the same key applies the same mask (backward pass). */
+int vacnic_dropout_inplace(void* x, int64_t n, float p_drop, const uint64_t* rng_state, uint32_t salt, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------
@@ -323,6 +327,10 @@ typedef struct vacnic_attn_desc {
    * All four arrays are int32 device pointers of length B. */
   const int32_t* q_start; const int32_t* q_len; const int32_t* k_start; const int32_t* k_len;
   int32_t total_q, total_k;
+  /* Attention dropout (config.attention_dropout: `nn.functional.dropout(attn_weights, p=self.dropout)` after the softmax,
+   * MFULL:546).  p_drop = 0 disables it.  Counter-based Bernoulli mask keyed by (*rng_state, salt, (sequence, head, query
+   * row), key): vacnic_attn_bwd regenerates it from the same values, nothing is stored. */
+  float p_drop; const uint64_t* rng_state; uint32_t salt;
 } vacnic_attn_desc;
 int vacnic_attn_fwd(const vacnic_attn_desc* d, void* stream);
 /* dq, dk, dv of the above (dq/dk carry the head_dim^-0.5 factor).  `out` must hold the forward result. */

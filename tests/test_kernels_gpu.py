@@ -386,3 +386,103 @@ def test_ner_map_block_applies_the_reference_dropout(cuda_device):
         again = Bk.NerMapFn.apply(ner, m.rt, layer.lin_nup, layer.lin_ndown, layer.ln_nmap).float()
     assert torch.equal(outs[False], again)
     assert (outs[True] - outs[False]).abs().mean().item() > 0.1
+
+
+def _keep_mask(seed, salt, rowid, key, p):
+    """Python restatement of ptx.cuh keep_elem / attn_sm100.cu keep_attn (uint32 arithmetic on int64 tensors)."""
+    M = 0xFFFFFFFF
+
+    def hash32(x):
+        x = x ^ (x >> 16); x = (x * 0x85EBCA6B) & M; x = x ^ (x >> 13); x = (x * 0xC2B2AE35) & M; x = x ^ (x >> 16)
+        return x
+    idx = (rowid << 16) | key
+    h = hash32(((idx & M) * 0x9E3779B1 + seed) & M)
+    h = hash32(h ^ (((idx >> 32) + salt * 0x7F4A7C15) & M))
+    thr = min(int(p * 4294967296.0), M)
+    return h >= thr
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,causal,masked", [(2, 3, 150, 200, False, True), (2, 2, 70, 70, True, False), (1, 4, 260, 130, False, False)])
+def test_attention_dropout_fwd_bwd(cuda_device, B, H, Sq, Sk, causal, masked):
+    """config.attention_dropout (MFULL:546): dropout on the probabilities AFTER the softmax.  The counter-based mask is
+    restated in Python, so forward and both backward kernels are checked against torch autograd with the SAME mask."""
+    from vacnic_b200 import kernels as K
+    dev = cuda_device
+    torch.manual_seed(Sq + Sk)
+    p, salt = 0.3, 77
+    rng = K.Rng(dev, seed=9)
+    q = (torch.randn(B, H, Sq, 64, device=dev) * 1.2).bfloat16()
+    k = (torch.randn(B, H, Sk, 64, device=dev) * 1.2).bfloat16()
+    v = (torch.randn(B, H, Sk, 64, device=dev) * 1.2).bfloat16()
+    key_mask = None
+    if masked:
+        key_mask = torch.ones(B, Sk, dtype=torch.uint8, device=dev)
+        key_mask[0, Sk - 37:] = 0
+        key_mask[1, 5] = 0
+    kl = K.mask_key_len(key_mask) if key_mask is not None else None
+    out, stats = K.attn_fwd(q, k, v, key_mask, kl, causal, p_drop=p, rng=rng, salt=salt)
+    out0, _ = K.attn_fwd(q, k, v, key_mask, kl, causal)
+    assert (out.float() - out0.float()).abs().mean().item() > 1e-2          # dropout really changes the result
+    seed = int(rng.state.item()) & 0xFFFFFFFF
+    rowid = ((torch.arange(B, device=dev)[:, None, None] * H + torch.arange(H, device=dev)[None, :, None]) * Sq
+             + torch.arange(Sq, device=dev)[None, None, :])[..., None].to(torch.int64)
+    keep = _keep_mask(seed, salt, rowid, torch.arange(Sk, device=dev, dtype=torch.int64)[None, None, None, :], p)
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    s = qf @ kf.transpose(-1, -2) * 0.125
+    neg = torch.finfo(torch.float32).min
+    if key_mask is not None:
+        s = s.masked_fill(key_mask[:, None, None, :] == 0, neg)
+    if causal:
+        s = s.masked_fill(torch.ones(Sq, Sk, dtype=torch.bool, device=dev).triu(1), neg)
+    pr = torch.softmax(s, -1) * keep / (1 - p)
+    ref = (pr @ vf).transpose(1, 2).reshape(B, Sq, H * 64)
+    err = (out.float() - ref).abs()
+    assert err.max().item() <= 4e-2 and err.mean().item() <= 3e-3, (err.max().item(), err.mean().item())
+    dO = torch.randn(B, Sq, H * 64, device=dev).bfloat16()
+    ref.backward(dO.float())
+    dq, dk, dv = (torch.full_like(t, float("nan")) for t in (q, k, v))
+    K.attn_bwd(dO, out, stats, q, k, v, dq, dk, dv, key_mask, kl, causal, p_drop=p, rng=rng, salt=salt)
+    for name, got, want in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        got = got.float()
+        assert torch.isfinite(got).all(), name
+        scale = want.abs().max().item() + 1e-6
+        e = (got - want).abs().max().item()
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0).item()
+        assert e <= 4e-2 * scale + 3e-3 and cos >= 0.998, (name, e, scale, cos)
+
+
+def test_activation_dropout_inplace_and_ffn_block(cuda_device):
+    """config.activation_dropout (MFULL:649, 660, 684, 740, 874): the in-place kernel keeps 1 - p of the elements scaled by
+    1 / (1 - p), the same key reproduces the same mask (backward), and the FFN block uses it in training mode only."""
+    from vacnic_b200 import kernels as K, spec
+    from vacnic_b200.modeling import VacnicBart
+    dev = cuda_device
+    rng = K.Rng(dev, seed=4)
+    x = torch.ones(1000, 1031, dtype=torch.bfloat16, device=dev)[:, :1024].contiguous()
+    a = K.dropout_inplace(x.clone(), 0.25, rng, 5)
+    b = K.dropout_inplace(x.clone(), 0.25, rng, 5)
+    c = K.dropout_inplace(x.clone(), 0.25, rng, 6)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs((a == 0).float().mean().item() - 0.25) < 0.01 and set(a.float().unique().tolist()) <= {0.0, float(torch.tensor(1 / 0.75).bfloat16())}
+    cfg = spec.VacnicConfig(d_model=768, heads=12, ffn=1024, enc_layers=1, dec_layers=1, prompt_size=4, max_pos=128)
+    outs = {}
+    for p_act in (0.0, 0.5):
+        m = VacnicBart(cfg, device=dev, p_drop=0.0, seed=1, p_act=p_act, p_attn=0.0)
+        from vacnic_b200 import synthetic
+        batch = synthetic.to_device(synthetic.make_batch(B=2, L=40, T=8, seed=1), dev)
+        face = batch["face_emb"]
+        kw = dict(input_ids=batch["article_ids"], attention_mask=(batch["article_ids"] != 1).long(), decoder_input_ids=batch["caption_ids"],
+                  image_features=batch["image_features"], face_features=face, face_mask=(face[:, :, -1] != 1).long(),
+                  name_ids=batch["names_art_ids"], name_mask=(batch["names_art_ids"] != 1).long())
+        m.eval()
+        with torch.no_grad():
+            outs[(p_act, "eval")] = m(**kw)["logits"].float().clone()
+        m.train()
+        out = m(ce_targets=batch["caption_ids"], **kw)
+        out["loss"].backward()
+        torch.cuda.synchronize()
+        assert torch.isfinite(m.store.grad).all()
+        outs[(p_act, "train")] = out["logits"].float().clone()
+    assert torch.equal(outs[(0.0, "eval")], outs[(0.5, "eval")])                     # inference never drops
+    assert (outs[(0.5, "train")] - outs[(0.0, "train")]).abs().mean().item() > 1e-3  # training with p_act > 0 does

@@ -33,6 +33,7 @@ SIGNATURES = {
     "vacnic_vit_embed_ln": [P, P, P, P, P, P, I64, I32, I32, F32, P],
     "vacnic_unpack_rows": [P, P, P, P, I32, I32, I32, P],
     "vacnic_rng_advance": [P, P],
+    "vacnic_dropout_inplace": [P, I64, F32, P, U32, P],
     "vacnic_clip_grad_scale": [P, I64, F32, F32, P, P, P, P],
     "vacnic_ce_fwd": [P, P, P, P, P, I64, I32, I64, I64, P],
     "vacnic_ce_bwd": [P, P, P, P, P, F32, P, I64, I32, I64, I64, P],

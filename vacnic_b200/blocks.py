@@ -22,9 +22,11 @@ from .store import Lin, ParamStore
 class Runtime:
     """Per-model execution context shared by all blocks."""
 
-    def __init__(self, store: ParamStore, p_drop: float = 0.0, seed: int = 0):
+    def __init__(self, store: ParamStore, p_drop: float = 0.0, seed: int = 0, p_attn: float = 0.0, p_act: float = 0.0):
         self.store = store
-        self.p_drop = p_drop
+        self.p_drop = p_drop      # config.dropout: embeddings, attention / FFN outputs (MFULL:705, 721, 742, 1249 ...)
+        self.p_attn = p_attn      # config.attention_dropout: on the probabilities, after the softmax (MFULL:546)
+        self.p_act = p_act        # config.activation_dropout: after the FFN activation (MFULL:649, 660, 684, 740, 874)
         self.training = False
         self.rng = K.Rng(store.device, seed)
         self._salt = 0
@@ -43,6 +45,14 @@ class Runtime:
     @property
     def drop(self) -> float:
         return self.p_drop if self.training else 0.0
+
+    @property
+    def attn_drop(self) -> float:
+        return self.p_attn if self.training else 0.0
+
+    @property
+    def act_drop(self) -> float:
+        return self.p_act if self.training else 0.0
 
 
 class LN:
@@ -115,22 +125,25 @@ class PackedMask:
         self.geo, self.k_tail = geo, int(k_tail)
 
 
-def sdpa_fwd(q4, k4, v4, key_mask, causal, want_stats=True):
-    """q4 [B,H,Sq,hd], k4/v4 [B,H,Sk,hd] (strided views).  Returns (O [B,Sq,H*hd], stats [B,H,Sq,2])."""
+def sdpa_fwd(q4, k4, v4, key_mask, causal, want_stats=True, drop=(0.0, None, 0)):
+    """q4 [B,H,Sq,hd], k4/v4 [B,H,Sk,hd] (strided views).  Returns (O [B,Sq,H*hd], stats [B,H,Sq,2]).
+    `drop` = (p, Rng, salt) of the attention dropout (p = 0: none)."""
+    dk = dict(p_drop=drop[0], rng=drop[1], salt=drop[2])
     if isinstance(key_mask, PackedMask):
-        return K.attn_fwd(q4, k4, v4, causal=causal, want_stats=want_stats, packed=key_mask.geo)
+        return K.attn_fwd(q4, k4, v4, causal=causal, want_stats=want_stats, packed=key_mask.geo, **dk)
     if key_mask is not None and tuple(key_mask.mask.shape) != (q4.shape[0], k4.shape[2]):
         raise ValueError(f"Attention mask should be of size {(q4.shape[0], 1, q4.shape[2], k4.shape[2])}, but is "
                          f"{(key_mask.mask.shape[0], 1, q4.shape[2], key_mask.mask.shape[1])}")  # MFULL:516-520
     return K.attn_fwd(q4, k4, v4, key_mask.mask if key_mask is not None else None,
-                      key_mask.len if key_mask is not None else None, causal, want_stats=want_stats)
+                      key_mask.len if key_mask is not None else None, causal, want_stats=want_stats, **dk)
 
 
-def sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4):
+def sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4, drop=(0.0, None, 0)):
+    dk = dict(p_drop=drop[0], rng=drop[1], salt=drop[2])
     if isinstance(key_mask, PackedMask):
-        return K.attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, causal=causal, packed=key_mask.geo)
+        return K.attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, causal=causal, packed=key_mask.geo, **dk)
     K.attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, key_mask.mask if key_mask is not None else None,
-               key_mask.len if key_mask is not None else None, causal)
+               key_mask.len if key_mask is not None else None, causal, **dk)
 
 
 def _heads(t2d: torch.Tensor, B: int, S: int, H: int, col0: int, hd: int) -> torch.Tensor:
@@ -172,7 +185,8 @@ class AttnBlockFn(torch.autograd.Function):
             if packed:
                 Bk, Sk = 1, Bk * Sk
             k4, v4 = _heads(kvp, Bk, Sk, H, 0, hd), _heads(kvp, Bk, Sk, H, d, hd)
-        O, stats = sdpa_fwd(q4, k4, v4, key_mask, causal, want_stats=not rt.store.frozen)
+        adrop = (rt.attn_drop, rt.rng, ln.salt + 4096)  # attention dropout on the probabilities (MFULL:546)
+        O, stats = sdpa_fwd(q4, k4, v4, key_mask, causal, want_stats=not rt.store.frozen, drop=adrop)
         a = K.gemm(O.view(B * Sq, d), lin_o.w16, bias=lin_o.b32)
         p = rt.drop if use_dropout else 0.0
         y32 = None
@@ -186,6 +200,7 @@ class AttnBlockFn(torch.autograd.Function):
         ctx.rt, ctx.lins, ctx.ln, ctx.H, ctx.p = rt, (lin_qkv, lin_q, lin_kv, lin_o), ln, H, p
         ctx.saved = (x2, kv_src, qkv, kvp, stats, O, a, mean, rstd, q4, k4, v4)
         ctx.mask = (key_mask, causal)
+        ctx.adrop = adrop
         hoisted = kv_pre is not None and dkv_all is not None
         ctx.dkv_pre = dkv_all.view(Bk * Sk, -1)[:, kv_col0:kv_col0 + 2 * d] if hoisted else None
         ctx.dkv_all = dkv_all if (hoisted and return_dkv_all) else None
@@ -213,7 +228,7 @@ class AttnBlockFn(torch.autograd.Function):
             if k_tail:  # key rows no sequence owns: the kernels never write their dK / dV (their dQ is written afterwards)
                 dqkv[-k_tail:].zero_()
             dk4, dv4, dq4 = (_heads(dqkv, Bq, Rq, H, c * d, hd) for c in range(3))
-            sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4)
+            sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4, drop=ctx.adrop)
             _wgrad(rt, lin_qkv, dqkv, x2, bias_from=dqkv)
             K.gemm(dqkv, lin_qkv.w16, out=dsum, b_mn=True, accumulate=True)  # dx = dsum + dqkv W
         else:
@@ -226,7 +241,7 @@ class AttnBlockFn(torch.autograd.Function):
                 if k_tail:
                     dkvp[-k_tail:].zero_()
             dk4, dv4 = _heads(dkvp, Bk, Sk, H, 0, hd), _heads(dkvp, Bk, Sk, H, d, hd)
-            sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4)
+            sdpa_bwd(dO, O, stats, q4, k4, v4, key_mask, causal, dq4, dk4, dv4, drop=ctx.adrop)
             _wgrad(rt, lin_q, dq, x2, bias_from=dq)
             K.gemm(dq, lin_q.w16, out=dsum, b_mn=True, accumulate=True)
             if ctx.dkv_pre is None:
@@ -253,6 +268,9 @@ class MlpBlockFn(torch.autograd.Function):
         rows = x2.shape[0]
         aux = torch.empty(rows, lin1.out_f, dtype=torch.bfloat16, device=x.device) if act == K.ACT_GELU else None
         h = K.gemm(x2, lin1.w16, bias=lin1.b32, act=act, aux_out=aux)
+        p_act = rt.act_drop if ln is not None else 0.0  # activation dropout of the FFN blocks (not of the ClipCap prefix MLP)
+        if p_act > 0.0:
+            K.dropout_inplace(h, p_act, rt.rng, ln.salt + 8192)
         z = K.gemm(h, lin2.w16, bias=lin2.b32)
         y32 = None
         if ln is not None:
@@ -269,7 +287,7 @@ class MlpBlockFn(torch.autograd.Function):
         else:
             ctx.lnstate = None
             out = z.view(shp[:-1] + (lin2.out_f,))
-        ctx.rt, ctx.lin1, ctx.lin2, ctx.act, ctx.ln = rt, lin1, lin2, act, ln
+        ctx.rt, ctx.lin1, ctx.lin2, ctx.act, ctx.ln, ctx.p_act = rt, lin1, lin2, act, ln, p_act
         ctx.saved = (x2, aux, h)
         ctx.in_shape = shp
         return out, y32
@@ -291,6 +309,8 @@ class MlpBlockFn(torch.autograd.Function):
         _wgrad(rt, lin2, dz, h)
         # dh * act'(.) fused in the data-gradient GEMM epilogue (GELU' from the pre-activation, tanh' from the output)
         dpre = K.gemm(dz, lin2.w16, b_mn=True, dact=act, aux_in=aux if act == K.ACT_GELU else h)
+        if ctx.p_act > 0.0:  # the mask of the forward pass (elementwise, commutes with act')
+            K.dropout_inplace(dpre, ctx.p_act, rt.rng, ln.salt + 8192)
         _wgrad(rt, lin1, dpre, x2, bias_from=dpre)
         if dsum is not None:
             K.gemm(dpre, lin1.w16, out=dsum, b_mn=True, accumulate=True)
@@ -381,13 +401,16 @@ class NerMapFn(torch.autograd.Function):
         x_rows = ner.reshape(B * d, E)
         z1 = torch.empty(B * d, up.out_f, dtype=torch.bfloat16, device=ner.device)
         y1 = K.gemm(x_rows, up.w16, bias=up.b32, act=K.ACT_GELU, aux_out=z1)
+        p_act = rt.act_drop  # MFULL:684
+        if p_act > 0.0:
+            K.dropout_inplace(y1, p_act, rt.rng, ln.salt + 8192)
         z2 = K.gemm(y1, down.w16, bias=down.b32)
         z2r = z2.view(B * G, d)
         # nn.functional.dropout(hidden_states_ner_prefix, p=self.dropout, training=self.training) sits between
         # ner_map_down and the reshape + ner_map_layer_norm (MFULL:685-687); elementwise, so it commutes with the reshape
         p = rt.drop
         y, mean, rstd = K.add_layernorm_fwd(z2r, None, ln.g, ln.b, p_drop=p, rng=rt.rng, salt=ln.salt)
-        ctx.rt, ctx.up, ctx.down, ctx.ln, ctx.p = rt, up, down, ln, p
+        ctx.rt, ctx.up, ctx.down, ctx.ln, ctx.p, ctx.p_act = rt, up, down, ln, p, p_act
         ctx.saved = (x_rows, z1, y1, z2r, mean, rstd)
         ctx.dims = (B, E, d, G)
         return y.view(B, G, d)
@@ -404,6 +427,8 @@ class NerMapFn(torch.autograd.Function):
         dz2p = K.pad_rows(dz2.view(R, G), Gp)[:, :G]  # 16-byte row pitch for TMA
         # dz1 = (dz2 W_down) * gelu'(z1) ; dx = dz1 W_up
         dz1 = K.gemm(dz2p, down.w16, b_mn=True, dact=K.ACT_GELU, aux_in=z1)
+        if ctx.p_act > 0.0:
+            K.dropout_inplace(dz1, ctx.p_act, rt.rng, ln.salt + 8192)
         dx = K.gemm(dz1, up.w16, b_mn=True)
         # weight gradients: [S, R/S, .]^T [S, R/S, .] partial products, then a fixed-order sum over the S slabs
         S = NerMapFn.SPLIT if R % NerMapFn.SPLIT == 0 and (R // NerMapFn.SPLIT) % 8 == 0 else 1

@@ -48,7 +48,15 @@ struct AttnArgs {
   // then only upper bounds (grid sizing) and stats is [H][total_q][2]
   const int32_t* q_start; const int32_t* q_len; const int32_t* k_start; const int32_t* k_len;
   int total_q;
+  // attention dropout (config.attention_dropout, MFULL:546): probabilities are dropped AFTER the softmax normalisation;
+  // counter-based mask keyed by (*rng, salt, (sequence, head, query row), key) -- the backward kernels regenerate it
+  float p_drop; const unsigned long long* rng; uint32_t salt;
 };
+
+// keep decision of attention dropout for (query row id = geo.sbase + row, key index inside the sequence)
+__device__ __forceinline__ bool keep_attn(uint32_t seed, uint32_t salt, long long rowid, int key, uint32_t thr) {
+  return keep_elem(seed, salt, (static_cast<uint64_t>(rowid) << 16) | static_cast<uint32_t>(key), thr);
+}
 
 // per-CTA view of "its" sequence: row counts, first rows in the (possibly packed) buffers, batch coordinate for TMA
 struct SeqGeo {
@@ -92,7 +100,7 @@ __device__ __forceinline__ float ex2f(float x) {
 
 // GENERAL = false: no padding-mask bytes and no causal mask (packed rows, prefix / CLIP attention): only the sequence end can
 // cut a key block.  Keeping the byte-load path out of this instantiation is what keeps it free of local-memory spills.
-template <bool GENERAL>
+template <bool GENERAL, bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
@@ -258,6 +266,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t atom = smem_u32(sP) + half * kTile + r * 128;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     const uint32_t t_o = tmem_o + (static_cast<uint32_t>(quad * 32) << 16) + half * 32;  // this thread's 32 O columns
+    const uint32_t dseed = DROP ? static_cast<uint32_t>(*a.rng) : 0u, dthr = drop_thresh(a.p_drop);
+    const float dinv = DROP ? 1.f / (1.f - a.p_drop) : 1.f;
     for (int j = 0; j < nkb; ++j, ++it) {
       mbar_wait(&sh->s_full, it & 1u);
       tc_fence_after();
@@ -322,10 +332,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int c = 0; c < 32; c += 2) {
         const float a0 = ex2f(fmaf(__uint_as_float(x0[c]), kk, -m)), a1 = ex2f(fmaf(__uint_as_float(x0[c + 1]), kk, -m));
         const float b0 = ex2f(fmaf(__uint_as_float(x1[c]), kk, -m)), b1 = ex2f(fmaf(__uint_as_float(x1[c + 1]), kk, -m));
-        l0 += a0 + a1;
+        l0 += a0 + a1;  // the row sum normalises the UNdropped probabilities (dropout follows the softmax, MFULL:546)
         l1 += b0 + b1;
-        pk[c >> 1] = pack_bf16x2(a0, a1);
-        pk[16 + (c >> 1)] = pack_bf16x2(b0, b1);
+        if constexpr (DROP) {
+          const long long rid = geo.sbase + row;
+          pk[c >> 1] = pack_bf16x2(keep_attn(dseed, a.salt, rid, kb + c, dthr) ? a0 * dinv : 0.f,
+                                   keep_attn(dseed, a.salt, rid, kb + c + 1, dthr) ? a1 * dinv : 0.f);
+          pk[16 + (c >> 1)] = pack_bf16x2(keep_attn(dseed, a.salt, rid, kb + 32 + c, dthr) ? b0 * dinv : 0.f,
+                                          keep_attn(dseed, a.salt, rid, kb + 32 + c + 1, dthr) ? b1 * dinv : 0.f);
+        } else {
+          pk[c >> 1] = pack_bf16x2(a0, a1);
+          pk[16 + (c >> 1)] = pack_bf16x2(b0, b1);
+        }
       }
       l += l0 + l1;
       if (j > 0) {
@@ -415,6 +433,7 @@ struct AttnBwdArgs {
   __nv_bfloat16* dv; long long lddv, dv_sh, dv_sb;
   const int32_t* q_start; const int32_t* q_len; const int32_t* k_start; const int32_t* k_len;  // packed mode, see AttnArgs
   int total_q;
+  float p_drop; const unsigned long long* rng; uint32_t salt;  // attention dropout, see AttnArgs
 };
 
 struct BwdSmem {
@@ -480,6 +499,7 @@ __device__ __forceinline__ void bwd_init(BwdSmem* sh, int warp, int lane) {
   tc_fence_after();
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -624,6 +644,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (half == 0) a.delta[si] = delta;
     }
     const uint32_t ds_row = smem_u32(sDS) + r * 128;
+    const uint32_t dseed = DROP ? static_cast<uint32_t>(*a.rng) : 0u, dthr = drop_thresh(a.p_drop);
+    const float dinv = DROP ? 1.f / (1.f - a.p_drop) : 1.f;
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(&sh->sdp_full, j & 1u);
       tc_fence_after();
@@ -648,7 +670,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (key >= geo.Sk) t = -INFINITY;
             else if ((mk != nullptr && mk[key] == 0) || (a.causal && key > row)) t = -FLT_MAX - m;
           }
-          ds[e] = ex2f(t) * (__uint_as_float(xp[c]) - delta) * coef;
+          float dp = __uint_as_float(xp[c]);
+          if constexpr (DROP) dp = keep_attn(dseed, a.salt, geo.sbase + row, kb0 + c, dthr) ? dp * dinv : 0.f;
+          ds[e] = ex2f(t) * (dp - delta) * coef;
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) dsp[q * 4 + e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
@@ -677,6 +701,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -788,6 +813,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     const uint32_t pt_row = smem_u32(sPT) + r * 128, dst_row = smem_u32(sDST) + r * 128;
     const long long sbase = geo.sbase;
+    const uint32_t dseed = DROP ? static_cast<uint32_t>(*a.rng) : 0u, dthr = drop_thresh(a.p_drop);
+    const float dinv = DROP ? 1.f / (1.f - a.p_drop) : 1.f;
     // row statistics of a 64-query block (threads 0..63): {reference max, 1/row sum, delta, scale/row sum}
     auto load_stat = [&](int i) -> float4 {
       const int qrow = i * 64 + tid;
@@ -820,7 +847,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(&sh->s_empty);
       uint32_t ppk[16], dsk[16];
-      if (warp_plain) {
+      if (warp_plain && !DROP) {
         // no key of this warp is masked and there is no causal mask: no per-element decisions (the common case)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -851,8 +878,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (key_oob) t = -INFINITY;
             else if (key_masked || (a.causal && key > qb0 + c)) t = -FLT_MAX;
             const float p = ex2f(t - st.x) * st.y;
-            pp[e] = p;
-            ds[e] = p * (__uint_as_float(xp[c]) - st.z) * a.scale;
+            float dp = __uint_as_float(xp[c]);
+            if constexpr (DROP) {
+              const bool kp = keep_attn(dseed, a.salt, sbase + qb0 + c, key, dthr);
+              pp[e] = kp ? p * dinv : 0.f;   // P^T as the forward pass applied it to V
+              dp = kp ? dp * dinv : 0.f;
+            } else {
+              pp[e] = p;
+            }
+            ds[e] = p * (dp - st.z) * a.scale;
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -926,19 +960,30 @@ extern "C" int vacnic_attn_fwd(const vacnic_attn_desc* d, void* stream) {
   a.out = static_cast<__nv_bfloat16*>(d->out); a.ldo = d->ldo; a.o_sb = d->o_sb;
   a.stats = d->stats;
   a.q_start = d->q_start; a.q_len = d->q_len; a.k_start = d->k_start; a.k_len = d->k_len; a.total_q = d->total_q;
+  VB_REQUIRE(d->p_drop >= 0.f && d->p_drop < 1.f && (d->p_drop == 0.f || d->rng_state), "attn_fwd: bad dropout args");
+  a.p_drop = d->p_drop; a.rng = reinterpret_cast<const unsigned long long*>(d->rng_state); a.salt = d->salt;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+      e = cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
     if (e != cudaSuccess) return fail(VACNIC_ECUDA, "attn_fwd: cudaFuncSetAttribute(smem=%d): %s", kAttnSmemBytes, cudaGetErrorString(e));
     configured = true;
   }
   const dim3 grid((d->Sq + kAQ - 1) / kAQ, d->H, d->B);
-  if (d->key_mask != nullptr || d->causal)
-    launch_pdl(attn_fwd_kernel<true>, grid, dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, a);
-  else
-    launch_pdl(attn_fwd_kernel<false>, grid, dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, a);
+  const bool general = d->key_mask != nullptr || d->causal;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a.p_drop > 0.f) {
+    if (general) launch_pdl(attn_fwd_kernel<true, true>, grid, dim3(kAttnThreads), kAttnSmemBytes, st, tq, tk, tv, a);
+    else launch_pdl(attn_fwd_kernel<false, true>, grid, dim3(kAttnThreads), kAttnSmemBytes, st, tq, tk, tv, a);
+  } else {
+    if (general) launch_pdl(attn_fwd_kernel<true, false>, grid, dim3(kAttnThreads), kAttnSmemBytes, st, tq, tk, tv, a);
+    else launch_pdl(attn_fwd_kernel<false, false>, grid, dim3(kAttnThreads), kAttnSmemBytes, st, tq, tk, tv, a);
+  }
   count_launch();
   return check_last("attn_fwd launch");
 }
@@ -982,22 +1027,33 @@ extern "C" int vacnic_attn_bwd(const vacnic_attn_desc* d, void* stream) {
   a.dk = static_cast<__nv_bfloat16*>(d->dk); a.lddk = d->lddk; a.dk_sh = d->dk_sh; a.dk_sb = d->dk_sb;
   a.dv = static_cast<__nv_bfloat16*>(d->dv); a.lddv = d->lddv; a.dv_sh = d->dv_sh; a.dv_sb = d->dv_sb;
   a.q_start = d->q_start; a.q_len = d->q_len; a.k_start = d->k_start; a.k_len = d->k_len; a.total_q = d->total_q;
+  VB_REQUIRE(d->p_drop >= 0.f && d->p_drop < 1.f && (d->p_drop == 0.f || d->rng_state), "attn_bwd: bad dropout args");
+  a.p_drop = d->p_drop; a.rng = reinterpret_cast<const unsigned long long*>(d->rng_state); a.salt = d->salt;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdDqSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdDqSmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdDkvSmemBytes);
+      e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdDkvSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdDqSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdDkvSmemBytes);
     if (e != cudaSuccess) return fail(VACNIC_ECUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  launch_pdl(attn_bwd_dq_kernel, dim3((d->Sq + kAQ - 1) / kAQ, d->H, d->B), dim3(kAttnThreads), kBwdDqSmemBytes, s, q128, k64,
-             v64, do128, o128, a);
+  const dim3 gq((d->Sq + kAQ - 1) / kAQ, d->H, d->B), gk((d->Sk + kAK - 1) / kAK, d->H, d->B);
+  if (a.p_drop > 0.f)
+    launch_pdl(attn_bwd_dq_kernel<true>, gq, dim3(kAttnThreads), kBwdDqSmemBytes, s, q128, k64, v64, do128, o128, a);
+  else
+    launch_pdl(attn_bwd_dq_kernel<false>, gq, dim3(kAttnThreads), kBwdDqSmemBytes, s, q128, k64, v64, do128, o128, a);
   count_launch();
   rc = check_last("attn_bwd dq launch");
   if (rc != VACNIC_OK) return rc;
-  launch_pdl(attn_bwd_dkv_kernel, dim3((d->Sk + kAK - 1) / kAK, d->H, d->B), dim3(kAttnThreads), kBwdDkvSmemBytes, s, q64, k128,
-             v128, do64, a);
+  if (a.p_drop > 0.f)
+    launch_pdl(attn_bwd_dkv_kernel<true>, gk, dim3(kAttnThreads), kBwdDkvSmemBytes, s, q64, k128, v128, do64, a);
+  else
+    launch_pdl(attn_bwd_dkv_kernel<false>, gk, dim3(kAttnThreads), kBwdDkvSmemBytes, s, q64, k128, v128, do64, a);
   count_launch();
   return check_last("attn_bwd dkv launch");
 }

@@ -171,6 +171,33 @@ unpack_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restr
   for (int v = lane; v < d / 8; v += 32) dp[v] = valid ? __ldg(sp + v) : make_uint4(0, 0, 0, 0);
 }
 
+
+// x = dropout(x) in place (bf16): activation dropout after the GELU of an FFN (config.activation_dropout: MFULL:649, 660, 684,
+// 740, 874) and, with the same (seed, salt), the matching mask on the gradient in the backward pass.
+__global__ void __launch_bounds__(256)
+dropout_inplace_kernel(__nv_bfloat16* __restrict__ x, long long n, float p, const unsigned long long* __restrict__ rng, uint32_t salt) {
+  pdl_sync();
+  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i >= n) return;
+  const uint32_t seed = static_cast<uint32_t>(*rng), thr = drop_thresh(p);
+  const float inv_keep = 1.f / (1.f - p);
+  if (i + 8 <= n) {
+    uint4 u = *reinterpret_cast<uint4*>(x + i);
+    uint32_t* w = &u.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = unpack_bf16x2(w[k]);
+      f.x = keep_elem(seed, salt, static_cast<uint64_t>(i + 2 * k), thr) ? f.x * inv_keep : 0.f;
+      f.y = keep_elem(seed, salt, static_cast<uint64_t>(i + 2 * k + 1), thr) ? f.y * inv_keep : 0.f;
+      w[k] = pack_bf16x2(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(x + i) = u;
+  } else {
+    for (long long k = i; k < n; ++k)
+      x[k] = keep_elem(seed, salt, static_cast<uint64_t>(k), thr) ? __float2bfloat16_rn(__bfloat162float(x[k]) * inv_keep) : __float2bfloat16_rn(0.f);
+  }
+}
+
 // out = a + b (+ c) on bf16, fp32 math; gradient fan-in of the residual / state streams
 __global__ void __launch_bounds__(256)
 add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
@@ -382,6 +409,18 @@ extern "C" int vacnic_unpack_rows(const void* src, const int32_t* start, const i
              static_cast<const __nv_bfloat16*>(src), start, len, static_cast<__nv_bfloat16*>(dst), rows, L, d);
   count_launch();
   return check_last("unpack_rows");
+}
+
+
+extern "C" int vacnic_dropout_inplace(void* x, int64_t n, float p_drop, const uint64_t* rng_state, uint32_t salt, void* stream) {
+  VB_REQUIRE(x && rng_state, "dropout_inplace: null pointer");
+  VB_REQUIRE(p_drop > 0.f && p_drop < 1.f, "dropout_inplace: p must be in (0, 1)");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "dropout_inplace: misaligned");
+  if (n <= 0) return VACNIC_OK;
+  launch_pdl(dropout_inplace_kernel, dim3(static_cast<unsigned>((n + 2047) / 2048)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             static_cast<__nv_bfloat16*>(x), static_cast<long long>(n), p_drop, reinterpret_cast<const unsigned long long*>(rng_state), salt);
+  count_launch();
+  return check_last("dropout_inplace");
 }
 
 extern "C" int vacnic_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream) {

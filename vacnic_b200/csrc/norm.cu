@@ -12,21 +12,6 @@ namespace vb {
 
 constexpr int kWarpsPerBlock = 8;
 
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {
-  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
-  return x;
-}
-// Bernoulli keep decision for element `idx` of call site `salt` in step `seed`.
-__device__ __forceinline__ bool keep_elem(uint32_t seed, uint32_t salt, uint64_t idx, uint32_t thresh) {
-  uint32_t h = hash32(static_cast<uint32_t>(idx) * 0x9E3779B1u + seed);
-  h = hash32(h ^ (static_cast<uint32_t>(idx >> 32) + salt * 0x7F4A7C15u));
-  return h >= thresh;
-}
-__host__ __device__ inline uint32_t drop_thresh(float p) {
-  double t = static_cast<double>(p) * 4294967296.0;
-  return t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
-}
-
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   float2 t;
   t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;

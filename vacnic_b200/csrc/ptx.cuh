@@ -264,6 +264,22 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 
 
+// Counter-based dropout (shared by LayerNorm, activation and attention dropout): Bernoulli keep decision for element `idx` of
+// call site `salt` in step `seed` -- the backward pass regenerates the mask from the same triple, nothing is stored.
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool keep_elem(uint32_t seed, uint32_t salt, uint64_t idx, uint32_t thresh) {
+  uint32_t h = hash32(static_cast<uint32_t>(idx) * 0x9E3779B1u + seed);
+  h = hash32(h ^ (static_cast<uint32_t>(idx >> 32) + salt * 0x7F4A7C15u));
+  return h >= thresh;
+}
+__host__ __device__ inline uint32_t drop_thresh(float p) {
+  double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+}
+
 // One AdamW element update (torch.optim.AdamW, TRAIN:95-101) with every rounding pinned by intrinsics, so that the flat
 // kernel (elementwise.cu) and the rank-sharded peer-memory kernel (dp.cu) produce bit-identical weights from identical
 // gradients whatever the compiler's FMA contraction does (a last-bit difference is enough to flip the sign-like Adam

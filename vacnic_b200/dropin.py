@@ -116,7 +116,9 @@ class _DropInBase(VacnicBart):
             device = torch.device("cuda", torch.cuda.current_device())
         self._ctor = dict(prompt_size=prompt_size, max_ner_type_len=max_ner_type_len, max_ner_type_len_gt=max_ner_type_len_gt,
                           only_image=only_image, dim_common=dim_common)
-        super().__init__(cfg, device=device, p_drop=float(_cfg_get(config, "dropout", 0.1)), seed=seed)
+        super().__init__(cfg, device=device, p_drop=float(_cfg_get(config, "dropout", 0.1)), seed=seed,
+                         p_attn=float(_cfg_get(config, "attention_dropout", 0.0) or 0.0),
+                         p_act=float(_cfg_get(config, "activation_dropout", 0.0) or 0.0))
         object.__setattr__(self, "config", config)
         self.clip_model = clip_model
         if freeze_clip and clip_model is not None:

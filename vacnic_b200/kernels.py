@@ -170,6 +170,14 @@ class Rng:
         check(lib().vacnic_rng_advance(self.state.data_ptr(), stream_ptr()), "vacnic_rng_advance")
 
 
+def dropout_inplace(x, p_drop, rng, salt):
+    """x = dropout(x) in place (contiguous bf16); the same (rng, salt) on the gradient applies the same mask."""
+    _c(x, torch.bfloat16, "dropout operand")
+    check(lib().vacnic_dropout_inplace(ptr(x), x.numel(), float(p_drop), rng.state.data_ptr(), int(salt), stream_ptr()),
+          "vacnic_dropout_inplace")
+    return x
+
+
 def add_layernorm_fwd(x, res, gamma, beta, out=None, rows_per_group=0, group_stride=0, p_drop=0.0, rng=None, salt=0,
                       want_stats=True, res32=None, want_y32=False, y32_out=None, sum32_out=None):
     """y = LN(res + dropout(x)); returns (y, mean, rstd).  `out` may be a [rows, d] view whose groups of
@@ -519,7 +527,7 @@ class Packed:
         self.n_seq, self.max_q, self.max_k = q_start.numel(), int(max_q), int(max_k)
 
 
-def _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed: "Packed | None" = None):
+def _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed: "Packed | None" = None, p_drop: float = 0.0, rng=None, salt: int = 0):
     B, H, Sq, hd = q4.shape
     Sk = k4.shape[2]
     for t in (q4, k4, v4):
@@ -541,15 +549,19 @@ def _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed: "Packed | None" = 
         d.B, d.Sq, d.Sk = packed.n_seq, packed.max_q, packed.max_k
         d.total_q, d.total_k = Sq, Sk
         d.q_start, d.q_len, d.k_start, d.k_len = (ptr(t) for t in (packed.q_start, packed.q_len, packed.k_start, packed.k_len))
+    if p_drop > 0.0:  # attention dropout (config.attention_dropout, MFULL:546); the same key rebuilds the mask in attn_bwd
+        if rng is None:
+            raise ValueError("attention dropout needs the model's Rng")
+        d.p_drop, d.rng_state, d.salt = float(p_drop), rng.state.data_ptr(), int(salt)
     return d
 
 
-def attn_fwd(q4, k4, v4, key_mask=None, key_len=None, causal=False, want_stats=True, packed=None):
+def attn_fwd(q4, k4, v4, key_mask=None, key_len=None, causal=False, want_stats=True, packed=None, p_drop=0.0, rng=None, salt=0):
     """Fused softmax(q k^T * hd^-0.5 + mask) v.  q4 [B,H,Sq,64], k4/v4 [B,H,Sk,64] strided views.
     Returns (O bf16 [B,Sq,H*64], stats fp32 [B,H,Sq,2] or None).  `packed` (kernels.Packed): varlen mode -- q4/k4/v4 are
     [1,H,rows,64] views of packed row buffers, O is [1,total_q,H*64], stats [1,H,total_q,2]."""
     B, H, Sq, hd = q4.shape
-    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed)
+    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed, p_drop, rng, salt)
     out = torch.empty(B, Sq, H * hd, dtype=torch.bfloat16, device=q4.device)
     stats = torch.empty(B, H, Sq, 2, dtype=torch.float32, device=q4.device) if want_stats else None
     d.out, d.ldo, d.o_sb, d.stats = out.data_ptr(), out.stride(1), out.stride(0), ptr(stats)
@@ -557,11 +569,12 @@ def attn_fwd(q4, k4, v4, key_mask=None, key_len=None, causal=False, want_stats=T
     return out, stats
 
 
-def attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, key_mask=None, key_len=None, causal=False, packed=None):
+def attn_bwd(dO, O, stats, q4, k4, v4, dq4, dk4, dv4, key_mask=None, key_len=None, causal=False, packed=None, p_drop=0.0,
+             rng=None, salt=0):
     """Gradients of attn_fwd.  dO / O bf16 [B,Sq,H*64] (row stride = stride(1), innermost 1); dq4/dk4/dv4 are
     [B,H,S,64] strided views that receive the results (dq, dk include the hd^-0.5 factor)."""
     B, H, Sq, hd = q4.shape
-    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed)
+    d = _attn_desc(q4, k4, v4, key_mask, key_len, causal, packed, p_drop, rng, salt)
     for t in (dO, O):
         if t.dtype != torch.bfloat16 or t.stride(2) != 1 or tuple(t.shape) != (B, Sq, H * hd):
             raise ValueError("attn_bwd: dO / O must be bf16 [B,Sq,H*hd] with innermost stride 1")

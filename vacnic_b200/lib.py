@@ -52,6 +52,7 @@ class AttnDesc(C.Structure):
         ("delta", C.c_void_p),
         ("q_start", C.c_void_p), ("q_len", C.c_void_p), ("k_start", C.c_void_p), ("k_len", C.c_void_p),
         ("total_q", C.c_int32), ("total_k", C.c_int32),
+        ("p_drop", C.c_float), ("rng_state", C.c_void_p), ("salt", C.c_uint32),
     ]
 
 

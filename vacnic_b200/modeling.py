@@ -382,7 +382,7 @@ class VacnicBart(nn.Module):
     classes in src/models/ add `from_pretrained` / `generate` on top of it."""
 
     def __init__(self, cfg: VacnicConfig, device="cuda", p_drop: float = 0.1, seed: int = 0, tie_lm_head: bool = False,
-                 frozen: bool = False, symmetric: Optional[bool] = None):
+                 frozen: bool = False, symmetric: Optional[bool] = None, p_attn: float = 0.0, p_act: float = 0.0):
         super().__init__()
         self.cfg = cfg
         self.model = BartModel(cfg)
@@ -404,7 +404,7 @@ class VacnicBart(nn.Module):
             symmetric = (not frozen and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
                          and dist.get_backend() == "nccl" and os.environ.get("VACNIC_DP_P2P", "1") != "0")
         self.store = ParamStore(self, device, first=first, frozen=frozen, symmetric=symmetric)
-        self.rt = Runtime(self.store, p_drop=p_drop, seed=seed)
+        self.rt = Runtime(self.store, p_drop=p_drop, seed=seed, p_attn=p_attn, p_act=p_act)
         self.model.encoder.bind(self.rt)
         self.model.decoder.bind(self.rt)
         self.lin_lm = self.store.lin([self.lm_head.weight], None)
@@ -462,12 +462,14 @@ class VacnicBart(nn.Module):
                 past_key_values=None, inputs_embeds=None, decoder_inputs_embeds=None, labels=None, use_cache=None,
                 output_attentions=None, output_hidden_states=None, return_dict=None, image_features=None,
                 face_features=None, face_mask=None, name_ids=None, name_mask=None, add_ner_ffn=True, ce_targets=None,
-                article_pack=None):
+                article_pack=None, need_logits: bool = True):
         """Signature of BartForMultiModalGeneration.forward (MFULL:1929-1953; MVIS:1783-1802 lacks the four
         face/name arguments).  `ce_targets` (extension): fuse the script's CrossEntropyLoss(ignore_index=pad)
         (TRAIN:287) into the LM head; the result is returned under "loss".  `article_pack` (extension,
         varlen.ArticlePack): the article arrives as packed rows instead of padded `input_ids` + `attention_mask`;
-        `encoder_last_hidden_state` is then the packed memory (varlen.unpack_rows restores the padded layout)."""
+        `encoder_last_hidden_state` is then the packed memory (varlen.unpack_rows restores the padded layout).
+        `need_logits=False` (extension): stop after the decoder -- the CoLaM guide (TRAIN:293) is only read for
+        `decoder_hidden_states[-1]`, its LM head (a 1024 x 50267 x 1024 GEMM + 206 MB of fp32 logits) is never looked at."""
         cfg = self.cfg
         for unsupported, name in ((head_mask, "head_mask"), (decoder_head_mask, "decoder_head_mask"),
                                   (cross_attn_head_mask, "cross_attn_head_mask"), (inputs_embeds, "inputs_embeds"),
@@ -508,6 +510,10 @@ class VacnicBart(nn.Module):
         dec = self.model.decoder(input_ids=decoder_input_ids, attention_mask=decoder_attention_mask,
                                  encoder_hidden_states=enc_h, encoder_attention_mask=attention_mask, pack=article_pack)
         x = dec["last_hidden_state"]
+        if not need_logits:
+            eo = encoder_outputs
+            return VacnicOutput(loss=None, logits=None, past_key_values=None, decoder_hidden_states=dec["hidden_states"],
+                                decoder_attentions=None, cross_attentions=None, encoder_last_hidden_state=enc_h)
         x_lm, x_out = Bk.fanout(x, 2)
         loss = None
         flb_lin = Bk.Lin(self.lin_lm.w16, self.final_logits_bias.view(-1), self.lin_lm.gw, None, self.lin_lm.key)

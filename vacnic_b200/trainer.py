@@ -170,7 +170,8 @@ class TrainStep:
         losses = {"txt": out["loss"]}
         if guide is not None:
             with torch.no_grad():
-                gout = guide(input_ids=src, attention_mask=b["src_mask"], decoder_input_ids=dec_in, article_pack=pack)
+                gout = guide(input_ids=src, attention_mask=b["src_mask"], decoder_input_ids=dec_in, article_pack=pack,
+                             need_logits=False)  # only decoder_hidden_states[-1] is read (TRAIN:293-296)
             margin = Bk.ColamFn.apply(out["decoder_hidden_states"][-1], gout["decoder_hidden_states"][-1], tgt, self.margin,
                                       cfg.pad_token_id)
             heads.append(margin); grads.append(self._g_margin)
