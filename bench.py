@@ -623,15 +623,15 @@ def train_roofline(model, guide, ts, devb, pk, step_tflops, ms_step, small, step
         tf = 2.0 * M_ * N_ * K_ / 1e12 / (us / 1e6)
         rep = {"shape": "fc1+bias+GELU M=16384 N=4096 K=1024 (bf16 out + bf16 pre-activation)", "us": us, "achieved": tf,
                "frac": tf / pk["bf16_tflops"], "peak": pk["bf16_tflops"], "peak_kind": "burst (kernel timed alone)",
-               "algorithmic_bytes": 2.0 * (M_ * K_ + N_ * K_ + 2 * M_ * N_), "traffic": 160.4e6}
+               "algorithmic_bytes": 2.0 * (M_ * K_ + N_ * K_ + 2 * M_ * N_), "traffic": 319.6e6}
         del sets
     return {"bound": "tensor", "kernel": "gemm2_sm100_kernel (CTA-pair tcgen05.mma.cta_group::2 / TMEM / TMA batched bf16 GEMM)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the representative launch below), from the committed
             # ncu --set full capture -- a profile figure per launch, not measured in this run
-            "traffic": 160.4e6 if not small else None,
-            "traffic_source": "profiles/r1_ncu_gemm2_fc1_gelu.md: fc1+GELU 16384x4096x1024, 55.1 MB read + 105.3 MB written "
-                              "(176 MB algorithmic operand+result bytes; the rest stays in L2)" if not small else None,
+            "traffic": 319.6e6 if not small else None,
+            "traffic_source": "profiles/r2_ncu_targets.md: fc1+bias+GELU 16384x4096x1024, 89.9 MB read + 229.7 MB written "
+                              "(310 MB algorithmic: A + W read, bf16 output + bf16 pre-activation written)" if not small else None,
             "representative_launch": rep, "peak_source": pk["_source"] + " sustained",
             "launches_per_step": len(big), "kernel_ms_per_step": gms, "kernel_tflop_per_step": gf / 1e12,
             "kernel_share_of_step": gms / ms_step,
