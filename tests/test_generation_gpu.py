@@ -209,7 +209,7 @@ def test_decode_self_attention_with_ancestry_matches_torch(cuda_device):
 
 
 @pytest.mark.parametrize("nb,lp", [(4, 2.0), (1, 1.0)])
-def test_device_search_follows_oracle_search_on_its_own_logits_full_length(cuda_device, nb, lp):
+def test_device_search_follows_oracle_search_on_its_own_logits_full_length(cuda_device, nb, lp, cfg=None):
     """Size-independent exactness property at BASELINE's inference sizes (L = 1024 article tokens, V = 50267, max_length
     50): the oracle's `_beam_search` / greedy loop is driven with the fp32 logits our cached decoder produces step by step;
     the device-side search, seeing the same numbers, must make the same decisions, so the final ids are identical — however
@@ -217,7 +217,8 @@ def test_device_search_follows_oracle_search_on_its_own_logits_full_length(cuda_
     from vacnic_b200 import generation
     from vacnic_b200.modeling import VacnicBart
     dev = cuda_device
-    cfg = spec.VacnicConfig(d_model=1024, heads=16, ffn=2048, enc_layers=2, dec_layers=2, prompt_size=20, max_pos=1024)
+    if cfg is None:
+        cfg = spec.VacnicConfig(d_model=1024, heads=16, ffn=2048, enc_layers=2, dec_layers=2, prompt_size=20, max_pos=1024)
     sd = spec.test_state_dict(cfg, 77, lm_scale=4.0)
     sd["final_logits_bias"][0, cfg.eos_token_id] = 9.0          # some beams finish early
     m = VacnicBart(cfg, device=dev, p_drop=0.0)
@@ -259,3 +260,65 @@ def test_device_search_follows_oracle_search_on_its_own_logits_full_length(cuda_
         want = ids
         got = eng.st["seq"][:, :want.shape[1]].long()
     assert got.shape == want.shape and bool((got == want).all()), (got, want)
+
+
+def test_full_depth_device_search_follows_oracle_search_on_its_own_logits(cuda_device):
+    """The same exactness property as above at FULL depth (BART-large VACNIC, 12 + 12 layers, ffn 4096) and BASELINE's
+    inference sizes (configs[2]: L = 1024, beam 4, max_length 50, length_penalty 2.0)."""
+    test_device_search_follows_oracle_search_on_its_own_logits_full_length(cuda_device, 4, 2.0, cfg=spec.bart_large())
+
+
+def test_full_depth_beam_scores_match_fp32_teacher_forcing(cuda_device):
+    """Full-size generation parity that needs no margin vetting: the captions the engine returns at
+    configs[2] sizes (BART-large VACNIC, L = 1024, beam 4, max_length 50, length_penalty 2.0, step graph ON) are scored
+    by the fp32 oracle with teacher forcing (one uncached forward over the whole caption, same weights).  The engine's
+    own `sequences_scores` -- accumulated token by token through the KV cache, the packed encoder and the fused search
+    kernels -- must agree: summed log-probability within 1.5e-2 per generated token (the full-size logit tolerance of
+    tests/test_fullsize_gpu.py is 5e-2 max / 8e-3 mean), i.e. well under 1 % of the score.  The fp32 oracle's own beam
+    search is run too: every caption the engine picked must score, under fp32, within 1 % of the oracle's best."""
+    from vacnic_b200 import generation
+    from vacnic_b200.modeling import VacnicBart
+    dev = cuda_device
+    cfg = spec.bart_large()
+    sd = spec.test_state_dict(cfg, 78, lm_scale=4.0)
+    sd["final_logits_bias"][0, cfg.eos_token_id] = 7.0
+    m = VacnicBart(cfg, device=dev, p_drop=0.0)
+    m.load_reference_state_dict(sd)
+    m.eval()
+    C, L, nb, max_len, lp = 4, 1024, 4, 50, 2.0
+    batch = synthetic.to_device(synthetic.make_batch(B=C, L=L, T=8, seed=23), dev)
+    kw = _gen_kwargs(cfg, batch)
+    eng = generation.Generator(m, C, nb, L, max_len, length_penalty=lp, use_graph=True)
+    ids = eng.generate(generation._enc_inputs(m, kw["input_ids"], kw["attention_mask"], kw["image_features"],
+                                              kw.get("face_features"), kw.get("face_mask"), kw.get("name_ids"), kw.get("name_mask")))
+    got_score, got_len = eng.sequences_scores.float(), eng.sequences_len.long()
+    assert ids.shape[0] == C and ids.shape[1] >= 3
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+
+    def fp32_sum_logprob(seq, n):
+        """Teacher-forced fp32 log-probability of the n generated tokens of each row (ForcedEOS at max_length - 1)."""
+        with torch.no_grad():
+            o = OM.model_forward(sdd, cfg.as_dict(), decoder_input_ids=seq[:, :-1].contiguous(), **kw)
+        logp = torch.log_softmax(o["logits"].float(), dim=-1)
+        if seq.shape[1] == max_len:
+            logp[:, max_len - 2, :] = -float("inf")
+            logp[:, max_len - 2, cfg.eos_token_id] = 0.0
+        tok = logp.gather(-1, seq[:, 1:, None]).squeeze(-1)
+        keep = torch.arange(seq.shape[1] - 1, device=dev)[None, :] < n[:, None]
+        return (tok * keep).sum(-1)
+
+    want_sum = fp32_sum_logprob(ids, got_len)
+    got_sum = got_score * got_len.float() ** lp
+    err = (got_sum - want_sum).abs()
+    assert bool((err <= 1.5e-2 * got_len.float()).all()), (got_sum, want_sum, got_len)
+    assert bool((err <= 1e-2 * want_sum.abs()).all()), (got_sum, want_sum)
+    # rows that ended early are padded after their EOS, and nothing follows an EOS
+    for r in range(C):
+        n = int(got_len[r])
+        assert bool((ids[r, 1 + n:] == cfg.pad_token_id).all())
+        assert n == max_len - 1 or int(ids[r, n]) == cfg.eos_token_id
+    # the fp32 oracle's own search (KV-cached, same weights): near-ties may flip tokens, but not the quality of the result
+    enc_inputs = {k: v for k, v in kw.items()}
+    want_ids, want_score = OG.beam_search(sdd, cfg.as_dict(), enc_inputs, num_beams=nb, max_length=max_len, length_penalty=lp)
+    ours_fp32 = want_sum / got_len.float() ** lp
+    assert bool((ours_fp32 >= want_score.float() - 1e-2 * want_score.float().abs()).all()), (ours_fp32, want_score)

@@ -78,6 +78,7 @@ class Generator:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self.steps_run = 0
+        self.sequences_scores = self.sequences_len = None   # beam search only; set by decode()
 
     # ------------------------------------------------------------------ encoder side
     def _reset_state(self):
@@ -263,6 +264,9 @@ class Generator:
         if self.nb > 1:
             ob = t & 1  # buffer written by the last executed step
             gen_len = int(st["fin_len"][ob, :, 0].max().item())
+            # transformers' `sequences_scores`: sum of token log-probs / generated_len ** length_penalty, best hypothesis
+            self.sequences_scores = st["fin_score"][ob, :, 0].clone()
+            self.sequences_len = st["fin_len"][ob, :, 0].clone()
             return st["fin_seq"][ob, :, 0, :1 + gen_len].to(torch.int64)
         return st["seq"][:, :stop_t + 1].to(torch.int64)
 
