@@ -276,7 +276,8 @@ int vacnic_decode_cross_attn(const void* q, int64_t ldq, const void* k, const vo
                              int32_t captions, int32_t nq, int32_t L, int32_t H, int32_t head_dim, void* stream);
 int vacnic_mask_key_len(const uint8_t* mask, int32_t* key_len, int32_t B, int32_t L, void* stream);
 /* Per row of fp32 logits [rows][ld]: log-softmax statistics and the K best entries, sorted (ties: lower
- * index).  top_lp[r][k] = logit - logsumexp(row). */
+ * index; -inf entries are never returned: missing slots hold -inf / 0x7fffffff).  top_lp[r][k] = logit -
+ * logsumexp(row).  V <= 65536, K <= 16, rows <= 65535.  One 8-CTA cluster per row, the row lives in registers. */
 int vacnic_decode_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, int32_t K, float* top_lp,
                        int32_t* top_idx, void* stream);
 /* One `_beam_search` iteration (top-2*beams continuations, running beams, finished set with

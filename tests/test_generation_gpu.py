@@ -124,16 +124,56 @@ def test_beam_step_kernels_follow_oracle(cuda_device, C, nb, V, max_len, eos_boo
 def test_topk_matches_torch(cuda_device):
     from vacnic_b200 import kernels as K
     torch.manual_seed(5)
-    for rows, V, Kc in ((3, 50267, 8), (9, 1000, 1), (2, 77, 16)):
-        ld = (V + 7) // 8 * 8
+    # vocabulary sizes on both sides of every per-lane register count of the cluster kernel (2 / 8 / 26 / 32 elements per
+    # lane x 2048 lanes per row), a row stride that is not 16-byte aligned, K up to 2 * 8 beams
+    for rows, V, Kc in ((3, 50267, 8), (9, 1000, 1), (2, 77, 16), (5, 4096, 8), (5, 4097, 8), (3, 16385, 6), (2, 53249, 16),
+                        (2, 65536, 8), (300, 50267, 8), (4, 16, 16)):
+        ld = (V + 7) // 8 * 8 + (1 if V % 2 else 0)
         buf = torch.randn(rows, ld, device=cuda_device) * 4
         lg = buf[:, :V]
         lp = torch.empty(rows, Kc, device=cuda_device)
         ix = torch.empty(rows, Kc, dtype=torch.int32, device=cuda_device)
         K.decode_topk(lg, V, Kc, lp, ix)
         ref_lp, ref_ix = torch.topk(torch.log_softmax(lg, -1), Kc)
-        assert bool((ix.long() == ref_ix).all())
-        assert torch.allclose(lp, ref_lp, atol=2e-5, rtol=1e-5)
+        assert bool((ix.long() == ref_ix).all()), (rows, V, Kc)
+        assert torch.allclose(lp, ref_lp, atol=2e-5, rtol=1e-5), (rows, V, Kc)
+
+
+def test_topk_ties_and_masked_entries(cuda_device):
+    """Equal logits resolve to the LOWER vocabulary index (the order `torch.topk` of the reference produces on sorted
+    ties is unspecified; transformers' beam search then prefers the lower flattened index, oracle/generate.py), the K best
+    may all sit in one warp's segment or one lane's registers, and -inf entries (suppressed tokens) are never returned
+    while finite ones remain."""
+    from vacnic_b200 import kernels as K
+    dev = cuda_device
+    V, Kc = 50267, 8
+    lg = torch.full((6, V), -3.0, device=dev)
+    lg[0, 40000:40003] = 5.0                       # three-way tie at the top, then a sea of equal values
+    lg[1, 7::32][:12] = torch.arange(12, 0, -1, device=dev).float()   # 12 winners in ONE lane of one warp
+    lg[2, 800:816] = torch.arange(16, 0, -1, device=dev).float()      # 16 winners in one warp segment
+    lg[3, :] = -float("inf")
+    lg[3, [5, 50266, 25000]] = torch.tensor([1.0, 1.0, 2.0], device=dev)   # only three finite entries
+    lg[4, V - 1] = 9.0                              # the last element of the ragged tail
+    lg[5] = torch.randn(V, device=dev).round()      # many exact ties everywhere
+    # finite values in only 7 of every 32 consecutive positions (fewer than K lanes of any warp hold one): no finite
+    # threshold exists, the candidate list overflows and the kernel's arg-max fallback has to produce the answer
+    sparse = torch.full((V,), -float("inf"), device=dev)
+    keep = (torch.arange(V, device=dev) % 32) < 7
+    sparse[keep] = torch.randn(int(keep.sum()), device=dev).round()
+    lg = torch.cat([lg, sparse[None, :], torch.full((1, V), -float("inf"), device=dev)])
+    lg[7, 31] = 0.5                                 # a single finite entry in the whole row
+    R = lg.shape[0]
+    lp = torch.empty(R, Kc, device=dev)
+    ix = torch.empty(R, Kc, dtype=torch.int32, device=dev)
+    K.decode_topk(lg, V, Kc, lp, ix)
+    ref = torch.log_softmax(lg, -1)
+    # reference order: value descending, index ascending == stable descending sort
+    order = torch.sort(ref, dim=-1, descending=True, stable=True)
+    for r in range(R):
+        n = int(torch.isfinite(ref[r]).sum().clamp(max=Kc))
+        assert ix[r, :n].long().tolist() == order.indices[r, :n].tolist(), r
+        assert torch.allclose(lp[r, :n], order.values[r, :n], atol=2e-5, rtol=1e-5), r
+        assert bool((lp[r, n:] == -float("inf")).all()), r
 
 
 # ---------------------------------------------------------------------------------------------- cached attention

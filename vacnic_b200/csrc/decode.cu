@@ -385,8 +385,21 @@ __global__ void mask_key_len_kernel(const uint8_t* __restrict__ mask, int32_t* _
 
 // ------------------------------------------------------------------------------------------------
 // Per-row log-softmax statistics + top-K of the LM-head logits (the `log_softmax` and the row-local part
-// of `torch.topk(..., 2*num_beams)` of _beam_search; greedy uses K = 1).  One CTA per row, the row is
-// staged once in shared memory.  Ties: lower vocabulary index first.
+// of `torch.topk(..., 2*num_beams)` of _beam_search; greedy uses K = 1).  Total order everywhere: value descending,
+// then vocabulary index ascending; -inf entries (suppressed tokens) are never returned.
+//
+// One thread-block CLUSTER of 8 CTAs per row.  Every lane keeps E elements of the row in REGISTERS (E coalesced 4-byte
+// loads, all in flight at once; no shared-memory staging), so the 200 KB row is read from HBM exactly once and several
+// CTAs per SM overlap each other's loads and selection.  Selection is by THRESHOLD, not by K extraction rounds:
+//   warp:    T_w = the K-th largest of its 32 lane maxima (found by counting, no sorting); at least K elements of the
+//            row are >= T_w, so T_w is a lower bound of the row's K-th best
+//   CTA:     T_c = best T_w of its 8 warps; every element >= T_c goes to a shared-memory candidate list (a few dozen
+//            for K = 8); the K best of the list are found by counting ranks, one candidate per thread
+//   cluster: every CTA stores its K best and its (max, sum of exp) into CTA 0's shared memory (distributed shared
+//            memory), arrives on the cluster barrier and exits; CTA 0 alone waits, ranks the 8 K candidates and writes
+//            the row's K (log-prob, index) pairs.
+// Inputs whose finite values sit in fewer than K lanes of every warp (threshold -inf), or with hundreds of values tied at
+// the threshold, overflow the candidate list; that CTA then falls back to K rounds of block-wide arg-max over its registers.
 // ------------------------------------------------------------------------------------------------
 struct ValIdx {
   float v;
@@ -405,112 +418,185 @@ __device__ __forceinline__ ValIdx warp_argmax(ValIdx a) {
 
 constexpr int kMaxBeams = 8;
 constexpr int kMaxCand = 2 * kMaxBeams * kMaxBeams;  // nb rows x K = 2 nb candidates each
-constexpr int kTopThreads = 1024;
+constexpr int kTopK = 2 * kMaxBeams;                 // largest K
+constexpr int kTopCluster = 8;                       // CTAs per row
+constexpr int kTopWarps = 8;
+constexpr int kTopThreads = 32 * kTopWarps;
+constexpr int kTopCap = kTopThreads;                 // candidate list: one candidate per thread in the ranking pass
+constexpr int kNoIdx = 0x7fffffff;
 
-__global__ void __launch_bounds__(kTopThreads)
+struct TopPart {  // one CTA's share of a row
+  float m, s;     // max, sum of exp(x - m)
+  float v[kTopK];
+  int i[kTopK];
+};
+
+__device__ __forceinline__ uint32_t dsmem_addr(const void* p, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_st_f32(uint32_t a, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_st_s32(uint32_t a, int v) {
+  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// no memory ordering (no MEMBAR / ERRBAR): for warps that published nothing
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int E>
+__global__ void __cluster_dims__(kTopCluster, 1, 1) __launch_bounds__(kTopThreads, E <= 26 ? 4 : 3)
 decode_topk_kernel(const float* __restrict__ logits, long long ld, int V, int K, float* __restrict__ top_lp,
                    int32_t* __restrict__ top_idx) {
+  cluster_arrive_relaxed();  // phase 0: "this CTA is running" -- waited for right before the first remote store
   pdl_sync();
-  extern __shared__ float row[];  // [V]
-  __shared__ float redf[32];
-  __shared__ float bc_f;
+  __shared__ TopPart parts[kTopCluster];  // gather target; only CTA 0's copy is read
+  __shared__ float w_m[kTopWarps], w_s[kTopWarps], thr_v[kTopWarps];
+  __shared__ __align__(16) float lane_max[kTopWarps][32];
+  __shared__ float cand_v[kTopCap], sel_v[kTopK];
+  __shared__ int cand_i[kTopCap], sel_i[kTopK];
+  __shared__ int n_cand;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* src = logits + static_cast<long long>(blockIdx.x) * ld;
-  float mx = -INFINITY;
-  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    // 16-byte loads, several in flight per thread: the row (200 KB) is the only HBM traffic of this kernel
-    const int v4 = V >> 2;
-    const float4* src4 = reinterpret_cast<const float4*>(src);
-    float4* row4 = reinterpret_cast<float4*>(row);
-#pragma unroll 4
-    for (int i = tid; i < v4; i += kTopThreads) {
-      const float4 x = __ldg(src4 + i);
-      row4[i] = x;
-      mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+  const int crank = blockIdx.x;  // gridDim.x == cluster size: the CTA's rank in its cluster
+  const long long row = blockIdx.y;
+  const float* src = logits + row * ld;
+  const int base = (crank * kTopWarps + warp) * (32 * E) + lane;  // the lane's first element; stride 32
+  float x[E];
+  if (base - lane + 32 * E <= V) {  // warp-uniform: the whole segment is inside the row
+#pragma unroll
+    for (int j = 0; j < E; ++j) x[j] = __ldg(src + base + j * 32);
+  } else {
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int i = base + j * 32;
+      x[j] = i < V ? __ldg(src + i) : -INFINITY;
     }
-    for (int i = (v4 << 2) + tid; i < V; i += kTopThreads) {
-      const float x = __ldg(src + i);
-      row[i] = x;
-      mx = fmaxf(mx, x);
+  }
+  if (tid == 0) n_cand = 0;
+  if (tid < kTopK) { sel_v[tid] = -INFINITY; sel_i[tid] = kNoIdx; }
+  // ---- lane maximum, warp max / sum of exp
+  float lmv = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < E; ++j) lmv = fmaxf(lmv, x[j]);
+  const float wm = warp_max(lmv);
+  float sum = 0.f;
+  if (wm > -INFINITY) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float nb = -wm * kLog2e;
+#pragma unroll
+    for (int j = 0; j < E; ++j) sum += ex2_approx(fmaf(x[j], kLog2e, nb));  // |d lse| ~ 1e-6, far below score gaps
+  }
+  sum = warp_sum(sum);
+  // ---- T_w: the K-th largest of the 32 lane maxima, by counting (values only: equal values form one group, and the
+  // filter below accepts everything >= T, so ties never lose a candidate).  -inf when fewer than K lanes hold a finite value.
+  lane_max[warp][lane] = lmv;
+  __syncwarp();
+  int gt = 0, ge = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = reinterpret_cast<const float4*>(lane_max[warp])[q];  // broadcast read
+    gt += (f.x > lmv) + (f.y > lmv) + (f.z > lmv) + (f.w > lmv);
+    ge += (f.x >= lmv) + (f.y >= lmv) + (f.z >= lmv) + (f.w >= lmv);
+  }
+  const unsigned holder = __ballot_sync(0xffffffffu, gt < K && K <= ge && lmv > -INFINITY);
+  float T = -INFINITY;
+  if (holder) T = __shfl_sync(0xffffffffu, lmv, __ffs(holder) - 1);
+  if (lane == 0) { w_m[warp] = wm; w_s[warp] = sum; thr_v[warp] = T; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kTopWarps; ++w) T = fmaxf(T, thr_v[w]);
+  // ---- candidates: finite elements >= T_c (warp-aggregated append; hits are rare, the branch is warp-uniform)
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const bool p = x[j] >= T && x[j] > -INFINITY;
+    const unsigned b = __ballot_sync(0xffffffffu, p);
+    if (b) {
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(&n_cand, __popc(b));
+      pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(b & ((1u << lane) - 1u));
+      if (p && pos < kTopCap) { cand_v[pos] = x[j]; cand_i[pos] = base + j * 32; }
+    }
+  }
+  __syncthreads();
+  const int n = n_cand;
+  if (n <= kTopCap) {
+    if (tid < n) {  // rank by counting; indices are distinct, so ranks are
+      const float v = cand_v[tid];
+      const int i = cand_i[tid];
+      int r = 0;
+      for (int u = 0; u < n; ++u) r += better(cand_v[u], cand_i[u], v, i) ? 1 : 0;
+      if (r < K) { sel_v[r] = v; sel_i[r] = i; }
     }
   } else {
-    for (int i = tid; i < V; i += kTopThreads) {
-      const float x = __ldg(src + i);
-      row[i] = x;
-      mx = fmaxf(mx, x);
-    }
-  }
-  mx = warp_max(mx);
-  if (lane == 0) redf[warp] = mx;
-  __syncthreads();
-  if (warp == 0) {
-    float m = warp_max(redf[lane]);
-    if (lane == 0) bc_f = m;
-  }
-  __syncthreads();
-  mx = bc_f;
-  float sum = 0.f;
-  for (int i = tid; i < V; i += kTopThreads) sum += __expf(row[i] - mx);  // ex2.approx: |d lse| ~ 1e-7, far below score gaps
-  sum = warp_sum(sum);
-  __syncthreads();
-  if (lane == 0) redf[warp] = sum;
-  __syncthreads();
-  if (warp == 0) {
-    float s = warp_sum(redf[lane]);
-    if (lane == 0) bc_f = mx + logf(s);
-  }
-  __syncthreads();
-  const float lse = bc_f;
-  // Stage 1: every warp extracts the K best of its own contiguous segment with warp shuffles only (no block barrier);
-  // stage 2: warp 0 merges the 32 sorted candidate lists.  Order everywhere: value descending, index ascending.
-  __shared__ float cand_v[32][2 * kMaxBeams];
-  __shared__ int cand_i[32][2 * kMaxBeams];
-  const int seg = (V + 31) / 32;
-  const int s0 = warp * seg, s1 = min(V, s0 + seg);
-  // every lane keeps the two best of its own elements, so that a full rescan (issued by the whole warp for one lane) is only
-  // needed when a lane has to supply a third candidate
-  ValIdx best = {-INFINITY, 0x7fffffff}, second = {-INFINITY, 0x7fffffff};
-  auto scan2 = [&]() {
-    best.v = second.v = -INFINITY;
-    best.i = second.i = 0x7fffffff;
-    for (int i = s0 + lane; i < s1; i += 32) {
-      const float x = row[i];
-      if (x > -INFINITY) {
-        if (better(x, i, best.v, best.i)) { second = best; best.v = x; best.i = i; }
-        else if (better(x, i, second.v, second.i)) { second.v = x; second.i = i; }
-      }
-    }
-  };
-  scan2();
-  bool second_valid = true;
-  for (int k = 0; k < K; ++k) {
-    const ValIdx w = warp_argmax(best);
-    if (lane == 0) { cand_v[warp][k] = w.v; cand_i[warp][k] = w.i; }
-    if (w.i != 0x7fffffff && ((w.i - s0) & 31) == lane) {  // owner lane: drop the winner, promote its runner-up
-      row[w.i] = -INFINITY;
-      if (second_valid) {
-        best = second;
-        second_valid = false;
-      } else {
-        scan2();
-        second_valid = true;
-      }
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  if (warp == 0) {
-    int head = 0;  // lane l walks the (sorted) list of warp l
+    // fallback: K rounds of block-wide arg-max over the registers (cand_* reused as the per-warp exchange)
     for (int k = 0; k < K; ++k) {
-      ValIdx mine = {-INFINITY, 0x7fffffff};
-      if (head < K) { mine.v = cand_v[lane][head]; mine.i = cand_i[lane][head]; }
-      const ValIdx w = warp_argmax(mine);
-      if (w.i == mine.i && w.i != 0x7fffffff) ++head;
-      if (lane == 0) {
-        top_lp[static_cast<long long>(blockIdx.x) * K + k] = w.v - lse;
-        top_idx[static_cast<long long>(blockIdx.x) * K + k] = w.i;
-      }
+      ValIdx b = {-INFINITY, kNoIdx};
+#pragma unroll
+      for (int j = 0; j < E; ++j)
+        if (x[j] > b.v) { b.v = x[j]; b.i = base + j * 32; }
+      b = warp_argmax(b);
+      __syncthreads();
+      if (lane == 0) { cand_v[warp] = b.v; cand_i[warp] = b.i; }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < kTopWarps; ++w)
+        if (better(cand_v[w], cand_i[w], b.v, b.i)) { b.v = cand_v[w]; b.i = cand_i[w]; }
+      if (tid == 0) { sel_v[k] = b.v; sel_i[k] = b.i; }
+#pragma unroll
+      for (int j = 0; j < E; ++j)
+        if (base + j * 32 == b.i) x[j] = -INFINITY;
     }
+  }
+  __syncthreads();
+  // ---- hand the CTA's result to CTA 0 of the cluster
+  cluster_wait();  // phase 0 complete: every CTA of the cluster has started, its shared memory may be written
+  const uint32_t dst = dsmem_addr(&parts[crank], 0);
+  if (tid < K) {
+    dsmem_st_f32(dst + offsetof(TopPart, v) + 4 * tid, sel_v[tid]);
+    dsmem_st_s32(dst + offsetof(TopPart, i) + 4 * tid, sel_i[tid]);
+  } else if (tid == 31) {  // K <= 16: a free lane of warp 0, the only warp that publishes
+    float cm = w_m[0];
+#pragma unroll
+    for (int w = 1; w < kTopWarps; ++w) cm = fmaxf(cm, w_m[w]);
+    float cs = 0.f;
+#pragma unroll
+    for (int w = 0; w < kTopWarps; ++w)
+      if (w_m[w] > -INFINITY) cs += w_s[w] * __expf(w_m[w] - cm);
+    dsmem_st_f32(dst + offsetof(TopPart, m), cm);
+    dsmem_st_f32(dst + offsetof(TopPart, s), cs);
+  }
+  __syncwarp();
+  if (warp == 0) cluster_arrive();  // phase 1 (release): this CTA's stores are done
+  else cluster_arrive_relaxed();
+  if (crank != 0) return;
+  cluster_wait();    // phase 1 (acquire): all 8 parts are in
+  // ---- CTA 0: rank the 8 K candidates
+  const int total = kTopCluster * K;
+  if (tid < kTopK) { sel_v[tid] = -INFINITY; sel_i[tid] = kNoIdx; }
+  if (tid < total) { cand_v[tid] = parts[tid / K].v[tid % K]; cand_i[tid] = parts[tid / K].i[tid % K]; }
+  __syncthreads();
+  if (tid < total && cand_i[tid] != kNoIdx) {
+    const float v = cand_v[tid];
+    const int i = cand_i[tid];
+    int r = 0;
+    for (int u = 0; u < total; ++u) r += better(cand_v[u], cand_i[u], v, i) ? 1 : 0;
+    if (r < K) { sel_v[r] = v; sel_i[r] = i; }
+  }
+  __syncthreads();
+  if (tid < K) {
+    float M = parts[0].m;
+#pragma unroll
+    for (int c = 1; c < kTopCluster; ++c) M = fmaxf(M, parts[c].m);
+    float S = 0.f;
+#pragma unroll
+    for (int c = 0; c < kTopCluster; ++c)
+      if (parts[c].m > -INFINITY) S += parts[c].s * expf(parts[c].m - M);
+    const float lse = M + logf(S);
+    top_lp[row * K + tid] = sel_v[tid] - lse;
+    top_idx[row * K + tid] = sel_i[tid];
   }
 }
 
@@ -792,16 +878,16 @@ extern "C" int vacnic_mask_key_len(const uint8_t* mask, int32_t* key_len, int32_
 extern "C" int vacnic_decode_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, int32_t K, float* top_lp,
                                   int32_t* top_idx, void* stream) {
   VB_REQUIRE(logits && top_lp && top_idx, "decode_topk: null pointer");
-  VB_REQUIRE(rows > 0 && V > 0 && K >= 1 && K <= 2 * kMaxBeams && K <= V, "decode_topk: bad shape (K <= %d)", 2 * kMaxBeams);
-  const size_t smem = static_cast<size_t>(V) * sizeof(float);
-  VB_REQUIRE(smem <= 220 * 1024, "decode_topk: vocabulary %d does not fit the shared-memory row buffer", V);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(decode_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(VACNIC_ECUDA, "decode_topk: smem %zu: %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
-  launch_pdl(decode_topk_kernel, dim3(rows), dim3(kTopThreads), smem, static_cast<cudaStream_t>(stream), logits, ld, V, K, top_lp, top_idx);
+  VB_REQUIRE(rows > 0 && rows <= 65535 && V > 0 && K >= 1 && K <= 2 * kMaxBeams && K <= V,
+             "decode_topk: bad shape (rows <= 65535, K <= %d)", 2 * kMaxBeams);
+  VB_REQUIRE(V <= kTopCluster * kTopThreads * 32, "decode_topk: vocabulary %d exceeds %d", V, kTopCluster * kTopThreads * 32);
+  const dim3 grid(kTopCluster, rows), block(kTopThreads);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int per_lane = (V + kTopCluster * kTopThreads - 1) / (kTopCluster * kTopThreads);  // elements each lane holds
+  if (per_lane <= 2) launch_pdl(decode_topk_kernel<2>, grid, block, 0, st, logits, ld, V, K, top_lp, top_idx);
+  else if (per_lane <= 8) launch_pdl(decode_topk_kernel<8>, grid, block, 0, st, logits, ld, V, K, top_lp, top_idx);
+  else if (per_lane <= 26) launch_pdl(decode_topk_kernel<26>, grid, block, 0, st, logits, ld, V, K, top_lp, top_idx);
+  else launch_pdl(decode_topk_kernel<32>, grid, block, 0, st, logits, ld, V, K, top_lp, top_idx);
   count_launch();
   return check_last("decode_topk");
 }
