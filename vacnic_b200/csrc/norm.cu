@@ -78,29 +78,38 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
   const uint32_t seed = drop ? static_cast<uint32_t>(*a.rng) : 0u;
   const uint32_t thr = drop_thresh(a.p_drop);
   const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  // Every load of the row is issued before the first use (the branches are warp-uniform): up to 3 x VPL 16-byte loads in
+  // flight per lane instead of 3, which is what a one-row-per-warp kernel needs to cover the HBM latency.
+  const float4* r4 = a.res32 ? reinterpret_cast<const float4*>(a.res32 + row * a.d) : nullptr;
+  uint4 rx[VPL], rr[VPL];
+  float4 r0[VPL], r1[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+    rx[j] = xp ? __ldg(xp + vi) : make_uint4(0u, 0u, 0u, 0u);
+    if (r4) {
+      r0[j] = __ldg(r4 + vi * 2);
+      r1[j] = __ldg(r4 + vi * 2 + 1);
+    } else {
+      rr[j] = rp ? __ldg(rp + vi) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   float v[VPL][8];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     const int vi = lane + 32 * j;
-    if (xp) {
-      unpack8(__ldg(xp + vi), v[j]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
-    }
+    unpack8(rx[j], v[j]);
     if (drop) {
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         v[j][e] = keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + vi * 8 + e, thr) ? v[j][e] * inv_keep : 0.f;
     }
-    if (a.res32) {  // residual stream carried in fp32 (what torch.autocast keeps: LayerNorm outputs stay fp32)
-      const float4* r4 = reinterpret_cast<const float4*>(a.res32 + row * a.d) + vi * 2;
-      const float4 r0 = __ldg(r4), r1 = __ldg(r4 + 1);
-      v[j][0] += r0.x; v[j][1] += r0.y; v[j][2] += r0.z; v[j][3] += r0.w;
-      v[j][4] += r1.x; v[j][5] += r1.y; v[j][6] += r1.z; v[j][7] += r1.w;
+    if (r4) {  // residual stream carried in fp32 (what torch.autocast keeps: LayerNorm outputs stay fp32)
+      v[j][0] += r0[j].x; v[j][1] += r0[j].y; v[j][2] += r0[j].z; v[j][3] += r0[j].w;
+      v[j][4] += r1[j].x; v[j][5] += r1[j].y; v[j][6] += r1[j].z; v[j][7] += r1[j].w;
     } else if (rp) {
       float r[8];
-      unpack8(__ldg(rp + vi), r);
+      unpack8(rr[j], r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[j][e] += r[e];
     }
@@ -224,37 +233,54 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_bwd_kernel(
     const uint4* xp = reinterpret_cast<const uint4*>(a.x + row * a.d);
     const uint4* rp = a.res ? reinterpret_cast<const uint4*>(a.res + row * a.d) : nullptr;
     const uint4* dyp = reinterpret_cast<const uint4*>(a.dy + (row / a.rpg) * a.dy_gs + (row % a.rpg) * a.d);
-    const float mean = a.mean[row], rstd = a.rstd[row];
-    float xh[VPL][8], g[VPL][8];
-    bool keep[VPL][8];
-    float s1 = 0.f, s2 = 0.f;
+    // Every load of the row is issued before the first use (3 x VPL 16-byte loads in flight per lane): with ~8 resident
+    // warps per SM the kernel lives on memory-level parallelism.  The raw bf16 words stay in registers and x_hat / g are
+    // recomputed in the second pass instead of being kept as 2 x 32 fp32 values across the row reduction.
+    uint4 rx[VPL], rdy[VPL], rr[VPL];
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       const int vi = lane + 32 * j;
-      float v[8], dyv[8];
-      unpack8(__ldg(xp + vi), v);
-      unpack8(__ldg(dyp + vi), dyv);
+      rx[j] = __ldg(xp + vi);
+      rdy[j] = __ldg(dyp + vi);
+      rr[j] = rp ? __ldg(rp + vi) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    uint32_t keep = 0xffffffffu;  // bit j*8+e (VPL <= 4)
+    if (drop) {
+      keep = 0u;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        keep[j][e] = !drop || keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + vi * 8 + e, thr);
-        v[e] = keep[j][e] ? v[e] * inv_keep : 0.f;
-      }
-      if (rp) {
-        float r[8];
-        unpack8(__ldg(rp + vi), r);
+      for (int j = 0; j < VPL; ++j)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += r[e];
-      }
+        for (int e = 0; e < 8; ++e)
+          keep |= static_cast<uint32_t>(keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + (lane + 32 * j) * 8 + e, thr))
+                  << (j * 8 + e);
+    }
+    auto xhat_g = [&](int j, float (&xh)[8], float (&g)[8], float (&dyv)[8]) {
+      const int vi = lane + 32 * j;
+      float v[8], r[8];
+      unpack8(rx[j], v);
+      unpack8(rdy[j], dyv);
+      unpack8(rr[j], r);
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2);
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma) + vi * 2 + 1);
       const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        xh[j][e] = (v[e] - mean) * rstd;
-        g[j][e] = dyv[e] * gm[e];
-        s1 += g[j][e];
-        s2 += g[j][e] * xh[j][e];
-        dg[j][e] += dyv[e] * xh[j][e];
+        const float xv = ((keep >> (j * 8 + e)) & 1u) ? v[e] * inv_keep : 0.f;
+        xh[e] = (xv + r[e] - mean) * rstd;
+        g[e] = dyv[e] * gm[e];
+      }
+    };
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      float xh[8], g[8], dyv[8];
+      xhat_g(j, xh, g, dyv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s1 += g[e];
+        s2 += g[e] * xh[e];
+        dg[j][e] += dyv[e] * xh[e];
         db[j][e] += dyv[e];
       }
     }
@@ -263,9 +289,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_bwd_kernel(
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       const int vi = lane + 32 * j;
-      float ds[8], dxv[8];
+      float xh[8], g[8], dyv[8], ds[8], dxv[8];
+      xhat_g(j, xh, g, dyv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) ds[e] = rstd * (g[j][e] - s1 - xh[j][e] * s2);
+      for (int e = 0; e < 8; ++e) ds[e] = rstd * (g[e] - s1 - xh[e] * s2);
       if (a.dsum) {
         uint4* p = reinterpret_cast<uint4*>(a.dsum + row * a.d) + vi;
         if (a.accumulate_dsum) {
@@ -278,7 +305,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_bwd_kernel(
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        dxv[e] = keep[j][e] ? ds[e] * inv_keep : 0.f;
+        dxv[e] = ((keep >> (j * 8 + e)) & 1u) ? ds[e] * inv_keep : 0.f;
         dbi[j][e] += dxv[e];
       }
       if (a.dx && a.dx != a.dsum) reinterpret_cast<uint4*>(a.dx + row * a.d)[vi] = pack8(dxv);
@@ -529,7 +556,9 @@ names_embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __res
 static int bwd_grid(long long rows) {
   const int sms = sm_count();
   long long want = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  long long cap = static_cast<long long>(sms > 0 ? sms : 148) * 4;
+  // the backward kernels hold 3 x d/32 accumulators per lane (~250 registers): one CTA per SM is resident, so one CTA per
+  // SM is launched -- a single wave, and the fewest end-of-CTA atomics on the parameter gradients
+  long long cap = static_cast<long long>(sms > 0 ? sms : 148);
   return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
