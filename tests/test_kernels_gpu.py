@@ -367,6 +367,18 @@ def test_ner_map_block_applies_the_reference_dropout(cuda_device):
     y, mean, rstd = k.add_layernorm_fwd(z, None, gamma, beta, p_drop=p, rng=rng, salt=3)
     kept_fwd = y.float() > 0
     assert abs((~kept_fwd).float().mean().item() - p) < 0.01
+    # the LayerNorm kernels draw TWO decisions from one counter hash (16-bit fields): the two elements of a pair, neighbouring
+    # pairs, and the same element under another salt / another step must be independent Bernoulli(1 - p) draws
+    kf = kept_fwd.float()
+    q = 1 - p
+    assert abs((kf[:, 0::2] * kf[:, 1::2]).mean().item() - q * q) < 0.01
+    assert abs((kf[:, 1:-1:2] * kf[:, 2::2]).mean().item() - q * q) < 0.01
+    y_salt, _, _ = k.add_layernorm_fwd(z, None, gamma, beta, p_drop=p, rng=rng, salt=4)
+    assert abs((kf * (y_salt.float() > 0).float()).mean().item() - q * q) < 0.01
+    rng2 = k.Rng(cuda_device, seed=6)
+    y_seed, _, _ = k.add_layernorm_fwd(z, None, gamma, beta, p_drop=p, rng=rng2, salt=3)
+    assert abs((kf * (y_seed.float() > 0).float()).mean().item() - q * q) < 0.01
+    assert abs(kf.mean(0).std().item() - (p * q / rows) ** 0.5) < 0.3 * (p * q / rows) ** 0.5   # per-column keep rates: binomial spread
     dg = torch.zeros(d, device=cuda_device); db = torch.zeros(d, device=cuda_device)
     dy = rnd((rows, d), cuda_device, 1.0, 9)
     _, dx = k.add_layernorm_bwd(dy, z, None, gamma, mean, rstd, dg, db, want_dx=True, p_drop=p, rng=rng, salt=3)

@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
   const uint4* rp = a.res ? reinterpret_cast<const uint4*>(a.res + row * a.d) : nullptr;
   const bool drop = a.p_drop > 0.f;
   const uint32_t seed = drop ? static_cast<uint32_t>(*a.rng) : 0u;
-  const uint32_t thr = drop_thresh(a.p_drop);
-  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t thr = drop_thresh16(a.p_drop);
+  const float inv_keep = drop ? 65536.f / static_cast<float>(65536u - thr) : 1.f;
   // Every load of the row is issued before the first use (the branches are warp-uniform): up to 3 x VPL 16-byte loads in
   // flight per lane instead of 3, which is what a one-row-per-warp kernel needs to cover the HBM latency.
   const float4* r4 = a.res32 ? reinterpret_cast<const float4*>(a.res32 + row * a.d) : nullptr;
@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
       rr[j] = rp ? __ldg(rp + vi) : make_uint4(0u, 0u, 0u, 0u);
     }
   }
+  const uint32_t keep = drop ? keep_row_bits<VPL>(seed, a.salt, row, a.d, lane, thr) : 0xffffffffu;
   float v[VPL][8];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
@@ -101,8 +102,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_fwd_kernel(
     unpack8(rx[j], v[j]);
     if (drop) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        v[j][e] = keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + vi * 8 + e, thr) ? v[j][e] * inv_keep : 0.f;
+      for (int e = 0; e < 8; ++e) v[j][e] = ((keep >> (j * 8 + e)) & 1u) ? v[j][e] * inv_keep : 0.f;
     }
     if (r4) {  // residual stream carried in fp32 (what torch.autocast keeps: LayerNorm outputs stay fp32)
       v[j][0] += r0[j].x; v[j][1] += r0[j].y; v[j][2] += r0[j].z; v[j][3] += r0[j].w;
@@ -213,20 +213,32 @@ struct LnBwdArgs {
   int accumulate_dsum;       // dsum += instead of = (residual stream fan-in)
 };
 
+// The parameter-gradient partial sums (d gamma, d beta, d bias: 3 x d fp32 per warp) live in SHARED memory, one private
+// slice per warp (lane l only ever touches its own columns, so no atomics and no barriers inside the row loop).  In
+// registers they cost 96 of ~250 registers and held the kernel at one 8-warp CTA per SM; in shared memory the kernel needs
+// < 128 registers and two CTAs are resident, i.e. twice the rows -- and bytes -- in flight, which is what bounds it.
 template <int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_bwd_kernel(const LnBwdArgs a) {
-  pdl_sync();
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) add_layernorm_bwd_kernel(const LnBwdArgs a) {
+  extern __shared__ __align__(16) float ln_acc[];  // [warp][3][D]
+  constexpr int D = VPL * 256;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  float* acc = ln_acc + warp * 3 * D;
+  for (int i = lane; i < 3 * D / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  pdl_sync();
   const bool drop = a.p_drop > 0.f;
   const uint32_t seed = drop ? static_cast<uint32_t>(*a.rng) : 0u;
-  const uint32_t thr = drop_thresh(a.p_drop);
-  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
-  float dg[VPL][8], db[VPL][8], dbi[VPL][8];
-#pragma unroll
-  for (int j = 0; j < VPL; ++j)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dg[j][e] = db[j][e] = dbi[j][e] = 0.f;
+  const uint32_t thr = drop_thresh16(a.p_drop);
+  const float inv_keep = drop ? 65536.f / static_cast<float>(65536u - thr) : 1.f;
+  const bool want_dbias = a.dbias != nullptr;
+  auto accumulate = [&](int which, int j, const float (&t)[8]) {  // acc[which][(lane + 32 j) * 8 + e] += t[e]
+    float4* p = reinterpret_cast<float4*>(acc + which * D) + (lane + 32 * j) * 2;
+    float4 u0 = p[0], u1 = p[1];
+    u0.x += t[0]; u0.y += t[1]; u0.z += t[2]; u0.w += t[3];
+    u1.x += t[4]; u1.y += t[5]; u1.z += t[6]; u1.w += t[7];
+    p[0] = u0; p[1] = u1;
+  };
 
   const long long wstride = static_cast<long long>(gridDim.x) * kWarpsPerBlock;
   for (long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; row < a.rows; row += wstride) {
@@ -245,16 +257,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_bwd_kernel(
       rr[j] = rp ? __ldg(rp + vi) : make_uint4(0u, 0u, 0u, 0u);
     }
     const float mean = a.mean[row], rstd = a.rstd[row];
-    uint32_t keep = 0xffffffffu;  // bit j*8+e (VPL <= 4)
-    if (drop) {
-      keep = 0u;
-#pragma unroll
-      for (int j = 0; j < VPL; ++j)
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          keep |= static_cast<uint32_t>(keep_elem(seed, a.salt, static_cast<uint64_t>(row) * a.d + (lane + 32 * j) * 8 + e, thr))
-                  << (j * 8 + e);
-    }
+    const uint32_t keep = drop ? keep_row_bits<VPL>(seed, a.salt, row, a.d, lane, thr) : 0xffffffffu;  // bit j*8+e
     auto xhat_g = [&](int j, float (&xh)[8], float (&g)[8], float (&dyv)[8]) {
       const int vi = lane + 32 * j;
       float v[8], r[8];
@@ -276,13 +279,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_bwd_kernel(
     for (int j = 0; j < VPL; ++j) {
       float xh[8], g[8], dyv[8];
       xhat_g(j, xh, g, dyv);
+      float t[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         s1 += g[e];
         s2 += g[e] * xh[e];
-        dg[j][e] += dyv[e] * xh[e];
-        db[j][e] += dyv[e];
+        t[e] = dyv[e] * xh[e];
       }
+      accumulate(0, j, t);
+      accumulate(1, j, dyv);
     }
     s1 = warp_sum(s1) / a.d;
     s2 = warp_sum(s2) / a.d;
@@ -304,33 +309,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) add_layernorm_bwd_kernel(
         *p = pack8(ds);
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        dxv[e] = ((keep >> (j * 8 + e)) & 1u) ? ds[e] * inv_keep : 0.f;
-        dbi[j][e] += dxv[e];
-      }
+      for (int e = 0; e < 8; ++e) dxv[e] = ((keep >> (j * 8 + e)) & 1u) ? ds[e] * inv_keep : 0.f;
+      if (want_dbias) accumulate(2, j, dxv);
       if (a.dx && a.dx != a.dsum) reinterpret_cast<uint4*>(a.dx + row * a.d)[vi] = pack8(dxv);
     }
   }
   // block-level reduction of the parameter gradients, then one atomic per column per block
-  __shared__ float red[kWarpsPerBlock][256];
+  __syncthreads();
   for (int which = 0; which < 3; ++which) {
-    if (which == 2 && a.dbias == nullptr) break;
     float* dst = which == 0 ? a.dgamma : (which == 1 ? a.dbeta : a.dbias);
     if (dst == nullptr) continue;
+    for (int c = threadIdx.x; c < D; c += kWarpsPerBlock * 32) {
+      float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      __syncthreads();
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        red[warp][lane * 8 + e] = which == 0 ? dg[j][e] : (which == 1 ? db[j][e] : dbi[j][e]);
-      __syncthreads();
-      // columns of this j-slab: vector (l + 32 j), element e  ->  col = (l + 32 j) * 8 + e
-      for (int c = threadIdx.x; c < 256; c += kWarpsPerBlock * 32) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < kWarpsPerBlock; ++w) s += red[w][c];
-        atomicAdd(dst + j * 256 + c, s);
-      }
+      for (int w = 0; w < kWarpsPerBlock; ++w) sum += ln_acc[(w * 3 + which) * D + c];
+      atomicAdd(dst + c, sum);
     }
   }
 }
@@ -553,12 +546,12 @@ names_embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __res
   }
 }
 
-static int bwd_grid(long long rows) {
+static int bwd_grid(long long rows, int ctas_per_sm) {
+  // the backward kernels are persistent over rows: exactly the resident CTAs are launched -- a single wave, and the fewest
+  // end-of-CTA atomics on the parameter gradients
   const int sms = sm_count();
   long long want = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  // the backward kernels hold 3 x d/32 accumulators per lane (~250 registers): one CTA per SM is resident, so one CTA per
-  // SM is launched -- a single wave, and the fewest end-of-CTA atomics on the parameter gradients
-  long long cap = static_cast<long long>(sms > 0 ? sms : 148);
+  long long cap = static_cast<long long>(sms > 0 ? sms : 148) * ctas_per_sm;
   return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
@@ -623,8 +616,18 @@ extern "C" int vacnic_add_layernorm_bwd(const void* dy, const void* x, const voi
   a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
   a.accumulate_dsum = accumulate_dsum;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = bwd_grid(rows);
-  VB_DISPATCH_VPL(d, (launch_pdl(add_layernorm_bwd_kernel<VPL>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, a)));
+  const int grid = bwd_grid(rows, 2);
+  const size_t smem = static_cast<size_t>(kWarpsPerBlock) * 3 * d * sizeof(float);  // 96 KB at d = 1024: two CTAs per SM
+  VB_DISPATCH_VPL(d, {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(add_layernorm_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kWarpsPerBlock * 3 * VPL * 256 * static_cast<int>(sizeof(float)));
+      if (e != cudaSuccess) return fail(VACNIC_ECUDA, "add_layernorm_bwd: smem attribute: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    launch_pdl(add_layernorm_bwd_kernel<VPL>, dim3(grid), dim3(kWarpsPerBlock * 32), smem, s, a);
+  });
   count_launch();
   return check_last("add_layernorm_bwd");
 }
@@ -668,7 +671,7 @@ extern "C" int vacnic_embed_ln_bwd(const void* dy, const int64_t* ids, const voi
   a.rng = reinterpret_cast<const unsigned long long*>(rng_state); a.salt = salt;
   a.pos_ids = pos_ids;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = bwd_grid(rows);
+  const int grid = bwd_grid(rows, 1);
   VB_DISPATCH_VPL(d, (embed_ln_bwd_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(a)));
   count_launch();
   return check_last("embed_ln_bwd");

@@ -275,6 +275,30 @@ __device__ __forceinline__ bool keep_elem(uint32_t seed, uint32_t salt, uint64_t
   h = hash32(h ^ (static_cast<uint32_t>(idx >> 32) + salt * 0x7F4A7C15u));
   return h >= thresh;
 }
+// Two keep decisions per counter hash (16-bit fields): for the LayerNorm kernels, whose instruction count is dominated by
+// the generator (two hash rounds per element were 53 % of the forward's and 39 % of the backward's instructions).  p is
+// quantised to 1/65536 (0.1 -> 0.10000610); the kernels scale by the matching 65536 / (65536 - t16).
+__host__ __device__ inline uint32_t drop_thresh16(float p) {
+  const double t = static_cast<double>(p) * 65536.0 + 0.5;
+  return t >= 65535.0 ? 65535u : static_cast<uint32_t>(t);
+}
+__device__ __forceinline__ uint32_t keep_pair(uint32_t seed, uint32_t salt, uint64_t pair, uint32_t t16) {
+  uint32_t h = hash32(static_cast<uint32_t>(pair) * 0x9E3779B1u + seed);
+  h = hash32(h ^ (static_cast<uint32_t>(pair >> 32) + salt * 0x7F4A7C15u));
+  return ((h & 0xffffu) >= t16 ? 1u : 0u) | ((h >> 16) >= t16 ? 2u : 0u);  // bit 0: element 2*pair, bit 1: element 2*pair + 1
+}
+// keep bits of the d/32 elements one lane holds of a row (vector lane + 32 j, element e -> bit j*8 + e; d <= 1024)
+template <int VPL>
+__device__ __forceinline__ uint32_t keep_row_bits(uint32_t seed, uint32_t salt, long long row, int d, int lane, uint32_t t16) {
+  uint32_t keep = 0u;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const uint64_t pair0 = (static_cast<uint64_t>(row) * d + (lane + 32 * j) * 8) >> 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) keep |= keep_pair(seed, salt, pair0 + q, t16) << (j * 8 + q * 2);
+  }
+  return keep;
+}
 __host__ __device__ inline uint32_t drop_thresh(float p) {
   double t = static_cast<double>(p) * 4294967296.0;
   return t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
