@@ -430,6 +430,8 @@ def main():
                    use_graph=not args.no_graph, process_group=None if args.exchange == "none" else pg,
                    pipeline_optimizer=False if args.no_pipeline_opt else None,
                    exchange=None if args.exchange in ("auto", "none") else args.exchange, varlen=not args.no_varlen)
+    config["prefix_side_stream"] = ts.side_stream is not None
+    config["guide_stream"] = ts.guide_stream is not None
     config["exchange"] = ts.exchange if (world > 1 and args.exchange != "none") else ("none" if world > 1 else "single GPU")
 
     n_batches = 4

@@ -62,6 +62,26 @@ def test_generate_ids_match_reference_generate(cuda_device, path, use_graph):
     assert bool((b2 == b).all())
 
 
+FULLSIZE = os.path.join(os.path.dirname(__file__), "golden", "fullsize", "large_full_gen.pt")
+
+
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "graph"])
+def test_fullsize_generate_ids_match_reference_generate(cuda_device, use_graph):
+    """BASELINE.json configs[2] at full size -- BART-large VACNIC (12 + 12 layers), a ragged L = 1024 batch, greedy and
+    beam 4 / length_penalty 2.0 / max_length 50: the token ids equal, EXACTLY, the ids the unmodified reference class
+    produced through transformers' real `generate()` on the same weights (tests/golden/make_golden_fullsize.py, margin-
+    vetted against logit noise of the size of the bf16 error at this depth)."""
+    from vacnic_b200 import generation
+    fx, cfg, m, batch = _build(FULLSIZE, cuda_device)
+    assert cfg.enc_layers == 12 and cfg.dec_layers == 12 and batch["article_ids"].shape[1] == 1024 and fx["max_length"] == 50
+    kw = _gen_kwargs(cfg, batch)
+    g = generation.generate(m, num_beams=1, max_length=fx["max_length"], use_graph=use_graph, **kw).cpu()
+    assert g.shape == fx["greedy_ids"].shape and bool((g == fx["greedy_ids"]).all()), (g, fx["greedy_ids"])
+    b = generation.generate(m, num_beams=fx["num_beams"], max_length=fx["max_length"], length_penalty=fx["length_penalty"],
+                            use_graph=use_graph, **kw).cpu()
+    assert b.shape == fx["beam4_ids"].shape and bool((b == fx["beam4_ids"]).all()), (b, fx["beam4_ids"])
+
+
 # ---------------------------------------------------------------------------------------------- search kernels
 @pytest.mark.parametrize("C,nb,V,max_len,eos_boost,lp", [(5, 4, 97, 12, 0.0, 2.0), (7, 4, 50267, 16, 9.0, 2.0),
                                                           (3, 2, 1000, 9, 3.0, 1.0), (4, 8, 300, 10, 2.0, 0.5),

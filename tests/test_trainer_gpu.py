@@ -9,9 +9,9 @@ from vacnic_b200 import spec, synthetic
 pytestmark = pytest.mark.gpu
 
 
-def _models(dev, seed=41):
+def _models(dev, seed=41, max_pos=128):
     from vacnic_b200.modeling import VacnicBart
-    cfg = spec.VacnicConfig(d_model=768, heads=12, ffn=1024, enc_layers=2, dec_layers=2, prompt_size=4, max_pos=128)
+    cfg = spec.VacnicConfig(d_model=768, heads=12, ffn=1024, enc_layers=2, dec_layers=2, prompt_size=4, max_pos=max_pos)
     gcfg = spec.VacnicConfig(**{**cfg.as_dict(), "stock": True})
     sd, gsd = spec.test_state_dict(cfg, seed), spec.test_state_dict(gcfg, seed + 100)
     m = VacnicBart(cfg, device=dev, p_drop=0.0)
@@ -129,3 +129,42 @@ def test_plain_loop_still_works_after_a_trainstep_used_the_model(cuda_device):
     z = m.store.z_begin
     denom = grads[0][z:].abs().max().item()
     assert denom > 0 and (grads[0][z:] - grads[1][z:]).abs().max().item() <= 1e-3 * denom   # not doubled
+
+
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "graph"])
+@pytest.mark.parametrize("varlen", [False, True], ids=["padded", "packed"])
+def test_side_streams_give_the_single_stream_step(cuda_device, use_graph, varlen):
+    """The prefix side of the encoder on a second stream (BartEncoder.forward, TrainStep(side_stream=True)) and the frozen
+    guide's forward on a third (TrainStep(guide_stream=True)) change the schedule of the kernels, not their arithmetic:
+    losses and gradients of every step, and the weights after three steps, equal the single-stream run up to the fp32
+    atomics of the bias / LayerNorm gradients."""
+    from vacnic_b200.trainer import TrainStep
+    batch = synthetic.make_batch(B=3, L=72, T=12, seed=19)
+    runs = []
+    for side, gstream in ((False, False), (False, False), (True, False), (False, True), (True, True)):
+        cfg, gcfg, sd, gsd, m, g = _models(cuda_device, max_pos=1024)
+        # small learning rate: the comparison is about the schedule of the kernels, not about how fast three Adam steps at
+        # lr 1e-3 amplify the last-bit noise of the fp32 atomics
+        ts = TrainStep(m, g, lr=2e-5, weight_decay=0.01, use_graph=use_graph, varlen=varlen, side_stream=side,
+                       guide_stream=gstream)
+        assert (ts.side_stream is not None) == side and (ts.guide_stream is not None) == gstream
+        losses, grads = [], []
+        for _ in range(3):
+            losses.append({k: float(v.detach()) for k, v in ts.step(batch).items()})
+            torch.cuda.synchronize()
+            grads.append(m.store.grad.clone())
+        assert not m.rt.keepalive and m.rt.side_stream is None
+        runs.append((losses, grads, m.store.master.clone()))
+    l0, g0, p0 = runs[0]
+    # runs[1] repeats the single-stream run: its distance from runs[0] is the run-to-run noise of the fp32 atomics
+    noise = max((g0[i] - runs[1][1][i]).abs().max().item() for i in range(3))
+    scale = max(g.abs().max().item() for g in g0)
+    for l1, g1, p1 in runs[2:]:
+        for a, b in zip(l0, l1):
+            for k in a:
+                assert abs(a[k] - b[k]) <= 1e-3 * max(1.0, abs(a[k])), (k, l0, l1)
+        for i in range(3):   # every step: the same gradient, element by element, within a few times the run-to-run noise
+            err = (g0[i] - g1[i]).abs().max().item()
+            assert err <= max(4 * noise, 1e-4 * scale), (i, err, noise, scale)
+            assert torch.nn.functional.cosine_similarity(g0[i], g1[i], dim=0).item() >= 0.99999
+        assert (p0 - p1).abs().mean().item() <= 1e-6

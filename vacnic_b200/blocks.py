@@ -37,6 +37,10 @@ class Runtime:
         self.res_fp32 = True
         # requires-grad root every block of a forward pass hangs off (store.anchor, or its ParamTouchFn image under DDP)
         self.fwd_anchor = store.anchor
+        # optional second stream for the prefix side of the encoder (set by the owner of the step, who also joins it after
+        # the backward pass and then clears `keepalive`: the tensors that crossed the two streams in this step)
+        self.side_stream = None
+        self.keepalive = []
 
     def new_salt(self) -> int:
         self._salt += 1

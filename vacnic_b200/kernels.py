@@ -11,13 +11,24 @@ from .lib import (ACT_GELU, ACT_NONE, ACT_QUICKGELU, ACT_TANH, DT_BF16, DT_F32, 
                   MASK_NONE, AttnDesc, GemmDesc, check, lib, ptr, stream_ptr)
 
 
-_WORKSPACES = {}  # device index -> zero-initialised split-K scratch of vacnic_gemm (GEMMs of one device are
-# issued on one stream at a time: eager stream, capture stream and graph replays never overlap)
+_WORKSPACES = {}  # (device index, stream slot) -> zero-initialised split-K scratch of vacnic_gemm.  GEMMs of one device are
+# issued on one stream at a time (eager stream, capture stream and graph replays never overlap) -- except the prefix side
+# stream of the encoder (BartEncoder.forward), which runs beside the main stream and therefore owns a scratch of its own
 SPLIT_K_BYTES = 64 << 20
+_SIDE_STREAMS = set()  # cudaStream_t handles registered by register_side_stream
+
+
+def register_side_stream(stream: "torch.cuda.Stream"):
+    """Give `stream` its own split-K scratch (allocated and zeroed here, outside any capture)."""
+    _SIDE_STREAMS.add(stream.cuda_stream)
+    key = (stream.device.index, stream.cuda_stream)
+    if key not in _WORKSPACES:
+        _WORKSPACES[key] = torch.zeros(SPLIT_K_BYTES, dtype=torch.uint8, device=stream.device)
 
 
 def _gemm_workspace(device):
-    key = device.index
+    cur = torch.cuda.current_stream(device).cuda_stream
+    key = (device.index, cur if cur in _SIDE_STREAMS else 0)
     ws = _WORKSPACES.get(key)
     if ws is None:
         if torch.cuda.is_current_stream_capturing():

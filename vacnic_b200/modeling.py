@@ -137,9 +137,17 @@ class BartEncoderLayer(nn.Module):
         """BartEncoderLayer.forward with every layer a fusion layer (MFULL:645-744 / MVIS:591-690).  Every state is a
         pair (bf16 tensor the GEMMs read, fp32 copy carried as the residual -- or None).  `pack` (varlen.ArticlePack):
         the article rows `h` are packed [1, rows, d]; the attention kernels get row ranges instead of `key_mask`."""
+        kv, img, face, ner = self.side(img, face, ner, face_name_mask)
+        return self.main(h, key_mask, kv, pack), face, ner, img
+
+    def side(self, img=None, face=None, ner=None, face_name_mask=None):
+        """The prefix side of the layer (MFULL:645-693): image FFN, face FFN, name attention over [faces; names], NER-prefix
+        map.  It reads and writes only the img / face / ner states -- never the article rows -- so the side chains of all
+        layers form one dependency chain of their own, which the encoder may run on a second stream (BartEncoder.forward).
+        Returns (kv, img, face, ner): kv = the prefix rows this layer's article rows cross-attend to."""
         rt, cfg, H = self.rt, self.cfg, self.cfg.heads
         kv = None
-        (h, h32), (img, img32), (face, face32), (ner, ner32) = h, img or (None, None), face or (None, None), ner or (None, None)
+        (img, img32), (face, face32), (ner, ner32) = img or (None, None), face or (None, None), ner or (None, None)
         if not cfg.stock:
             img, img32 = Bk.MlpBlockFn.apply(img, img32, rt.fwd_anchor, rt, self.lin_iup, self.lin_idown, K.ACT_GELU, self.ln_img)
             img_kv, img = Bk.fanout(img, 2)
@@ -156,6 +164,12 @@ class BartEncoderLayer(nn.Module):
                 kv = Bk.Concat2Fn.apply(img_kv, prefix)
             else:
                 kv = img_kv
+        return kv, (img, img32), (face, face32), (ner, ner32)
+
+    def main(self, h, key_mask, kv, pack=None):
+        """The article side of the layer (MFULL:695-744): self-attention, cross-attention to the prefix rows `kv`, FFN."""
+        rt, cfg, H = self.rt, self.cfg, self.cfg.heads
+        h, h32 = h
         a = self.self_attn
         h, h32 = Bk.AttnBlockFn.apply(h, h32, None, None, rt, a.lin_qkv, None, None, a.lin_o, a.ln, H,
                                       key_mask if pack is None else pack.self_mask, False, True, 0, None, False)
@@ -164,7 +178,7 @@ class BartEncoderLayer(nn.Module):
             h, h32 = Bk.AttnBlockFn.apply(h, h32, kv, None, rt, None, a.lin_q, a.lin_kv, a.lin_o, a.ln, H,
                                           None if pack is None else pack.prefix_mask, False, True, 0, None, False)
         h, h32 = Bk.MlpBlockFn.apply(h, h32, rt.fwd_anchor, rt, self.lin_fc1, self.lin_fc2, K.ACT_GELU, self.ln_final)
-        return (h, h32), (face, face32), (ner, ner32), (img, img32)
+        return (h, h32)
 
 
 class BartDecoderLayer(nn.Module):
@@ -265,26 +279,57 @@ class BartEncoder(nn.Module):
             key_mask = Bk.KeyMask(attention_mask)
             h = Bk.EmbedFn.apply(rt.fwd_anchor, input_ids.contiguous(), rt, self.embed_tokens.weight, self.embed_positions.weight,
                                  self.ln_emb, 2, cfg.pad_token_id)
-        img = face = ner = fn_mask = None
-        if not cfg.stock:
-            if not cfg.only_image:
-                ner = Bk.EmbedFn.apply(rt.fwd_anchor, name_ids.contiguous(), rt, self.embed_tokens_ner.weight,
-                                       self.embed_positions_ner.weight, self.ln_emb_ner, 2, cfg.pad_token_id)
-                fn_mask = Bk.KeyMask(torch.cat((face_mask, name_mask), dim=1))  # MFULL:1262
-                face = (Bk.LinearFn.apply(face_features.to(torch.bfloat16), rt.fwd_anchor, rt, self.lin_face, torch.bfloat16, False,
-                                          None, None), None)
-            z, _ = Bk.MlpBlockFn.apply(image_features.to(torch.bfloat16), None, rt.fwd_anchor, rt, self.lin_p0, self.lin_p2,
-                                       K.ACT_TANH, None)
-            img = z.view(B, cfg.prompt_size, CLIP_DIM)  # MFULL:1276
-            if cfg.d_model == 1024:
-                img = Bk.LinearFn.apply(img, rt.fwd_anchor, rt, self.lin_vmap, torch.bfloat16, True, None, None)
-            img = (img, None)
+        # The prefix side (ClipCap MLP, visual_map, name / face embeddings and the img / face / ner chain of every layer)
+        # never reads the article rows: with `rt.side_stream` set (TrainStep, VACNIC_SIDE_STREAM) it is enqueued as a whole
+        # on a second, high-priority stream and the article side of layer i only waits for that layer's prefix rows, so its
+        # ~25 small latency-bound kernels per layer run in the wave tails of the article-side GEMMs instead of between them.
+        # The autograd engine runs each backward node on the stream of its forward, so the backward pass forks the same way.
+        side = rt.side_stream if (not cfg.stock and torch.is_grad_enabled()) else None
+        main = torch.cuda.current_stream()
+        if side is not None:
+            side.wait_stream(main)
+        kvs = []
+        with torch.cuda.stream(side if side is not None else main):
+            img = face = ner = fn_mask = None
+            if not cfg.stock:
+                if not cfg.only_image:
+                    ner = Bk.EmbedFn.apply(rt.fwd_anchor, name_ids.contiguous(), rt, self.embed_tokens_ner.weight,
+                                           self.embed_positions_ner.weight, self.ln_emb_ner, 2, cfg.pad_token_id)
+                    fn_mask = Bk.KeyMask(torch.cat((face_mask, name_mask), dim=1))  # MFULL:1262
+                    face = (Bk.LinearFn.apply(face_features.to(torch.bfloat16), rt.fwd_anchor, rt, self.lin_face, torch.bfloat16,
+                                              False, None, None), None)
+                z, _ = Bk.MlpBlockFn.apply(image_features.to(torch.bfloat16), None, rt.fwd_anchor, rt, self.lin_p0, self.lin_p2,
+                                           K.ACT_TANH, None)
+                img = z.view(B, cfg.prompt_size, CLIP_DIM)  # MFULL:1276
+                if cfg.d_model == 1024:
+                    img = Bk.LinearFn.apply(img, rt.fwd_anchor, rt, self.lin_vmap, torch.bfloat16, True, None, None)
+                img = (img, None)
+            if side is not None:
+                for layer in self.layers:
+                    kv, img, face, ner = layer.side(img, face, ner, fn_mask)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    kvs.append((kv, ev))
+                # tensors that cross the two streams stay referenced until the step is over (rt.keepalive is cleared by the
+                # owner of the step after the streams have joined): the caching allocator recycles a block on the stream
+                # that allocated it as soon as the last reference dies, which the OTHER stream's pending kernels cannot see
+                rt.keepalive += [t for kv, _ in kvs for t in (kv,)] + [t for pair in (img, face, ner) if pair for t in pair
+                                                                       if t is not None]
+                if fn_mask is not None:
+                    rt.keepalive += [fn_mask.mask, fn_mask.len]
         states = []
         for i, layer in enumerate(self.layers):
             if output_hidden_states:
                 states.append(h[0])
             h = (Bk.grad_mark(h[0], rt, ("enc", i)), h[1])  # backward: gradients of encoder layers >= i are final
-            h, face, ner, img = layer(h, key_mask, img, face, ner, fn_mask, pack)
+            if side is not None:
+                kv, ev = kvs[i]
+                main.wait_event(ev)
+                h = layer.main(h, key_mask, kv, pack)
+            else:
+                h, face, ner, img = layer(h, key_mask, img, face, ner, fn_mask, pack)
+        if side is not None:
+            main.wait_stream(side)  # the final img / face / ner states are read on the main stream from here on
         h, img, face, ner = h[0], img and img[0], face and face[0], ner and ner[0]
         if output_hidden_states:
             states.append(h)

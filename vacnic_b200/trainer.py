@@ -22,6 +22,10 @@ from .modeling import VacnicBart, shift_tokens_right
 from .varlen import ArticlePack, pack_articles
 
 
+SIDE_STREAM_DEFAULT = "1"
+GUIDE_STREAM_DEFAULT = "1"
+
+
 def linear_schedule(step: int, warmup: int, total: int) -> float:
     """transformers.get_linear_schedule_with_warmup (TRAIN:102): multiplier applied to the base lr."""
     if step < warmup:
@@ -34,7 +38,8 @@ class TrainStep:
                  betas=(0.9, 0.999), eps: float = 1e-8, warmup_steps: int = 0, total_steps: int = 1_000_000,
                  margin: float = 1.0, alpha: float = 0.5, secla_weight: float = 1.0, use_graph: bool = True,
                  process_group=None, pipeline_optimizer: Optional[bool] = None, max_grad_norm: Optional[float] = None,
-                 exchange: Optional[str] = None, varlen: bool = False):
+                 exchange: Optional[str] = None, varlen: bool = False, side_stream: Optional[bool] = None,
+                 guide_stream: Optional[bool] = None):
         """`exchange` (world > 1): "p2p" = rank-sharded optimizer over NVLink peer memory (one fused reduce-scatter + AdamW +
         all-gather kernel per bucket, csrc/dp.cu; needs the model's store in symmetric memory), "p2p-mc" = the same through
         the NVSwitch multicast object (multimem.ld_reduce / multimem.st), "nccl" = in-place NCCL all-reduce of the fp32
@@ -120,6 +125,21 @@ class TrainStep:
         env_serial, env_overlap = os.environ.get("VACNIC_DP_SERIAL"), os.environ.get("VACNIC_DP_OVERLAP")
         self.overlap = (self.p2p is None) if (env_serial is None and env_overlap is None) else (
             env_overlap == "1" if env_overlap is not None else env_serial != "1")
+        # Prefix side of the encoder on a second (high-priority) stream, forward and backward (BartEncoder.forward).  Not with
+        # exchange overlap: the backward-pass markers describe the main stream only.  VACNIC_SIDE_STREAM=0/1 overrides.
+        self.side_stream = None
+        want_side = (os.environ.get("VACNIC_SIDE_STREAM", SIDE_STREAM_DEFAULT) == "1") if side_stream is None else bool(side_stream)
+        if want_side and not self.cfg.stock and not (self.buckets is not None and self.overlap):
+            self.side_stream = torch.cuda.Stream(device=dev, priority=-1)
+            K.register_side_stream(self.side_stream)
+        # The frozen guide's forward (no gradient, independent of the model until the CoLaM loss) on a stream of its own,
+        # enqueued BEFORE the model's forward: its latency-bound decoder kernels (1024 rows) then run beside the model's
+        # encoder GEMMs and its encoder GEMMs beside the model's decoder.  VACNIC_GUIDE_STREAM=0/1 overrides.
+        self.guide_stream = None
+        want_g = (os.environ.get("VACNIC_GUIDE_STREAM", GUIDE_STREAM_DEFAULT) == "1") if guide_stream is None else bool(guide_stream)
+        if want_g and guide is not None:
+            self.guide_stream = torch.cuda.Stream(device=dev)
+            K.register_side_stream(self.guide_stream)
         self._g_txt = torch.ones(1, device=dev)
         self._g_margin = torch.full((1,), alpha, device=dev)
         self._g_secla = torch.full((1,), secla_weight, device=dev)
@@ -152,6 +172,16 @@ class TrainStep:
             self.buckets.begin_step()
             self._ready = []
         model.rt.rng.advance()
+        model.rt.side_stream = self.side_stream
+        try:
+            return self._fwd_bwd_update(b, dry)
+        finally:
+            model.rt.side_stream = None
+            model.rt.keepalive.clear()
+
+    def _fwd_bwd_update(self, b: Dict[str, torch.Tensor], dry: bool):
+        model, guide, cfg = self.model, self.guide, self.cfg
+        st = model.store
         src, tgt = b["article_ids"], b["caption_ids"]
         dec_in = b["decoder_input_ids"]
         pack = None
@@ -165,13 +195,23 @@ class TrainStep:
         if not cfg.only_image:
             kw.update(face_features=b["face_emb"], face_mask=b["face_mask"], name_ids=b["names_art_ids"],
                       name_mask=b["name_mask"])
+        gout, gs = None, self.guide_stream
+        gkw = dict(input_ids=src, attention_mask=b["src_mask"], decoder_input_ids=dec_in, article_pack=pack,
+                   need_logits=False)  # only decoder_hidden_states[-1] is read (TRAIN:293-296)
+        if guide is not None and gs is not None:
+            gs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(gs), torch.no_grad():
+                gout = guide(**gkw)
         out = model(**kw)
         heads, grads = [out["loss"]], [self._g_txt]
         losses = {"txt": out["loss"]}
         if guide is not None:
-            with torch.no_grad():
-                gout = guide(input_ids=src, attention_mask=b["src_mask"], decoder_input_ids=dec_in, article_pack=pack,
-                             need_logits=False)  # only decoder_hidden_states[-1] is read (TRAIN:293-296)
+            if gout is None:
+                with torch.no_grad():
+                    gout = guide(**gkw)
+            else:  # join; `gout` (allocated on the guide's stream, read on this one) stays referenced until the step returns
+                torch.cuda.current_stream().wait_stream(gs)
+                model.rt.keepalive.append(gout["decoder_hidden_states"][-1])
             margin = Bk.ColamFn.apply(out["decoder_hidden_states"][-1], gout["decoder_hidden_states"][-1], tgt, self.margin,
                                       cfg.pad_token_id)
             heads.append(margin); grads.append(self._g_margin)
@@ -184,6 +224,8 @@ class TrainStep:
             heads.append(secla); grads.append(self._g_secla)
             losses["secla"] = secla
         torch.autograd.backward(heads, grads)
+        if self.side_stream is not None:  # join: the prefix side's backward nodes ran on the side stream
+            torch.cuda.current_stream().wait_stream(self.side_stream)
         st.finish_backward()
         if dry:
             return losses
