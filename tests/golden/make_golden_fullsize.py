@@ -7,6 +7,12 @@ BASELINE.json configs[2] sizes: BART-large VACNIC (12 + 12 layers, ffn 4096, P =
 articles (`synthetic.make_batch(B=2, L=1024)`: row 0 fills all 1024 positions, row 1 is shorter and right-padded), greedy
 and beam 4 / length_penalty 2.0 / max_length 50.
 
+A random-init BART this deep decodes ONE token whatever the input (the common component of the last hidden state picks
+it with a lead of several logits), which would make the fixture blind.  `final_logits_bias` -- a buffer of the checkpoint,
+MFULL:1997 -- is therefore set so that the LEVEL_TOP tokens with the largest position-averaged logit start level, well above
+the rest of the vocabulary: which of them wins at a step then depends on the article, the image / face / name inputs and
+the position through the whole encoder-decoder stack.  The bias entries are stored in the fixture.
+
 `search` walks batch seeds until the ids the (reference-pinned) oracle decodes are robust to logit noise of the size of
 the bf16 logit error at this depth: a cheap pre-filter (every greedy decision must win by more than the noise amplitude)
 and then 10 noisy re-decodings, greedy and beam, that must all reproduce the noise-free ids.  `emit` then builds the
@@ -32,6 +38,7 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fullsize")
 NAME = "large_full_gen"
 WEIGHT_SEED, LM_SCALE, EOS_BIAS = 31, 8.0, 0.0
 L, MAX_LEN, NB, LP, B = 1024, 50, 4, 2.0, 2
+LEVEL_TOP, LEVEL_LIFT, CAL_SEED = 3, 8.0, 7
 AMP = 1e-2 * LM_SCALE   # uniform logit noise amplitude (sigma 5.8e-3 * lm_scale; bf16 logit error at this size: mean-abs 3.6e-3)
 TRIALS = 10
 
@@ -90,13 +97,22 @@ def vet(sd, cfgd, batch):
 def weights(cfg):
     sd = spec.test_state_dict(cfg, WEIGHT_SEED, lm_scale=LM_SCALE)
     sd["final_logits_bias"][0, cfg.eos_token_id] = EOS_BIAS
-    return sd
+    # level the leading tokens (module docstring): teacher-forced logits of a calibration batch, averaged over positions
+    inp = enc_inputs_of(make_row(CAL_SEED))
+    dec_in = torch.randint(3, 50000, (B, MAX_LEN - 1), generator=torch.Generator().manual_seed(5))
+    dec_in[:, 0] = cfg.decoder_start_token_id
+    with torch.no_grad():
+        mean = OM.model_forward(sd, cfg.as_dict(), decoder_input_ids=dec_in, **inp)["logits"].float().mean((0, 1))
+    top = mean.topk(LEVEL_TOP)
+    idx, val = top.indices, (top.values[0] - top.values) + LEVEL_LIFT
+    sd["final_logits_bias"][0, idx] += val
+    return sd, idx, sd["final_logits_bias"][0, idx].clone()
 
 
 def search(worker, nworkers):
     torch.set_num_threads(max(1, (os.cpu_count() - 2) // nworkers))   # two cores stay free for the rest of the build
     cfg = spec.bart_large()
-    sd = weights(cfg)
+    sd, _, _ = weights(cfg)
     found = os.path.join(OUT, "found_seed.json")
     t0 = time.time()
     for attempt in range(worker, 100000, nworkers):
@@ -116,7 +132,7 @@ def emit(seed):
     from make_golden import build_reference
     torch.set_num_threads(os.cpu_count())
     cfg = spec.bart_large()
-    sd = weights(cfg)
+    sd, bias_idx, bias_val = weights(cfg)
     batch = make_row(seed)
     inp = enc_inputs_of(batch)
     m = build_reference(cfg, sd)
@@ -129,13 +145,14 @@ def emit(seed):
     assert og.shape == ids_g.shape and bool((og == ids_g).all()), ("greedy ids differ", og, ids_g)
     assert ob.shape == ids_b.shape and bool((ob == ids_b).all()), ("beam ids differ", ob, ids_b)
     fx = dict(case=NAME, cfg=cfg.as_dict(), batch_kwargs=dict(B=B, L=L, T=8, seed=seed), weight_seed=WEIGHT_SEED,
-              lm_scale=LM_SCALE, eos_bias=EOS_BIAS, max_length=MAX_LEN, num_beams=NB, length_penalty=LP,
+              lm_scale=LM_SCALE, eos_bias=EOS_BIAS, logit_bias_idx=bias_idx, logit_bias_val=bias_val, max_length=MAX_LEN, num_beams=NB, length_penalty=LP,
               vetted_logit_noise=AMP, article_len=inp["attention_mask"].sum(-1).tolist(),
               weight_checksum=float(sum(v.double().sum() for k, v in sd.items() if k not in spec.TIED_TO_SHARED)),
               batch_checksum=float(sum(v.double().sum() for v in batch.values())),
               greedy_ids=ids_g, beam4_ids=ids_b, torch_version=torch.__version__)
     os.makedirs(OUT, exist_ok=True)
     torch.save(fx, os.path.join(OUT, NAME + ".pt"))
+    print("distinct tokens: greedy", ids_g.unique().numel(), "beam", ids_b.unique().numel())
     print(NAME, "ok: article length", fx["article_len"], "greedy", ids_g.tolist(), "beam4", ids_b.tolist(), flush=True)
 
 

@@ -28,6 +28,8 @@ def _build(path, dev):
     cfg = spec.VacnicConfig(**fx["cfg"])
     sd = spec.test_state_dict(cfg, fx["weight_seed"], lm_scale=fx["lm_scale"])
     sd["final_logits_bias"][0, cfg.eos_token_id] = fx.get("eos_bias", 0.0)
+    if "logit_bias_idx" in fx:   # full-size fixture: levelled leading tokens (tests/golden/make_golden_fullsize.py)
+        sd["final_logits_bias"][0, fx["logit_bias_idx"]] = fx["logit_bias_val"]
     m = VacnicBart(cfg, device=dev, p_drop=0.0)
     m.load_reference_state_dict(sd)
     m.eval()
@@ -60,6 +62,39 @@ def test_generate_ids_match_reference_generate(cuda_device, path, use_graph):
     # a second call replays the cached engine and must give the same answer
     b2 = generation.generate(m, num_beams=4, max_length=fx["max_length"], length_penalty=2.0, use_graph=use_graph, **kw).cpu()
     assert bool((b2 == b).all())
+
+
+@pytest.mark.parametrize("nb,lp", [(4, 2.0), (1, 1.0)], ids=["beam4", "greedy"])
+@pytest.mark.parametrize("lanes", [2, 4])
+def test_decode_lanes_give_the_single_lane_ids(cuda_device, nb, lp, lanes):
+    """Decode lanes (captions cut into groups with their own state, step graph and stream) change the schedule, not the
+    search: ids and scores equal the one-lane engine's, also when the lanes stop at different lengths (EOS-biased head)."""
+    from vacnic_b200 import generation
+    from vacnic_b200.modeling import VacnicBart
+    dev = cuda_device
+    cfg = spec.VacnicConfig(d_model=768, heads=12, ffn=1024, enc_layers=2, dec_layers=2, prompt_size=4, max_pos=128)
+    sd = spec.test_state_dict(cfg, 21, lm_scale=8.0)
+    sd["final_logits_bias"][0, cfg.eos_token_id] = 15.0
+    m = VacnicBart(cfg, device=dev, p_drop=0.0)
+    m.load_reference_state_dict(sd)
+    m.eval()
+    C, L, max_len = 64, 48, 24
+    batch = synthetic.to_device(synthetic.make_batch(B=C, L=L, T=8, seed=77), dev)
+    kw = _gen_kwargs(cfg, batch)
+    enc_in = generation._enc_inputs(m, kw["input_ids"], kw["attention_mask"], kw["image_features"], kw.get("face_features"),
+                                    kw.get("face_mask"), kw.get("name_ids"), kw.get("name_mask"))
+    one = generation.Generator(m, C, nb, L, max_len, length_penalty=lp, use_graph=True, lanes=1)
+    many = generation.Generator(m, C, nb, L, max_len, length_penalty=lp, use_graph=True, lanes=lanes)
+    assert one.n_lanes == 1 and many.n_lanes == lanes
+    want = one.generate(enc_in)
+    for _ in range(2):   # the second call replays the captured lane graphs
+        got = many.generate(enc_in)
+        assert got.shape == want.shape and bool((got == want).all()), (got, want)
+        if nb > 1:
+            assert torch.equal(many.sequences_len, one.sequences_len)
+            assert torch.allclose(many.sequences_scores, one.sequences_scores, rtol=0, atol=1e-3)
+    lens = (want != cfg.pad_token_id).sum(1)
+    assert int(lens.min()) < int(lens.max())   # the case does exercise captions of different lengths
 
 
 FULLSIZE = os.path.join(os.path.dirname(__file__), "golden", "fullsize", "large_full_gen.pt")

@@ -15,6 +15,7 @@ the graph and polls a stop flag every few steps.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -22,11 +23,47 @@ import torch
 from . import kernels as K
 
 
+DECODE_LANES_DEFAULT = "1"
+
+
+class _Lane:
+    """Captions [c0, c1) of a Generator: row-slice views of its buffers, own search state, step graph and stream."""
+
+    def __init__(self, g: "Generator", c0: int, c1: int, dev, multi: bool):
+        nb = g.nb
+        r0, r1 = c0 * nb, c1 * nb
+        self.c0, self.c1, self.C, self.R = c0, c1, c1 - c0, r1 - r0
+        for name in ("x", "x2", "attn", "proj", "qb", "x32", "x32b", "qkv", "h", "logits", "top_lp", "top_idx"):
+            setattr(self, name, getattr(g, name)[r0:r1])
+        self.kc, self.vc = g.kc[:, r0:r1], g.vc[:, r0:r1]            # [layer][rows][maxT][d]: kc[l] is contiguous
+        self.cross_kv = g.cross_kv[:, c0:c1]                          # [layer][captions][k|v][head][L][64]
+        self.key_mask, self.key_len = g.key_mask[c0:c1], g.key_len[c0:c1]
+        bf, f32, i32, u8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
+        C, maxT = self.C, g.maxT
+
+        def buf(*shape, dtype=bf):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        st: Dict[str, torch.Tensor] = {"cur_len": buf(1, dtype=i32), "flags": buf(maxT + 1, 2, dtype=i32)}
+        if nb > 1:
+            st.update(run_seq=buf(2, C, nb, maxT, dtype=i32), run_anc=buf(2, C, nb, maxT, dtype=i32),
+                      run_score=buf(2, C, nb, dtype=f32), fin_seq=buf(2, C, nb, maxT, dtype=i32),
+                      fin_score=buf(2, C, nb, dtype=f32), fin_len=buf(2, C, nb, dtype=i32),
+                      fin_flag=buf(2, C, nb, dtype=u8), unsat=buf(C, dtype=u8))
+        else:
+            st.update(seq=buf(C, maxT, dtype=i32), unfinished=buf(C, dtype=u8))
+        self.st = st
+        self.flags_host = torch.zeros(g.max_len + 1, 2, dtype=torch.int32).pin_memory()
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.stream = torch.cuda.Stream(device=dev) if multi else None
+        self.t, self.stop_t, self.pending, self.done = 1, None, None, False
+
+
 class Generator:
     """Decode engine specialised for (captions, beams, article length, max_length) on one model."""
 
     def __init__(self, model, captions: int, beams: int, L: int, max_length: int, length_penalty: float = 1.0,
-                 use_graph: bool = True, poll_every: int = 4, varlen: bool = True):
+                 use_graph: bool = True, poll_every: int = 4, varlen: bool = True, lanes: Optional[int] = None):
         cfg = model.cfg
         if max_length < 2 or max_length > 256:
             raise ValueError("max_length must be in 2..256")
@@ -43,7 +80,6 @@ class Generator:
         # packed (varlen) article rows through the encoder: the padding of the batch never enters a GEMM / LayerNorm /
         # attention tile (vacnic_b200.varlen); the memory is un-packed once for the per-caption cross K/V projection
         self.varlen = bool(varlen)
-        self.flags_host = torch.zeros(max_length + 1, 2, dtype=torch.int32).pin_memory()
         dev = model.store.device
         d, f, V = cfg.d_model, cfg.ffn, cfg.vocab
         R, nl = self.R, cfg.dec_layers
@@ -66,40 +102,54 @@ class Generator:
         self.Kc = 2 * beams if beams > 1 else 1
         self.top_lp = buf(R, self.Kc, dtype=f32)
         self.top_idx = buf(R, self.Kc, dtype=i32)
-        st: Dict[str, torch.Tensor] = {"cur_len": buf(1, dtype=i32), "flags": buf(self.maxT + 1, 2, dtype=i32)}
-        if beams > 1:
-            st.update(run_seq=buf(2, captions, beams, self.maxT, dtype=i32), run_anc=buf(2, captions, beams, self.maxT, dtype=i32),
-                      run_score=buf(2, captions, beams, dtype=f32), fin_seq=buf(2, captions, beams, self.maxT, dtype=i32),
-                      fin_score=buf(2, captions, beams, dtype=f32), fin_len=buf(2, captions, beams, dtype=i32),
-                      fin_flag=buf(2, captions, beams, dtype=u8), unsat=buf(captions, dtype=u8))
-        else:
-            st.update(seq=buf(captions, self.maxT, dtype=i32), unfinished=buf(captions, dtype=u8))
-        self.st = st
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        # Decode lanes.  A decode step is half HBM-bound (cross-attention streams every caption's K/V: 0.83 of the HBM
+        # peak) and half latency-bound (73 small GEMMs, LayerNorms, top-k: a few dozen CTAs each).  Captions are independent,
+        # so the batch is cut into `lanes` groups with their own search state, step graph and stream: one lane's small
+        # kernels run under another lane's K/V streaming.  A lane is a set of row-slice VIEWS of the buffers above.
+        if lanes is None:
+            lanes = int(os.environ.get("VACNIC_DECODE_LANES", DECODE_LANES_DEFAULT))
+        if not use_graph or captions % max(1, lanes) != 0 or captions // max(1, lanes) < 16:
+            lanes = 1
+        self.n_lanes = lanes
+        self.lanes = []
+        cl = captions // lanes
+        for i in range(lanes):
+            self.lanes.append(_Lane(self, i * cl, (i + 1) * cl, dev, multi=lanes > 1))
         self.launches_per_step = 0
         self.steps_run = 0
         self.sequences_scores = self.sequences_len = None   # beam search only; set by decode()
 
+    # single-lane views kept for the kernel tests / profiling tools that drive the engine step by step
+    @property
+    def st(self):
+        return self.lanes[0].st
+
+    @property
+    def graph(self):
+        return self.lanes[0].graph
+
     # ------------------------------------------------------------------ encoder side
     def _reset_state(self):
-        cfg, st = self.cfg, self.st
-        st["cur_len"].fill_(1)
-        st["flags"].zero_()
-        if self.nb > 1:
-            st["run_seq"].fill_(cfg.pad_token_id)
-            st["run_seq"][:, :, :, 0] = cfg.decoder_start_token_id
-            st["fin_seq"].copy_(st["run_seq"])
-            st["run_anc"].zero_()
-            st["run_score"].fill_(-1.0e9)
-            st["run_score"][:, :, 0] = 0.0
-            st["fin_score"].fill_(-1.0e9)
-            st["fin_len"].zero_()
-            st["fin_flag"].zero_()
-            st["unsat"].fill_(1)
-        else:
-            st["seq"].fill_(cfg.pad_token_id)
-            st["seq"][:, 0] = cfg.decoder_start_token_id
-            st["unfinished"].fill_(1)
+        cfg = self.cfg
+        for lane in self.lanes:
+            st = lane.st
+            st["cur_len"].fill_(1)
+            st["flags"].zero_()
+            if self.nb > 1:
+                st["run_seq"].fill_(cfg.pad_token_id)
+                st["run_seq"][:, :, :, 0] = cfg.decoder_start_token_id
+                st["fin_seq"].copy_(st["run_seq"])
+                st["run_anc"].zero_()
+                st["run_score"].fill_(-1.0e9)
+                st["run_score"][:, :, 0] = 0.0
+                st["fin_score"].fill_(-1.0e9)
+                st["fin_len"].zero_()
+                st["fin_flag"].zero_()
+                st["unsat"].fill_(1)
+            else:
+                st["seq"].fill_(cfg.pad_token_id)
+                st["seq"][:, 0] = cfg.decoder_start_token_id
+                st["unfinished"].fill_(1)
 
     @torch.no_grad()
     def encode(self, enc_inputs: dict):
@@ -163,41 +213,46 @@ class Generator:
         return ArticlePack({"ids": pid, "pos": pos, "start": start, "len": ln, "qlen": qlen}, C, L, prefix, 1)
 
     # ------------------------------------------------------------------ one decoding step (capturable)
-    def _step(self):
-        model, cfg, st = self.model, self.cfg, self.st
+    def _step(self, lane=None):
+        """One decoding step of `lane` (default: every lane in turn) on the current stream."""
+        if lane is None:
+            for ln in self.lanes:
+                self._step(ln)
+            return
+        model, cfg, st = self.model, self.cfg, lane.st
         dec = model.model.decoder
         store = model.store
         d, H, V = cfg.d_model, cfg.heads, cfg.vocab
         beam = self.nb > 1
-        x, x2 = self.x, self.x2
-        r32, r32b = (self.x32, self.x32b) if model.rt.res_fp32 else (None, None)
+        x, x2 = lane.x, lane.x2
+        r32, r32b = (lane.x32, lane.x32b) if model.rt.res_fp32 else (None, None)
         K.decode_embed_ln(st["run_seq"] if beam else st["seq"], st["cur_len"], store.w16(dec.embed_tokens.weight),
                           store.w16(dec.embed_positions.weight), dec.ln_emb.g, dec.ln_emb.b, x, self.maxT, pos_offset=2,
                           pingpong=beam, y32=r32)
         anc = st["run_anc"] if beam else None
         for l, layer in enumerate(dec.layers):
             a = layer.self_attn
-            K.gemm(x, a.lin_qkv.w16, out=self.qkv, bias=a.lin_qkv.b32)
-            K.decode_self_attn(self.qkv, self.kc[l], self.vc[l], anc, st["cur_len"], self.attn, H, self.maxT)
-            K.gemm(self.attn, a.lin_o.w16, out=self.proj, bias=a.lin_o.b32)
-            K.add_layernorm_fwd(self.proj, x, a.ln.g, a.ln.b, out=x2, want_stats=False, res32=r32, y32_out=r32b)
+            K.gemm(x, a.lin_qkv.w16, out=lane.qkv, bias=a.lin_qkv.b32)
+            K.decode_self_attn(lane.qkv, lane.kc[l], lane.vc[l], anc, st["cur_len"], lane.attn, H, self.maxT)
+            K.gemm(lane.attn, a.lin_o.w16, out=lane.proj, bias=a.lin_o.b32)
+            K.add_layernorm_fwd(lane.proj, x, a.ln.g, a.ln.b, out=x2, want_stats=False, res32=r32, y32_out=r32b)
             a = layer.encoder_attn
-            K.gemm(x2, a.lin_q.w16, out=self.qb, bias=a.lin_q.b32)
-            K.decode_cross_attn(self.qb, self.cross_kv[l, :, 0], self.cross_kv[l, :, 1], self.key_mask, self.key_len, self.attn,
+            K.gemm(x2, a.lin_q.w16, out=lane.qb, bias=a.lin_q.b32)
+            K.decode_cross_attn(lane.qb, lane.cross_kv[l][:, 0], lane.cross_kv[l][:, 1], lane.key_mask, lane.key_len, lane.attn,
                                 self.nb)
-            K.gemm(self.attn, a.lin_o.w16, out=self.proj, bias=a.lin_o.b32)
-            K.add_layernorm_fwd(self.proj, x2, a.ln.g, a.ln.b, out=x, want_stats=False, res32=r32b, y32_out=r32)
-            K.gemm(x, layer.lin_fc1.w16, out=self.h, bias=layer.lin_fc1.b32, act=K.ACT_GELU)
-            K.gemm(self.h, layer.lin_fc2.w16, out=self.proj, bias=layer.lin_fc2.b32)
-            K.add_layernorm_fwd(self.proj, x, layer.ln_final.g, layer.ln_final.b, out=x2, want_stats=False, res32=r32, y32_out=r32b)
+            K.gemm(lane.attn, a.lin_o.w16, out=lane.proj, bias=a.lin_o.b32)
+            K.add_layernorm_fwd(lane.proj, x2, a.ln.g, a.ln.b, out=x, want_stats=False, res32=r32b, y32_out=r32)
+            K.gemm(x, layer.lin_fc1.w16, out=lane.h, bias=layer.lin_fc1.b32, act=K.ACT_GELU)
+            K.gemm(lane.h, layer.lin_fc2.w16, out=lane.proj, bias=layer.lin_fc2.b32)
+            K.add_layernorm_fwd(lane.proj, x, layer.ln_final.g, layer.ln_final.b, out=x2, want_stats=False, res32=r32, y32_out=r32b)
             x, x2 = x2, x
             r32, r32b = r32b, r32
-        K.gemm(x, model.lin_lm.w16, out=self.logits[:, :V], bias=model.final_logits_bias.view(-1))
-        K.decode_topk(self.logits, V, self.Kc, self.top_lp, self.top_idx)
+        K.gemm(x, model.lin_lm.w16, out=lane.logits[:, :V], bias=model.final_logits_bias.view(-1))
+        K.decode_topk(lane.logits, V, self.Kc, lane.top_lp, lane.top_idx)
         if beam:
-            K.beam_step(self.top_lp, self.top_idx, st, self.C, self.nb, self.maxT, self.max_len, cfg.eos_token_id, V, self.lp)
+            K.beam_step(lane.top_lp, lane.top_idx, st, lane.C, self.nb, self.maxT, self.max_len, cfg.eos_token_id, V, self.lp)
         else:
-            K.greedy_step(self.top_idx, st["seq"], st["unfinished"], st["flags"], st["cur_len"], self.R, self.maxT,
+            K.greedy_step(lane.top_idx, st["seq"], st["unfinished"], st["flags"], st["cur_len"], lane.R, self.maxT,
                           self.max_len, cfg.eos_token_id, cfg.pad_token_id)
         K.advance_len(st["cur_len"])
 
@@ -210,17 +265,19 @@ class Generator:
             self._step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        c0 = K._l.launch_count()
-        with torch.cuda.graph(self.graph):
-            self._step()
-        self.launches_per_step = K._l.launch_count() - c0
+        for lane in self.lanes:  # one graph per lane: lanes are replayed on their own streams and drift freely
+            lane.graph = torch.cuda.CUDAGraph()
+            c0 = K._l.launch_count()
+            with torch.cuda.graph(lane.graph):
+                self._step(lane)
+            self.launches_per_step = K._l.launch_count() - c0
+        torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ search loop
     @torch.no_grad()
     def decode(self) -> torch.Tensor:
         """Run the search on the encoded captions; returns int64 ids like transformers' generate()."""
-        if self.use_graph and self.graph is None:
+        if self.use_graph and self.lanes[0].graph is None:
             self._reset_state()
             self._capture()
         self._reset_state()
@@ -228,47 +285,75 @@ class Generator:
         # chunk (copied into pinned memory behind that chunk) while the GPU is already working on the current one, so the
         # device never idles on the stop test.  At most one extra chunk runs after every caption has finished; finished
         # hypotheses are frozen by the step kernels (`unsat` / `unfinished`), so the result does not depend on it.
-        t, stop_t, pending = 1, None, None
+        # With several lanes every lane has its own stream, flags and stop test; a lane that has stopped is not replayed
+        # again, the loop ends when all have.
+        cur = torch.cuda.current_stream()
+        multi = self.n_lanes > 1
+        for lane in self.lanes:
+            lane.t, lane.stop_t, lane.pending, lane.done = 1, None, None, False
+            if multi:
+                lane.stream.wait_stream(cur)  # the encoder side (and the state reset above) ran on the caller's stream
 
-        def check(p):
+        def check(lane, p):
             ev, t0, n = p
             ev.synchronize()  # device -> host read: the stop test of the search loop
-            fl = self.flags_host[t0:t0 + n]
+            fl = lane.flags_host[t0:t0 + n]
             go = (fl[:, 0] != 0) & (fl[:, 1] != 0)
             return None if bool(go.all()) else t0 + int((~go).nonzero()[0])
 
-        while t < self.max_len:
-            n = min(self.poll_every, self.max_len - t)
+        while not all(lane.done for lane in self.lanes):
+            live = [lane for lane in self.lanes if not lane.done]
+            n = min(self.poll_every, self.max_len - live[0].t)  # live lanes are in step: they all started at t = 1
             for _ in range(n):
-                if self.use_graph:
-                    self.graph.replay()
-                else:
-                    c0 = K._l.launch_count()
-                    self._step()
-                    self.launches_per_step = K._l.launch_count() - c0
-            self.flags_host[t:t + n].copy_(self.st["flags"][t:t + n], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            if pending is not None:
-                stop_t = check(pending)
-            pending = (ev, t, n)
-            t += n
-            if stop_t is not None:
-                break
-        if stop_t is None and pending is not None:
-            stop_t = check(pending)
-        self.steps_run = t - 1
-        if stop_t is None:
-            stop_t = self.max_len - 1
-        st = self.st
+                for lane in live:
+                    if self.use_graph:
+                        if multi:
+                            with torch.cuda.stream(lane.stream):
+                                lane.graph.replay()
+                        else:
+                            lane.graph.replay()
+                    else:
+                        c0 = K._l.launch_count()
+                        self._step(lane)
+                        self.launches_per_step = K._l.launch_count() - c0
+            for lane in live:
+                with torch.cuda.stream(lane.stream if multi else cur):
+                    lane.flags_host[lane.t:lane.t + n].copy_(lane.st["flags"][lane.t:lane.t + n], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                if lane.pending is not None:
+                    lane.stop_t = check(lane, lane.pending)
+                lane.pending = (ev, lane.t, n)
+                lane.t += n
+                if lane.stop_t is not None or lane.t >= self.max_len:
+                    lane.done = True
+        for lane in self.lanes:
+            if lane.stop_t is None and lane.pending is not None:
+                lane.stop_t = check(lane, lane.pending)
+            if lane.stop_t is None:
+                lane.stop_t = self.max_len - 1
+            if multi:
+                cur.wait_stream(lane.stream)
+        self.steps_run = max(lane.t for lane in self.lanes) - 1
+        pad = self.cfg.pad_token_id
+        outs = []
         if self.nb > 1:
-            ob = t & 1  # buffer written by the last executed step
-            gen_len = int(st["fin_len"][ob, :, 0].max().item())
-            # transformers' `sequences_scores`: sum of token log-probs / generated_len ** length_penalty, best hypothesis
-            self.sequences_scores = st["fin_score"][ob, :, 0].clone()
-            self.sequences_len = st["fin_len"][ob, :, 0].clone()
-            return st["fin_seq"][ob, :, 0, :1 + gen_len].to(torch.int64)
-        return st["seq"][:, :stop_t + 1].to(torch.int64)
+            scores, lens = [], []
+            for lane in self.lanes:
+                st = lane.st
+                ob = lane.t & 1  # buffer written by the last executed step
+                gen_len = int(st["fin_len"][ob, :, 0].max().item())
+                # transformers' `sequences_scores`: sum of token log-probs / generated_len ** length_penalty, best hypothesis
+                scores.append(st["fin_score"][ob, :, 0].clone())
+                lens.append(st["fin_len"][ob, :, 0].clone())
+                outs.append(st["fin_seq"][ob, :, 0, :1 + gen_len].to(torch.int64))
+            self.sequences_scores, self.sequences_len = torch.cat(scores), torch.cat(lens)
+        else:
+            outs = [lane.st["seq"][:, :lane.stop_t + 1].to(torch.int64) for lane in self.lanes]
+        if len(outs) == 1:
+            return outs[0]
+        width = max(o.shape[1] for o in outs)  # hypotheses are padded after their EOS, exactly as within one lane
+        return torch.cat([torch.nn.functional.pad(o, (0, width - o.shape[1]), value=pad) for o in outs], dim=0)
 
     def generate(self, enc_inputs: dict) -> torch.Tensor:
         self.encode(enc_inputs)
