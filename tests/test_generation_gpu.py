@@ -105,7 +105,11 @@ def test_fullsize_generate_ids_match_reference_generate(cuda_device, use_graph):
     """BASELINE.json configs[2] at full size -- BART-large VACNIC (12 + 12 layers), a ragged L = 1024 batch, greedy and
     beam 4 / length_penalty 2.0 / max_length 50: the token ids equal, EXACTLY, the ids the unmodified reference class
     produced through transformers' real `generate()` on the same weights (tests/golden/make_golden_fullsize.py, margin-
-    vetted against logit noise of the size of the bf16 error at this depth)."""
+    vetted against logit noise of the size of the bf16 error at this depth).  What this fixture can and cannot see: a
+    random-init model this deep decodes from a handful of tokens (three levelled leaders, see the generator script), and
+    margin vetting keeps the cases whose decisions are clear -- the ids here switch token at two positions of the ragged
+    row only.  It pins the full-size plumbing (12 + 12 layers, L = 1024 with padding, 49 cached steps, beam bookkeeping)
+    against the real `generate()`; the sensitive full-size check is the score-level test below."""
     from vacnic_b200 import generation
     fx, cfg, m, batch = _build(FULLSIZE, cuda_device)
     assert cfg.enc_layers == 12 and cfg.dec_layers == 12 and batch["article_ids"].shape[1] == 1024 and fx["max_length"] == 50

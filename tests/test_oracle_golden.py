@@ -83,3 +83,26 @@ def test_oracle_generation_matches_reference_generate(path):
     assert g.shape == fx["greedy_ids"].shape and bool((g == fx["greedy_ids"]).all())
     b, _ = OG.beam_search(sd, cfg.as_dict(), inp, num_beams=4, max_length=fx["max_length"], length_penalty=2.0)
     assert b.shape == fx["beam4_ids"].shape and bool((b == fx["beam4_ids"]).all())
+
+
+def test_oracle_generation_matches_reference_generate_at_full_size():
+    """BART-large (12 + 12 layers), ragged L = 1024 batch, max_length 50: the oracle decodes the ids the unmodified
+    reference class produced through transformers' real `generate()` (tests/golden/make_golden_fullsize.py)."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "fullsize", "large_full_gen.pt")
+    fx = torch.load(path, weights_only=False)
+    cfg = spec.VacnicConfig(**fx["cfg"])
+    sd = spec.test_state_dict(cfg, fx["weight_seed"], lm_scale=fx["lm_scale"])
+    sd["final_logits_bias"][0, cfg.eos_token_id] = fx["eos_bias"]
+    sd["final_logits_bias"][0, fx["logit_bias_idx"]] = fx["logit_bias_val"]
+    batch = synthetic.make_batch(**fx["batch_kwargs"])
+    chk = float(sum(v.double().sum() for k, v in sd.items() if k not in spec.TIED_TO_SHARED))
+    assert abs(chk - fx["weight_checksum"]) <= 1e-6 * abs(fx["weight_checksum"])   # the seeded weights reproduce
+    assert abs(float(sum(v.double().sum() for v in batch.values())) - fx["batch_checksum"]) <= 1e-6 * abs(fx["batch_checksum"])
+    inp = enc_inputs(cfg, batch)
+    with torch.no_grad():
+        enc = OM.encoder_forward(sd, cfg.as_dict(), **inp)
+    g = OG.greedy(sd, cfg.as_dict(), inp, max_length=fx["max_length"], enc=enc)
+    assert g.shape == fx["greedy_ids"].shape and bool((g == fx["greedy_ids"]).all())
+    b, _ = OG.beam_search(sd, cfg.as_dict(), inp, num_beams=fx["num_beams"], max_length=fx["max_length"],
+                          length_penalty=fx["length_penalty"], enc=enc)
+    assert b.shape == fx["beam4_ids"].shape and bool((b == fx["beam4_ids"]).all())

@@ -1,4 +1,5 @@
-"""2+ GPU check of the overlapped, bucketed gradient all-reduce (run under torchrun):
+"""2+ GPU check of the overlapped, bucketed gradient all-reduce -- exchange="nccl", the fallback path; the default
+rank-sharded peer-memory exchange is checked by tools/dp_p2p_check.py -- (run under torchrun):
 the flat gradient after TrainStep's exchange must equal the sum over ranks of the local gradients, and the
 losses / parameters after a graph-captured step must agree across ranks."""
 import os
@@ -31,7 +32,7 @@ if not SKIP_EAGER:
     want = local_grad.clone()
     dist.all_reduce(want)
     # 2. the data-parallel step (eager), lr = 0 so the weights do not move
-    ts = TrainStep(model, guide, use_graph=False, process_group=dist.group.WORLD, lr=0.0)
+    ts = TrainStep(model, guide, use_graph=False, process_group=dist.group.WORLD, lr=0.0, exchange="nccl")
     ts.step(batch, prepared=True)
     torch.cuda.synchronize()
     got = model.store.grad
@@ -48,7 +49,7 @@ if not SKIP_EAGER:
 if not SKIP_EAGER:
     dist.destroy_process_group()
     sys.exit(0)
-tg = TrainStep(model, guide, use_graph=True, process_group=dist.group.WORLD, lr=1e-4)
+tg = TrainStep(model, guide, use_graph=True, process_group=dist.group.WORLD, lr=1e-4, exchange="nccl")
 for i in range(3):
     losses = tg.step(batch, prepared=True)
 torch.cuda.synchronize()
