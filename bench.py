@@ -581,7 +581,8 @@ def train_roofline(model, guide, ts, devb, pk, step_tflops, ms_step, small, step
     launching stream), Sum 2MNK over the launches routed to the CTA-pair kernel / Sum of their durations."""
     from vacnic_b200 import kernels as K
     from vacnic_b200.trainer import TrainStep
-    eager = TrainStep(model, guide, use_graph=False, process_group=None, varlen=ts.varlen)
+    # single stream: the per-launch CUDA events must bracket one kernel, not one kernel plus whatever a second stream ran
+    eager = TrainStep(model, guide, use_graph=False, process_group=None, varlen=ts.varlen, side_stream=False, guide_stream=False)
     eager.m, eager.v = ts.m, ts.v
     eager.step_dev.copy_(ts.step_dev)
     try:
