@@ -58,4 +58,9 @@ allc = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(allc, chk)
 assert all(torch.equal(allc[0], c) for c in allc), allc
 print(f"rank {rank}: graph DP steps ok, txt loss {float(losses['txt']):.4f}, master checksum {float(chk):.6f}", flush=True)
-dist.destroy_process_group()
+# the captured step graph holds NCCL nodes: tearing the communicator down under it was seen to hang at exit (2 x B200,
+# after both ranks had printed the line above) -- drop the graph first and leave without the collective teardown
+tg.close()
+torch.cuda.synchronize()
+sys.stdout.flush()
+os._exit(0)
