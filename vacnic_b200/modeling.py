@@ -313,8 +313,7 @@ class BartEncoder(nn.Module):
                 # tensors that cross the two streams stay referenced until the step is over (rt.keepalive is cleared by the
                 # owner of the step after the streams have joined): the caching allocator recycles a block on the stream
                 # that allocated it as soon as the last reference dies, which the OTHER stream's pending kernels cannot see
-                rt.keepalive += [t for kv, _ in kvs for t in (kv,)] + [t for pair in (img, face, ner) if pair for t in pair
-                                                                       if t is not None]
+                rt.keepalive += [kv for kv, _ in kvs] + [t for pair in (img, face, ner) if pair for t in pair if t is not None]
                 if fn_mask is not None:
                     rt.keepalive += [fn_mask.mask, fn_mask.len]
         states = []
