@@ -113,3 +113,14 @@ def test_bench_refuses_a_gpus_flag_that_disagrees_with_the_launch():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "2"], env=env, capture_output=True, text=True,
                          timeout=300)
     assert out.returncode != 0 and "WORLD_SIZE" in (out.stderr + out.stdout)
+
+
+def test_profiles_index_names_existing_files():
+    """profiles/README.md is the index the evidence is read through: every file it names exists."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(__file__)), "profiles")
+    text = open(os.path.join(root, "README.md")).read()
+    names = set(re.findall(r"`((?:r1|r2)_[A-Za-z0-9_.]+\.(?:json|md|txt|log|csv))`", text))
+    assert len(names) >= 25
+    missing = [n for n in sorted(names) if not os.path.exists(os.path.join(root, n))]
+    assert not missing, missing

@@ -106,3 +106,18 @@ def test_oracle_generation_matches_reference_generate_at_full_size():
     b, _ = OG.beam_search(sd, cfg.as_dict(), inp, num_beams=fx["num_beams"], max_length=fx["max_length"],
                           length_penalty=fx["length_penalty"], enc=enc)
     assert b.shape == fx["beam4_ids"].shape and bool((b == fx["beam4_ids"]).all())
+
+
+def test_fullsize_fixture_is_reproduced_by_its_generator():
+    """The committed generator script rebuilds the levelled `final_logits_bias` entries stored in the full-size fixture
+    (same tokens; values to fp32 re-execution accuracy) from the seeds alone."""
+    import importlib.util
+    here = os.path.dirname(__file__)
+    spec_ = importlib.util.spec_from_file_location("make_golden_fullsize", os.path.join(here, "golden", "make_golden_fullsize.py"))
+    mod = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mod)
+    fx = torch.load(os.path.join(here, "golden", "fullsize", "large_full_gen.pt"), weights_only=False)
+    assert (fx["weight_seed"], fx["lm_scale"], fx["max_length"], fx["num_beams"]) == (mod.WEIGHT_SEED, mod.LM_SCALE, mod.MAX_LEN, mod.NB)
+    _, idx, val = mod.weights(spec.bart_large())
+    assert idx.tolist() == fx["logit_bias_idx"].tolist()
+    assert torch.allclose(val, fx["logit_bias_val"], rtol=0, atol=2e-3)
