@@ -167,4 +167,4 @@ def test_side_streams_give_the_single_stream_step(cuda_device, use_graph, varlen
             err = (g0[i] - g1[i]).abs().max().item()
             assert err <= max(4 * noise, 1e-4 * scale), (i, err, noise, scale)
             assert torch.nn.functional.cosine_similarity(g0[i], g1[i], dim=0).item() >= 0.99999
-        assert (p0 - p1).abs().mean().item() <= 1e-6
+        assert (p0 - p1).abs().mean().item() <= 3e-6   # three steps of lr 2e-5 move a weight by up to 6e-5
